@@ -1,0 +1,161 @@
+/*
+ * prs.h -- C ABI of libprs.so, the B200-native retrieval engine that drops in under the
+ * retriever of alirezafarzipour/persian-rag-system (reference paths below are relative to
+ * that repository).
+ *
+ * The reference is pure Python; its hot path bottoms out in three third-party calls.  Each
+ * entry point here is what a binding (ctypes / cffi / pybind) for that path would bind; the
+ * call it replaces is cited next to it.  Plain pointers and sizes only -- no torch types.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative PRS_E* code; prs_last_error() gives the
+ *     thread-local message of the last failure on the calling thread;
+ *   - "host" pointers are ordinary (pageable or pinned) host memory, "device" pointers are CUDA
+ *     device pointers on the index's device; `stream` is a cudaStream_t passed as void* (NULL =
+ *     the legacy default stream);
+ *   - the library owns the device copies it makes; the caller owns every buffer it passes in;
+ *   - search is re-entrant for concurrent readers (per-call workspace under an internal lock);
+ *     add/write must not run concurrently with search (same contract as faiss);
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails with
+ *     PRS_ECUDA.
+ */
+#ifndef PRS_H
+#define PRS_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* error codes */
+#define PRS_OK        0
+#define PRS_EINVAL   -1   /* bad argument (dimension mismatch, k out of range, null pointer) */
+#define PRS_ECUDA    -2   /* CUDA runtime / driver failure, or no device */
+#define PRS_EIO      -3   /* file could not be read / written / parsed */
+#define PRS_ENOMEM   -4   /* host or device allocation failed */
+#define PRS_EUNSUP   -5   /* valid request this build does not implement */
+
+/* metric: numeric values are faiss MetricType (index file field `metric_type`) */
+#define PRS_METRIC_IP 0   /* faiss.METRIC_INNER_PRODUCT, fourcc IxFI */
+#define PRS_METRIC_L2 1   /* faiss.METRIC_L2, fourcc IxF2 -- what the reference uses */
+
+/* element types (corpus storage and tensor hand-off) */
+#define PRS_F32  0
+#define PRS_F16  1
+#define PRS_BF16 2
+#define PRS_F64  3        /* sparse weights only */
+
+#define PRS_MAX_K 1024
+
+typedef struct prs_index  prs_index;    /* flat dense index  (faiss.IndexFlatL2 / IndexFlatIP) */
+typedef struct prs_sparse prs_sparse;   /* inverted sparse index (rank_bm25.BM25Okapi / TF-IDF matrix) */
+
+const char* prs_last_error(void);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+int64_t prs_launch_count(void);
+/* compute capability * 10 of `device` (100 for B200), or a negative error */
+int prs_device_arch(int device);
+
+/* ---------------------------------------------------------------------------------------
+ * Flat dense index.
+ * replaces: faiss.IndexFlatL2(dimension)            src/create_embeddings.py:130
+ *           faiss.IndexFlatL2(dimension)            scripts/phase3_pdf_chunking.py:47
+ * `storage` selects how rows are kept in HBM: PRS_F32 (exact-parity mode, what the reference
+ * stores), PRS_F16 / PRS_BF16 (throughput mode, fp32 accumulate).
+ * ------------------------------------------------------------------------------------- */
+int prs_index_create(int d, int metric, int storage, int device, prs_index** out);
+void prs_index_free(prs_index* idx);
+/* pre-size the device buffers for `n_total` rows (avoids regrowth copies for large shards) */
+int prs_index_reserve(prs_index* idx, int64_t n_total);
+
+/* replaces: index.add(embeddings)                   src/create_embeddings.py:133
+ *           index.add(batch)                        scripts/phase3_pdf_chunking.py:64 */
+int prs_index_add_host(prs_index* idx, const float* x, int64_t n);
+/* same, rows already on the device (dtype PRS_F32/F16/BF16, row-major [n, d], contiguous) */
+int prs_index_add_device(prs_index* idx, const void* x, int dtype, int64_t n, void* stream);
+
+int64_t prs_index_ntotal(const prs_index* idx);      /* index.ntotal   src/retrieval.py:56 */
+int     prs_index_d(const prs_index* idx);           /* index.d        src/create_embeddings.py:286 */
+int     prs_index_metric(const prs_index* idx);
+int     prs_index_storage(const prs_index* idx);
+
+/* replaces: faiss_index.search(query_embedding, top_k)   src/retrieval.py:102
+ *           index.search(test_vector, 1)                 src/create_embeddings.py:291
+ * q: [nq, d] float32 row-major.  D: [nq, k] float32 (squared L2 ascending, or inner product
+ * descending).  I: [nq, k] int64 row ids, -1 (and +/-FLT_MAX in D) where fewer than k rows exist.
+ * Ties are ordered (value, id ascending). */
+int prs_index_search_host(prs_index* idx, const float* q, int64_t nq, int k, float* D, int64_t* I);
+/* same with q, D, I on the device; qdtype PRS_F32/F16/BF16.  Asynchronous on `stream`. */
+int prs_index_search_device(prs_index* idx, const void* q, int qdtype, int64_t nq, int k,
+                            float* D, int64_t* I, void* stream);
+/* id_offset is added to every returned row id (row-sharded corpora: global id = local + offset) */
+int prs_index_set_id_offset(prs_index* idx, int64_t id_offset);
+/* force a kernel family: 0 = automatic, 1 = CUDA-core scan, 2 = tcgen05 scan (tests/bench) */
+int prs_index_set_path(prs_index* idx, int path);
+/* which family the last search on this index used (1 or 2), and its main kernel's name */
+int prs_index_last_path(const prs_index* idx);
+
+/* copy rows [i0, i0+n) back as float32 (index.reconstruct_n) */
+int prs_index_reconstruct_host(prs_index* idx, int64_t i0, int64_t n, float* out);
+
+/* replaces: faiss.write_index(index, index_file)    src/create_embeddings.py:136
+ *           faiss.read_index(faiss_index_file)      src/retrieval.py:55, src/create_embeddings.py:284
+ * fp32 storage reads/writes faiss's byte-exact IndexFlat file (fourcc IxF2 / IxFI).  fp16/bf16
+ * storage writes a tagged container (fourcc PRSh / PRSb: the same 45-byte header followed by the
+ * 16-bit rows) that only this library reads.  prs_index_read converts to `storage` on load. */
+int prs_index_write(prs_index* idx, const char* path);
+int prs_index_read(const char* path, int storage, int device, prs_index** out);
+
+/* ---------------------------------------------------------------------------------------
+ * Row-sharded search: merge step.  Each of `nparts` shards contributes its local
+ * top-k for the same nq queries, concatenated as D_parts/I_parts [nparts, nq, k] on the device
+ * (what ncclAllGather of the per-rank results produces, in rank order; shards hold ascending
+ * contiguous row blocks).  Writes the global top-k.  largest: 1 for IP / sparse scores, 0 for L2.
+ * tie_high_id: 0 -> ties by id ascending (dense), 1 -> id descending (sparse path).
+ * ------------------------------------------------------------------------------------- */
+int prs_merge_topk_device(const float* D_parts, const int64_t* I_parts, int nparts, int64_t nq, int k,
+                          int largest, int tie_high_id, float* D, int64_t* I, int device, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Sparse scoring (BM25 / TF-IDF) over an inverted index.
+ * replaces: BM25Okapi(tokenized_chunks)             src/retrieval.py:67   (build)
+ *           bm25_index.get_scores(query_tokens)     src/retrieval.py:127  + np.argsort(...)[::-1][:k] :130
+ *           cosine_similarity(query_vector, matrix) src/retrieval.py:156  + np.argsort(...)[::-1][:k] :159
+ * The caller supplies the doc-by-term matrix in CSR (indptr [n_docs+1] int64, indices [nnz]
+ * int32 term ids, values [nnz] of `vdtype` PRS_F32 or PRS_F64): BM25 per-posting weights
+ * idf(t)*tf*(k1+1)/(tf+k1*(1-b+b*dl/avgdl)), or l2-normalised tf-idf.  The library transposes it
+ * into term-major postings on the device.
+ * ------------------------------------------------------------------------------------- */
+int prs_sparse_build(const int64_t* indptr, const int32_t* indices, const void* values, int vdtype,
+                     int64_t n_docs, int32_t n_terms, int device, prs_sparse** out);
+void prs_sparse_free(prs_sparse* sp);
+int64_t prs_sparse_ndocs(const prs_sparse* sp);
+int64_t prs_sparse_nnz(const prs_sparse* sp);
+/* queries in CSR: q_indptr [nq+1] int64, q_terms [.] int32 term ids (repeats allowed, order kept,
+ * ids outside [0, n_terms) are ignored like unknown words), q_weights [.] float64 (1.0 for BM25).
+ * score(doc) = sum over the query's entries IN ORDER of q_weight * posting weight, accumulated in
+ * float64.  Returns the k best docs per query ordered (score desc, id DESC) -- the order of
+ * np.argsort(scores, kind="stable")[::-1] -- including zero-score docs, as the reference does.
+ * S: [nq, k] float64 scores, I: [nq, k] int64 doc ids (-1 padded).  Host pointers. */
+int prs_sparse_search_host(prs_sparse* sp, const int64_t* q_indptr, const int32_t* q_terms,
+                           const double* q_weights, int64_t nq, int k, double* S, int64_t* I);
+/* sum of postings touched by the last search (8 or 12 bytes each): the algorithmic bytes */
+int64_t prs_sparse_last_postings(const prs_sparse* sp);
+int prs_sparse_set_id_offset(prs_sparse* sp, int64_t id_offset);
+
+/* ---------------------------------------------------------------------------------------
+ * Encoder output epilogue: attention-masked mean pooling (+ optional L2 normalisation).
+ * replaces the tail of SentenceTransformer.encode  src/retrieval.py:98, src/create_embeddings.py:97-101
+ *   out[b,:] = sum_t hidden[b,t,:]*mask[b,t] / max(sum_t mask[b,t], 1e-9);  if normalize:
+ *   out[b,:] /= max(||out[b,:]||_2, 1e-12)
+ * hidden: [B,T,H] device, dtype PRS_F32/F16/BF16; mask: [B,T] device int64 (0/1); out: [B,H]
+ * device float32.  Asynchronous on `stream`.
+ * ------------------------------------------------------------------------------------- */
+int prs_pool_norm(const void* hidden, int dtype, const int64_t* mask, int B, int T, int H,
+                  int normalize, float* out, int device, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PRS_H */

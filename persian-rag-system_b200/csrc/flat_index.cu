@@ -1,0 +1,619 @@
+// flat_index.cu -- host side of the flat dense index behind the C ABI in include/prs.h.
+//
+// Mirrors the faiss objects the reference touches (IndexFlatL2 at src/create_embeddings.py:130,
+// add :133, write_index :136, read_index src/retrieval.py:55, search src/retrieval.py:102) and
+// dispatches to the sm_100a kernels in flat_simt.cuh / flat_umma.cuh.  No CPU compute path.
+#include <mutex>
+#include <new>
+#include <vector>
+
+#include <algorithm>
+#include <cerrno>
+
+#include "flat_simt_launch.h"
+#include "flat_umma.cuh"
+#include "host_common.h"
+#include "topk_merge.cuh"
+
+namespace prs {
+
+thread_local std::string t_error;
+std::atomic<long long> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    t_error = buf;
+}
+
+static inline int elem_size(int dt) { return dt == PRS_F32 ? 4 : (dt == PRS_F64 ? 8 : 2); }
+
+// ------------------------------------------------------------------------------------------
+// small utility kernels
+// ------------------------------------------------------------------------------------------
+template <typename T> __device__ __forceinline__ float to_f32(T v);
+template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f32<__half>(__half v) { return __half2float(v); }
+template <> __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ __half from_f32<__half>(float v) { return __float2half_rn(v); }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+// one warp per row: convert [n, d] -> storage rows [n, pitch] (zero padded) and write the squared
+// norm of the STORED (rounded) row, which is what the expanded L2 form needs.
+template <typename TI, typename TO>
+__global__ void ingest_rows_kernel(const TI* __restrict__ in, long long n, int d, int pitch,
+                                   TO* __restrict__ out, float* __restrict__ norm) {
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= n) return;
+    float acc = 0.f;
+    for (int c = lane; c < pitch; c += 32) {
+        TO o = from_f32<TO>(0.f);
+        if (c < d) o = from_f32<TO>(to_f32<TI>(in[row * d + c]));
+        out[row * pitch + c] = o;
+        const float f = to_f32<TO>(o);
+        acc = fmaf(f, f, acc);
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) norm[row] = acc;
+}
+
+template <typename TI>
+__global__ void to_f32_kernel(const TI* __restrict__ in, long long n, float* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = to_f32<TI>(in[i]);
+}
+
+template <typename TS>
+__global__ void reconstruct_kernel(const TS* __restrict__ x, long long i0, long long n, int d, int pitch,
+                                   float* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * d) return;
+    const long long r = i / d;
+    const int c = (int)(i - r * d);
+    out[i] = to_f32<TS>(x[(i0 + r) * pitch + c]);
+}
+
+__global__ void fill_empty_kernel(float* D, long long* I, long long n, float dv) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { D[i] = dv; I[i] = -1; }
+}
+
+__global__ void qnorm_kernel(const float* __restrict__ q, int d, int stride, float* __restrict__ out) {
+    const int row = blockIdx.x, lane = threadIdx.x;
+    float acc = 0.f;
+    for (int c = lane; c < d; c += 32) { const float v = q[(size_t)row * stride + c]; acc = fmaf(v, v, acc); }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) out[row] = acc;
+}
+
+// ------------------------------------------------------------------------------------------
+// row-sharded merge: [nparts, nq, k] (score, id) lists -> [nq, k]
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(MERGE_THREADS) merge_parts_kernel(
+    const float* __restrict__ Dp, const long long* __restrict__ Ip, int nparts, long long nq, int k, int sortn,
+    int largest, int tie_high, float* __restrict__ D, long long* __restrict__ I) {
+    extern __shared__ __align__(16) unsigned char msm[];
+    u64* buf = reinterpret_cast<u64*>(msm);
+    int* s_n = reinterpret_cast<int*>(msm + (size_t)sortn * 8);
+    const long long q = blockIdx.x;
+    const int tid = threadIdx.x;
+    // position p = part * k + j.  Within a part equal scores are already ordered by the tie
+    // rule and parts hold ascending row blocks, so ordering ties by position reproduces the
+    // global-id tie rule without needing 64-bit ids in the key.
+    auto fetch = [&](long long i) -> u64 {
+        const int part = (int)(i / k), j = (int)(i - (long long)part * k);
+        const size_t o = ((size_t)part * nq + q) * k + j;
+        if (Ip[o] < 0) return 0ull;
+        const float s = sanitize(largest ? Dp[o] : -Dp[o]);
+        const uint32_t lo = tie_high ? (uint32_t)(part * k + (k - 1 - j)) : ~(uint32_t)(part * k + j);
+        return ((u64)f2ord(s) << 32) | lo;
+    };
+    const int n = block_topk_stream(fetch, (long long)nparts * k, k, buf, sortn, s_n, tid, MERGE_THREADS, 1);
+    for (int j = tid; j < k; j += MERGE_THREADS) {
+        if (j < n) {
+            const uint32_t lo = (uint32_t)buf[j];
+            int part, jj;
+            if (tie_high) { part = (int)(lo / k); jj = k - 1 - (int)(lo - (uint32_t)part * k); }
+            else { const uint32_t p = ~lo; part = (int)(p / k); jj = (int)(p - (uint32_t)part * k); }
+            const size_t o = ((size_t)part * nq + q) * k + jj;
+            D[q * k + j] = Dp[o];
+            I[q * k + j] = Ip[o];
+        } else {
+            D[q * k + j] = largest ? -3.402823466e+38f : 3.402823466e+38f;
+            I[q * k + j] = -1;
+        }
+    }
+}
+
+}  // namespace prs
+
+using namespace prs;
+
+// ------------------------------------------------------------------------------------------
+// the index object
+// ------------------------------------------------------------------------------------------
+struct prs_index {
+    int d = 0, pitch = 0, metric = PRS_METRIC_L2, storage = PRS_F32, device = 0, sm_count = 0;
+    long long n = 0, cap_rows = 0;
+    void* x = nullptr;
+    float* xnorm = nullptr;
+    long long id_offset = 0;
+    int path_force = 0, last_path = 0;
+    std::mutex mu, host_mu;
+    cudaEvent_t ws_event = nullptr;
+    cudaStream_t ws_stream = nullptr;
+    bool ws_used = false;
+    DevBuf lists, cand, cand_cnt, qf32, qnorm, qlow, hD, hI, hQ, stage;
+    UmmaState umma;
+};
+
+static int index_grow(prs_index* idx, long long n_total) {
+    if (n_total <= idx->cap_rows) return 0;
+    const size_t es = elem_size(idx->storage);
+    void* nx = nullptr;
+    float* nn = nullptr;
+    const size_t xb = (size_t)n_total * idx->pitch * es;
+    cudaError_t e = cudaMalloc(&nx, xb ? xb : 256);
+    if (e != cudaSuccess) { cudaGetLastError(); set_error("cudaMalloc(%zu bytes) for corpus failed: %s", xb, cudaGetErrorString(e)); return PRS_ENOMEM; }
+    e = cudaMalloc(&nn, (size_t)n_total * 4 + 256);
+    if (e != cudaSuccess) { cudaGetLastError(); cudaFree(nx); set_error("cudaMalloc for norms failed: %s", cudaGetErrorString(e)); return PRS_ENOMEM; }
+    if (idx->n > 0) {
+        PRS_CUDA(cudaMemcpy(nx, idx->x, (size_t)idx->n * idx->pitch * es, cudaMemcpyDeviceToDevice));
+        PRS_CUDA(cudaMemcpy(nn, idx->xnorm, (size_t)idx->n * 4, cudaMemcpyDeviceToDevice));
+    }
+    if (idx->x) cudaFree(idx->x);
+    if (idx->xnorm) cudaFree(idx->xnorm);
+    idx->x = nx; idx->xnorm = nn; idx->cap_rows = n_total;
+    idx->umma.invalidate();
+    return 0;
+}
+
+template <typename TI>
+static int ingest_dispatch(prs_index* idx, const void* x, long long n, cudaStream_t st) {
+    const int wpb = 8;
+    const unsigned grid = (unsigned)((n + wpb - 1) / wpb);
+    const size_t es = elem_size(idx->storage);
+    unsigned char* dst = (unsigned char*)idx->x + (size_t)idx->n * idx->pitch * es;
+    float* nrm = idx->xnorm + idx->n;
+    switch (idx->storage) {
+        case PRS_F32: ingest_rows_kernel<TI, float><<<grid, wpb * 32, 0, st>>>((const TI*)x, n, idx->d, idx->pitch, (float*)dst, nrm); break;
+        case PRS_F16: ingest_rows_kernel<TI, __half><<<grid, wpb * 32, 0, st>>>((const TI*)x, n, idx->d, idx->pitch, (__half*)dst, nrm); break;
+        default: ingest_rows_kernel<TI, __nv_bfloat16><<<grid, wpb * 32, 0, st>>>((const TI*)x, n, idx->d, idx->pitch, (__nv_bfloat16*)dst, nrm); break;
+    }
+    PRS_LAUNCH_CHECK();
+    return 0;
+}
+
+static int add_device_impl(prs_index* idx, const void* x, int dtype, long long n, cudaStream_t st) {
+    if (n == 0) return 0;
+    if (idx->n + n > idx->cap_rows) {
+        // growth copies run on the legacy stream; make sure earlier async work is done
+        PRS_CUDA(cudaStreamSynchronize(st));
+        long long want = idx->n + n;
+        if (idx->cap_rows > 0) { long long g = idx->cap_rows + idx->cap_rows / 2; if (g > want) want = g; }
+        int rc = index_grow(idx, want);
+        if (rc) return rc;
+    }
+    int rc;
+    switch (dtype) {
+        case PRS_F32: rc = ingest_dispatch<float>(idx, x, n, st); break;
+        case PRS_F16: rc = ingest_dispatch<__half>(idx, x, n, st); break;
+        case PRS_BF16: rc = ingest_dispatch<__nv_bfloat16>(idx, x, n, st); break;
+        default: set_error("add: unsupported dtype %d", dtype); return PRS_EINVAL;
+    }
+    if (rc) return rc;
+    idx->n += n;
+    idx->umma.invalidate();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// SIMT path dispatch
+// ------------------------------------------------------------------------------------------
+static int launch_simt(int storage, bool l2, int QB, int R, const SimtParams& p, int grid, size_t smem, cudaStream_t st) {
+    switch (storage) {
+        case PRS_F32: return launch_simt_f32(l2, QB, R, p, grid, smem, st);
+        case PRS_F16: return launch_simt_f16(l2, QB, R, p, grid, smem, st);
+        default: return launch_simt_bf16(l2, QB, R, p, grid, smem, st);
+    }
+}
+
+static int launch_merge(prs_index* idx, int parts, long long nq, int k, int out_mode, const float* qnorm,
+                        float* D, int64_t* I, cudaStream_t st) {
+    const int sortn = next_pow2(k + MERGE_THREADS);
+    const size_t smem = (size_t)sortn * 8 + 16;
+    PRS_CUDA(cudaFuncSetAttribute(merge_cand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    merge_cand_kernel<<<(unsigned)nq, MERGE_THREADS, smem, st>>>((const u64*)idx->cand.p, (const int*)idx->cand_cnt.p, parts,
+                                                                (int)nq, k, sortn, out_mode, qnorm, idx->id_offset, D,
+                                                                (long long*)I);
+    PRS_LAUNCH_CHECK();
+    return 0;
+}
+
+static int search_simt(prs_index* idx, const float* qf, int q_stride, long long nq, int k, float* D, int64_t* I, cudaStream_t st) {
+    const int es = elem_size(idx->storage);
+    const int row_bytes = idx->pitch * es;
+    if ((long long)SIMT_NW * row_bytes > 64 * 1024) {
+        set_error("flat scan: d=%d too large for the shared-memory tile (row of %d bytes)", idx->d, row_bytes);
+        return PRS_EUNSUP;
+    }
+    const int cap = std::max(128, next_pow2(2 * k));
+    const int sortn = next_pow2(k + SIMT_THREADS);
+    const int qb_max = nq >= 8 ? 8 : (nq >= 4 ? 4 : (nq >= 2 ? 2 : 1));
+    int grid = 0;
+    int rc;
+    long long done = 0;
+    // workspace is sized for the widest group; every group uses the same grid
+    int R0 = 4;
+    while (R0 > 1 && (SIMT_NW * R0 * row_bytes > 48 * 1024 || R0 * qb_max > 32)) R0 >>= 1;
+    {
+        const int m = std::max(1, 32768 / (SIMT_NW * R0 * row_bytes));
+        const int tile_rows = SIMT_NW * R0 * m;
+        const long long n_tiles = (idx->n + tile_rows - 1) / tile_rows;
+        grid = (int)std::min<long long>(idx->sm_count, n_tiles);
+    }
+    if ((rc = idx->lists.ensure((size_t)grid * SIMT_NW * qb_max * cap * 8))) return rc;
+    if ((rc = idx->cand.ensure((size_t)grid * nq * k * 8))) return rc;
+    if ((rc = idx->cand_cnt.ensure((size_t)grid * nq * 4))) return rc;
+    while (done < nq) {
+        const long long left = nq - done;
+        const int QB = left >= 8 ? 8 : (left >= 4 ? 4 : (left >= 2 ? 2 : 1));
+        SimtParams p;
+        p.x = idx->x; p.q = qf + (size_t)done * q_stride; p.n_rows = idx->n; p.d = idx->d; p.pitch = idx->pitch;
+        p.q_stride = q_stride; p.nq = QB; p.k = k; p.cap = cap;
+        // R and tile geometry are fixed per search (R0) so that `grid` and the workspace agree
+        const int R = R0;
+        const int m = std::max(1, 32768 / (SIMT_NW * R * row_bytes));
+        p.tile_rows = SIMT_NW * R * m;
+        const size_t qbytes = (((size_t)QB * idx->pitch * 4) + 127) & ~(size_t)127;
+        const size_t tile_bytes = (size_t)p.tile_rows * row_bytes;
+        int stages = (int)((200 * 1024 - 512 - qbytes) / tile_bytes);
+        if (stages > SIMT_MAX_STAGES) stages = SIMT_MAX_STAGES;
+        if (stages < 2 || (size_t)stages * tile_bytes < (size_t)sortn * 8) {
+            set_error("flat scan: cannot fit the pipeline in shared memory (d=%d, k=%d)", idx->d, k);
+            return PRS_EUNSUP;
+        }
+        p.stages = stages;
+        p.lists = (u64*)idx->lists.p; p.cand = (u64*)idx->cand.p; p.cand_cnt = (int*)idx->cand_cnt.p;
+        p.nq_total = (int)nq; p.q0 = (int)done; p.sortn = sortn;
+        const size_t smem = 512 + qbytes + (size_t)stages * tile_bytes;
+        if ((rc = launch_simt(idx->storage, idx->metric == PRS_METRIC_L2, QB, R, p, grid, smem, st))) return rc;
+        done += QB;
+    }
+    return launch_merge(idx, grid, nq, k, idx->metric == PRS_METRIC_L2 ? 1 : 0, nullptr, D, I, st);
+}
+
+static int search_device_impl(prs_index* idx, const void* q, int qdtype, long long nq, int k, float* D, int64_t* I, cudaStream_t st) {
+    if (k < 1 || k > PRS_MAX_K) { set_error("search: k=%d out of range [1, %d]", k, PRS_MAX_K); return PRS_EINVAL; }
+    if (nq < 0) { set_error("search: nq=%lld < 0", nq); return PRS_EINVAL; }
+    if (nq == 0) return 0;
+    if (!q || !D || !I) { set_error("search: null pointer"); return PRS_EINVAL; }
+    if (nq > (1 << 22)) { set_error("search: nq=%lld too large for one call", nq); return PRS_EINVAL; }
+    std::lock_guard<std::mutex> lock(idx->mu);
+    // the scan workspace is shared by all searches on this index: order a search issued on a new
+    // stream after the previous one (same-stream searches are ordered already)
+    if (!idx->ws_event) PRS_CUDA(cudaEventCreateWithFlags(&idx->ws_event, cudaEventDisableTiming));
+    if (idx->ws_used && idx->ws_stream != st) PRS_CUDA(cudaStreamWaitEvent(st, idx->ws_event, 0));
+    struct Rec { prs_index* i; cudaStream_t s; ~Rec() { cudaEventRecord(i->ws_event, s); i->ws_stream = s; i->ws_used = true; } } rec{idx, st};
+    if (idx->n == 0) {
+        const long long tot = nq * k;
+        fill_empty_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(D, (long long*)I, tot,
+                                                                        idx->metric == PRS_METRIC_L2 ? 3.402823466e+38f : -3.402823466e+38f);
+        PRS_LAUNCH_CHECK();
+        return 0;
+    }
+    int rc;
+    const float* qf = (const float*)q;
+    if (qdtype != PRS_F32) {
+        const long long tot = nq * idx->d;
+        if ((rc = idx->qf32.ensure((size_t)tot * 4))) return rc;
+        if (qdtype == PRS_F16) to_f32_kernel<__half><<<(unsigned)((tot + 255) / 256), 256, 0, st>>>((const __half*)q, tot, (float*)idx->qf32.p);
+        else if (qdtype == PRS_BF16) to_f32_kernel<__nv_bfloat16><<<(unsigned)((tot + 255) / 256), 256, 0, st>>>((const __nv_bfloat16*)q, tot, (float*)idx->qf32.p);
+        else { set_error("search: unsupported query dtype %d", qdtype); return PRS_EINVAL; }
+        PRS_LAUNCH_CHECK();
+        qf = (const float*)idx->qf32.p;
+    }
+    int path = idx->path_force;
+    if (path == 0) path = umma_eligible(idx->storage, idx->d, idx->pitch, nq, k) ? 2 : 1;
+    if (path == 2) {
+        if (!umma_eligible(idx->storage, idx->d, idx->pitch, 8, k)) {
+            set_error("tcgen05 path needs fp16/bf16 storage and k <= %d (storage=%d, k=%d)", UMMA_MAX_K, idx->storage, k);
+            return PRS_EUNSUP;
+        }
+        idx->last_path = 2;
+        if ((rc = idx->qnorm.ensure((size_t)nq * 4))) return rc;
+        qnorm_kernel<<<(unsigned)nq, 32, 0, st>>>(qf, idx->d, idx->d, (float*)idx->qnorm.p);
+        PRS_LAUNCH_CHECK();
+        int parts = 0;
+        if ((rc = search_umma(idx->umma, idx->x, idx->xnorm, idx->n, idx->d, idx->pitch, idx->storage, idx->metric, idx->sm_count,
+                              qf, nq, k, idx->cand, idx->cand_cnt, &parts, st))) return rc;
+        return launch_merge(idx, parts, nq, k, idx->metric == PRS_METRIC_L2 ? 2 : 0, (const float*)idx->qnorm.p, D, I, st);
+    }
+    idx->last_path = 1;
+    return search_simt(idx, qf, idx->d, nq, k, D, I, st);
+}
+
+// ------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------
+extern "C" {
+
+const char* prs_last_error(void) { return t_error.c_str(); }
+int64_t prs_launch_count(void) { return (int64_t)g_launches.load(); }
+
+int prs_device_arch(int device) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); set_error("no CUDA device available"); return PRS_ECUDA; }
+    if (device < 0 || device >= ndev) { set_error("device %d out of range (have %d)", device, ndev); return PRS_EINVAL; }
+    cudaDeviceProp prop;
+    PRS_CUDA(cudaGetDeviceProperties(&prop, device));
+    return prop.major * 10 + prop.minor;
+}
+
+int prs_index_create(int d, int metric, int storage, int device, prs_index** out) {
+    if (!out) { set_error("create: out is null"); return PRS_EINVAL; }
+    *out = nullptr;
+    if (d < 1 || d > 65536) { set_error("create: d=%d out of range", d); return PRS_EINVAL; }
+    if (metric != PRS_METRIC_IP && metric != PRS_METRIC_L2) { set_error("create: unknown metric %d", metric); return PRS_EINVAL; }
+    if (storage != PRS_F32 && storage != PRS_F16 && storage != PRS_BF16) { set_error("create: unknown storage %d", storage); return PRS_EINVAL; }
+    int arch = prs_device_arch(device);
+    if (arch < 0) return arch;
+    if (arch != 100) { set_error("libprs is built for sm_100a (B200); device %d is sm_%d", device, arch); return PRS_ECUDA; }
+    prs_index* idx = new (std::nothrow) prs_index();
+    if (!idx) { set_error("out of host memory"); return PRS_ENOMEM; }
+    idx->d = d; idx->pitch = (d + 63) / 64 * 64; idx->metric = metric; idx->storage = storage; idx->device = device;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete idx; set_error("cudaGetDeviceProperties failed"); return PRS_ECUDA; }
+    idx->sm_count = prop.multiProcessorCount;
+    *out = idx;
+    return 0;
+}
+
+void prs_index_free(prs_index* idx) {
+    if (!idx) return;
+    DeviceGuard g(idx->device);
+    if (idx->x) cudaFree(idx->x);
+    if (idx->xnorm) cudaFree(idx->xnorm);
+    idx->lists.release(); idx->cand.release(); idx->cand_cnt.release(); idx->qf32.release(); idx->qnorm.release();
+    idx->qlow.release(); idx->hD.release(); idx->hI.release(); idx->hQ.release(); idx->stage.release();
+    idx->umma.release();
+    if (idx->ws_event) cudaEventDestroy(idx->ws_event);
+    delete idx;
+}
+
+int prs_index_reserve(prs_index* idx, int64_t n_total) {
+    if (!idx) { set_error("null index"); return PRS_EINVAL; }
+    DeviceGuard g(idx->device);
+    std::lock_guard<std::mutex> lock(idx->mu);
+    PRS_CUDA(cudaDeviceSynchronize());
+    return index_grow(idx, n_total);
+}
+
+int prs_index_add_device(prs_index* idx, const void* x, int dtype, int64_t n, void* stream) {
+    if (!idx) { set_error("null index"); return PRS_EINVAL; }
+    if (n < 0 || (n > 0 && !x)) { set_error("add: bad arguments"); return PRS_EINVAL; }
+    if (idx->n + n > 0xFFFFFFFFll) { set_error("add: more than 2^32-1 rows per index (shard it)"); return PRS_EINVAL; }
+    DeviceGuard g(idx->device);
+    std::lock_guard<std::mutex> lock(idx->mu);
+    return add_device_impl(idx, x, dtype, n, (cudaStream_t)stream);
+}
+
+int prs_index_add_host(prs_index* idx, const float* x, int64_t n) {
+    if (!idx) { set_error("null index"); return PRS_EINVAL; }
+    if (n < 0 || (n > 0 && !x)) { set_error("add: bad arguments"); return PRS_EINVAL; }
+    if (idx->n + n > 0xFFFFFFFFll) { set_error("add: more than 2^32-1 rows per index (shard it)"); return PRS_EINVAL; }
+    DeviceGuard g(idx->device);
+    std::lock_guard<std::mutex> lock(idx->mu);
+    const long long chunk = std::max<long long>(1, (64ll << 20) / ((long long)idx->d * 4));
+    int rc;
+    if (idx->n + n > idx->cap_rows) {
+        PRS_CUDA(cudaDeviceSynchronize());
+        if ((rc = index_grow(idx, idx->n + n))) return rc;
+    }
+    for (long long o = 0; o < n; o += chunk) {
+        const long long c = std::min<long long>(chunk, n - o);
+        if ((rc = idx->stage.ensure((size_t)c * idx->d * 4))) return rc;
+        PRS_CUDA(cudaMemcpy(idx->stage.p, x + (size_t)o * idx->d, (size_t)c * idx->d * 4, cudaMemcpyHostToDevice));
+        if ((rc = add_device_impl(idx, idx->stage.p, PRS_F32, c, 0))) return rc;
+        PRS_CUDA(cudaStreamSynchronize(0));
+    }
+    return 0;
+}
+
+int64_t prs_index_ntotal(const prs_index* idx) { return idx ? idx->n : -1; }
+int prs_index_d(const prs_index* idx) { return idx ? idx->d : -1; }
+int prs_index_metric(const prs_index* idx) { return idx ? idx->metric : -1; }
+int prs_index_storage(const prs_index* idx) { return idx ? idx->storage : -1; }
+int prs_index_last_path(const prs_index* idx) { return idx ? idx->last_path : -1; }
+
+int prs_index_set_id_offset(prs_index* idx, int64_t off) {
+    if (!idx) { set_error("null index"); return PRS_EINVAL; }
+    idx->id_offset = off;
+    return 0;
+}
+int prs_index_set_path(prs_index* idx, int path) {
+    if (!idx || path < 0 || path > 2) { set_error("set_path: bad arguments"); return PRS_EINVAL; }
+    idx->path_force = path;
+    return 0;
+}
+
+int prs_index_search_device(prs_index* idx, const void* q, int qdtype, int64_t nq, int k, float* D, int64_t* I, void* stream) {
+    if (!idx) { set_error("null index"); return PRS_EINVAL; }
+    DeviceGuard g(idx->device);
+    return search_device_impl(idx, q, qdtype, nq, k, D, I, (cudaStream_t)stream);
+}
+
+int prs_index_search_host(prs_index* idx, const float* q, int64_t nq, int k, float* D, int64_t* I) {
+    if (!idx) { set_error("null index"); return PRS_EINVAL; }
+    if (k < 1 || k > PRS_MAX_K) { set_error("search: k=%d out of range [1, %d]", k, PRS_MAX_K); return PRS_EINVAL; }
+    if (nq < 0) { set_error("search: nq < 0"); return PRS_EINVAL; }
+    if (nq == 0) return 0;
+    if (!q || !D || !I) { set_error("search: null pointer"); return PRS_EINVAL; }
+    DeviceGuard g(idx->device);
+    int rc;
+    // concurrent host searches on one index serialise here (re-entrant, not parallel): they share
+    // the index's staging buffers and the legacy stream
+    std::lock_guard<std::mutex> hl(idx->host_mu);
+    void *dq, *dD, *dI;
+    {
+        std::lock_guard<std::mutex> lock(idx->mu);
+        if ((rc = idx->hQ.ensure((size_t)nq * idx->d * 4))) return rc;
+        if ((rc = idx->hD.ensure((size_t)nq * k * 4))) return rc;
+        if ((rc = idx->hI.ensure((size_t)nq * k * 8))) return rc;
+        dq = idx->hQ.p; dD = idx->hD.p; dI = idx->hI.p;
+    }
+    PRS_CUDA(cudaMemcpyAsync(dq, q, (size_t)nq * idx->d * 4, cudaMemcpyHostToDevice, 0));
+    if ((rc = search_device_impl(idx, dq, PRS_F32, nq, k, (float*)dD, (int64_t*)dI, 0))) return rc;
+    PRS_CUDA(cudaMemcpyAsync(D, dD, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, 0));
+    PRS_CUDA(cudaMemcpyAsync(I, dI, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, 0));
+    PRS_CUDA(cudaStreamSynchronize(0));
+    return 0;
+}
+
+int prs_index_reconstruct_host(prs_index* idx, int64_t i0, int64_t n, float* out) {
+    if (!idx) { set_error("null index"); return PRS_EINVAL; }
+    if (i0 < 0 || n < 0 || i0 + n > idx->n || (n > 0 && !out)) { set_error("reconstruct: range out of bounds"); return PRS_EINVAL; }
+    if (n == 0) return 0;
+    DeviceGuard g(idx->device);
+    std::lock_guard<std::mutex> lock(idx->mu);
+    const long long chunk = std::max<long long>(1, (64ll << 20) / ((long long)idx->d * 4));
+    int rc;
+    for (long long o = 0; o < n; o += chunk) {
+        const long long c = std::min<long long>(chunk, n - o);
+        if ((rc = idx->stage.ensure((size_t)c * idx->d * 4))) return rc;
+        const long long tot = c * idx->d;
+        const unsigned grid = (unsigned)((tot + 255) / 256);
+        switch (idx->storage) {
+            case PRS_F32: reconstruct_kernel<float><<<grid, 256>>>((const float*)idx->x, i0 + o, c, idx->d, idx->pitch, (float*)idx->stage.p); break;
+            case PRS_F16: reconstruct_kernel<__half><<<grid, 256>>>((const __half*)idx->x, i0 + o, c, idx->d, idx->pitch, (float*)idx->stage.p); break;
+            default: reconstruct_kernel<__nv_bfloat16><<<grid, 256>>>((const __nv_bfloat16*)idx->x, i0 + o, c, idx->d, idx->pitch, (float*)idx->stage.p); break;
+        }
+        PRS_LAUNCH_CHECK();
+        PRS_CUDA(cudaMemcpy(out + (size_t)o * idx->d, idx->stage.p, (size_t)tot * 4, cudaMemcpyDeviceToHost));
+    }
+    return 0;
+}
+
+int prs_merge_topk_device(const float* Dp, const int64_t* Ip, int nparts, int64_t nq, int k, int largest,
+                          int tie_high_id, float* D, int64_t* I, int device, void* stream) {
+    if (nparts < 1 || nq < 0 || k < 1 || k > PRS_MAX_K) { set_error("merge: bad arguments"); return PRS_EINVAL; }
+    if ((long long)nparts * k > (1ll << 30)) { set_error("merge: nparts*k too large"); return PRS_EINVAL; }
+    if (nq == 0) return 0;
+    if (!Dp || !Ip || !D || !I) { set_error("merge: null pointer"); return PRS_EINVAL; }
+    DeviceGuard g(device);
+    const int sortn = next_pow2(k + MERGE_THREADS);
+    const size_t smem = (size_t)sortn * 8 + 16;
+    PRS_CUDA(cudaFuncSetAttribute(merge_parts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    merge_parts_kernel<<<(unsigned)nq, MERGE_THREADS, smem, (cudaStream_t)stream>>>(Dp, (const long long*)Ip, nparts, nq, k, sortn,
+                                                                                   largest, tie_high_id, D, (long long*)I);
+    PRS_LAUNCH_CHECK();
+    return 0;
+}
+
+// ---- on-disk format: faiss IndexFlat (IxF2 / IxFI), SURVEY.md 8f-2 ----
+#pragma pack(push, 1)
+struct FlatHeader {
+    char fourcc[4];
+    int32_t d;
+    int64_t ntotal;
+    int64_t dummy1, dummy2;
+    uint8_t is_trained;
+    int32_t metric_type;
+    uint64_t n_values;
+};
+#pragma pack(pop)
+static_assert(sizeof(FlatHeader) == 45, "faiss IndexFlat header is 45 bytes");
+
+int prs_index_write(prs_index* idx, const char* path) {
+    if (!idx || !path) { set_error("write: bad arguments"); return PRS_EINVAL; }
+    FlatHeader h;
+    const char* cc = idx->storage == PRS_F32 ? (idx->metric == PRS_METRIC_L2 ? "IxF2" : "IxFI")
+                                             : (idx->storage == PRS_F16 ? "PRSh" : "PRSb");
+    memcpy(h.fourcc, cc, 4);
+    h.d = idx->d; h.ntotal = idx->n; h.dummy1 = h.dummy2 = 1 << 20; h.is_trained = 1; h.metric_type = idx->metric;
+    h.n_values = (uint64_t)idx->n * idx->d;
+    FILE* f = fopen(path, "wb");
+    if (!f) { set_error("write: cannot open %s: %s", path, strerror(errno)); return PRS_EIO; }
+    bool ok = fwrite(&h, sizeof(h), 1, f) == 1;
+    const long long chunk = std::max<long long>(1, (64ll << 20) / ((long long)idx->d * 4));
+    std::vector<float> host((size_t)std::min<long long>(chunk, std::max<long long>(idx->n, 1)) * idx->d);
+    std::vector<uint16_t> half;
+    for (long long o = 0; ok && o < idx->n; o += chunk) {
+        const long long c = std::min<long long>(chunk, idx->n - o);
+        int rc = prs_index_reconstruct_host(idx, o, c, host.data());
+        if (rc) { fclose(f); return rc; }
+        if (idx->storage == PRS_F32) {
+            ok = fwrite(host.data(), 4, (size_t)c * idx->d, f) == (size_t)c * idx->d;
+        } else {
+            // values are exactly representable in the 16-bit type (they came from it)
+            half.resize((size_t)c * idx->d);
+            for (size_t i = 0; i < half.size(); ++i) {
+                uint32_t u; memcpy(&u, &host[i], 4);
+                if (idx->storage == PRS_BF16) half[i] = (uint16_t)(u >> 16);
+                else { __half hv = __float2half_rn(host[i]); memcpy(&half[i], &hv, 2); }
+            }
+            ok = fwrite(half.data(), 2, half.size(), f) == half.size();
+        }
+    }
+    if (fclose(f) != 0) ok = false;
+    if (!ok) { set_error("write: short write to %s", path); return PRS_EIO; }
+    return 0;
+}
+
+int prs_index_read(const char* path, int storage, int device, prs_index** out) {
+    if (!path || !out) { set_error("read: bad arguments"); return PRS_EINVAL; }
+    *out = nullptr;
+    FILE* f = fopen(path, "rb");
+    if (!f) { set_error("read: cannot open %s: %s", path, strerror(errno)); return PRS_EIO; }
+    FlatHeader h;
+    if (fread(&h, sizeof(h), 1, f) != 1) { fclose(f); set_error("read: %s is shorter than an IndexFlat header", path); return PRS_EIO; }
+    int file_dt;
+    if (!memcmp(h.fourcc, "IxF2", 4) || !memcmp(h.fourcc, "IxFI", 4)) file_dt = PRS_F32;
+    else if (!memcmp(h.fourcc, "PRSh", 4)) file_dt = PRS_F16;
+    else if (!memcmp(h.fourcc, "PRSb", 4)) file_dt = PRS_BF16;
+    else {
+        fclose(f);
+        set_error("read: %s has fourcc '%.4s'; only flat indices (IxF2/IxFI/PRSh/PRSb) are supported", path, h.fourcc);
+        return PRS_EUNSUP;
+    }
+    if (h.d < 1 || h.ntotal < 0 || h.n_values != (uint64_t)h.ntotal * (uint64_t)h.d ||
+        (h.metric_type != PRS_METRIC_IP && h.metric_type != PRS_METRIC_L2)) {
+        fclose(f); set_error("read: %s has an inconsistent header", path); return PRS_EIO;
+    }
+    prs_index* idx = nullptr;
+    int rc = prs_index_create(h.d, h.metric_type, storage, device, &idx);
+    if (rc) { fclose(f); return rc; }
+    DeviceGuard g(device);
+    if ((rc = prs_index_reserve(idx, h.ntotal))) { fclose(f); prs_index_free(idx); return rc; }
+    const int fes = elem_size(file_dt);
+    const long long chunk = std::max<long long>(1, (64ll << 20) / ((long long)h.d * fes));
+    std::vector<unsigned char> host((size_t)std::min<long long>(chunk, std::max<long long>(h.ntotal, 1)) * h.d * fes);
+    for (long long o = 0; o < h.ntotal; o += chunk) {
+        const long long c = std::min<long long>(chunk, h.ntotal - o);
+        const size_t bytes = (size_t)c * h.d * fes;
+        if (fread(host.data(), 1, bytes, f) != bytes) { fclose(f); prs_index_free(idx); set_error("read: %s is truncated", path); return PRS_EIO; }
+        if (file_dt == PRS_F32) rc = prs_index_add_host(idx, (const float*)host.data(), c);
+        else {
+            std::lock_guard<std::mutex> lock(idx->mu);
+            rc = idx->stage.ensure(bytes);
+            if (!rc) {
+                if (cudaMemcpy(idx->stage.p, host.data(), bytes, cudaMemcpyHostToDevice) != cudaSuccess) { set_error("read: H2D copy failed"); rc = PRS_ECUDA; }
+                else { rc = add_device_impl(idx, idx->stage.p, file_dt, c, 0); cudaStreamSynchronize(0); }
+            }
+        }
+        if (rc) { fclose(f); prs_index_free(idx); return rc; }
+    }
+    fclose(f);
+    *out = idx;
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,394 @@
+// flat_umma.cuh -- tcgen05 flat scan with a fused per-query top-k (fp16 / bf16 storage).
+//
+// Replaces faiss IndexFlat::search (reference call site src/retrieval.py:102) for query batches
+// that make the scan a real GEMM while it is still HBM-bound (8 <= nq; 128 queries per pass).
+//
+//   D[128 queries x TILE_N rows] (+)= A[128 x K] * B[TILE_N x K]^T      (tcgen05.mma, kind::f16)
+//
+//   A  = the query block, converted to the storage type once, RESIDENT IN TENSOR MEMORY for the
+//        whole kernel (tcgen05.st, one TMEM lane per query).  Shared memory therefore holds
+//        nothing but the streaming ring, and the MMA never re-reads queries from smem or L2.
+//   B  = corpus rows, K-major, streamed HBM -> smem by TMA (cp.async.bulk.tensor.2d, 128-byte
+//        swizzle) in K-blocks of 64 elements through an mbarrier ring.
+//   D  = fp32 accumulators in TMEM, double buffered (2 x TILE_N columns).
+//   epilogue (4 warps, one thread per query): tcgen05.ld its lane's TILE_N scores, apply the L2
+//        bias (2 q.x - ||x||^2), compare with the thread's k-th best, and on the rare hit insert
+//        into a thread-private sorted list in shared memory.  The score matrix never exists in
+//        HBM; each CTA emits one sorted top-k per query (cand[cta][query][k]).
+//
+// TMEM budget (512 columns): A uses pitch/2 columns (two 16-bit values per column), D uses
+// 2*TILE_N.  pitch <= 512 -> TILE_N = 128; pitch <= 768 -> TILE_N = 64.
+//
+// Warp roles (192 threads): warp 0 = TMA producer + TMEM allocator, warp 1 = MMA issuer,
+// warps 2..5 = epilogue (TMEM lane quarter = warp % 4).
+#pragma once
+#include <cuda.h>
+
+#include "common.cuh"
+#include "host_common.h"
+
+namespace prs {
+
+constexpr int UMMA_MAX_K = 16;         // thread-private sorted lists live in shared memory
+constexpr int UMMA_THREADS = 192;
+constexpr int UMMA_M = 128;            // queries per pass
+constexpr int UMMA_MAX_STAGES = 24;
+constexpr int UMMA_TMEM_COLS = 512;
+
+struct UmmaParams {
+    const uint16_t* qlow;   // [128, pitch] 16-bit queries of this pass (zero padded)
+    const float* xnorm;     // [n_rows] squared norms of the stored rows
+    long long n_rows;
+    int pitch, nq, k, l2, stages, is_bf16;
+    int nq_total, q0;
+    u64* cand;              // [grid][nq_total][k]
+    int* cand_cnt;          // [grid][nq_total]
+};
+
+// ---------------- PTX wrappers (tcgen05 / TMA) ----------------
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem desc]
+__device__ __forceinline__ void umma_ts_f16(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, {%5, %6, %7, %8}, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(0), "r"(0), "r"(0), "r"(0)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tmap, int x, int y, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(x), "r"(y), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+          "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]),
+          "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]),
+          "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// shared-memory matrix descriptor: K-major, 128-byte swizzle, 8-row groups 1024 bytes apart
+// (cute::UMMA::SmemDescriptor: start[0,14) LBO[16,30) SBO[32,46) version[46,48)=1 layout[61,64)=2)
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+
+// thread-private sorted (descending) list of k keys, stride UMMA_M between entries.
+// Returns the new admission threshold.
+__device__ __noinline__ float umma_topk_insert(u64* list, int k, float s, uint32_t id, float thr) {
+    const u64 key = make_key<PRS_TIE_LOW_ID>(s, id);
+    u64 last = list[(k - 1) * UMMA_M];
+    if (key <= last) return thr;
+    int pos = k - 1;
+    while (pos > 0) {
+        const u64 up = list[(pos - 1) * UMMA_M];
+        if (up >= key) break;
+        list[pos * UMMA_M] = up;
+        --pos;
+    }
+    list[pos * UMMA_M] = key;
+    last = list[(k - 1) * UMMA_M];
+    return last ? key_score(last) : -INFINITY;
+}
+
+template <int TILE_N>
+__global__ void __launch_bounds__(UMMA_THREADS, 1) flat_scan_umma_kernel(const __grid_constant__ CUtensorMap tmap, const UmmaParams p) {
+    extern __shared__ unsigned char umma_smem_raw[];
+    constexpr uint32_t STAGE_BYTES = TILE_N * 128;
+    constexpr uint32_t D_OFF = UMMA_TMEM_COLS - 2 * TILE_N;     // accumulator columns at the top
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // 1024-byte aligned carve-up (SWIZZLE_128B atoms are 1024 bytes)
+    const uint32_t raw = smem_u32(umma_smem_raw);
+    unsigned char* base = umma_smem_raw + (((raw + 1023u) & ~1023u) - raw);
+    unsigned char* ring = base;
+    u64* lists = reinterpret_cast<u64*>(ring + (size_t)p.stages * STAGE_BYTES);           // [k][128]
+    float* snorm = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(lists) + (size_t)UMMA_MAX_K * UMMA_M * 8);  // [4][TILE_N]
+    uint64_t* full = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(snorm) + 4 * TILE_N * 4);
+    uint64_t* empty = full + UMMA_MAX_STAGES;
+    uint64_t* tmem_full = empty + UMMA_MAX_STAGES;
+    uint64_t* tmem_empty = tmem_full + 2;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+    const int kblocks = p.pitch >> 6;
+    const long long n_tiles = (p.n_rows + TILE_N - 1) / TILE_N;
+
+    if (tid == 0) {
+        for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 4); }
+        mbar_fence_init();
+    }
+    for (int i = tid; i < UMMA_MAX_K * UMMA_M; i += UMMA_THREADS) lists[i] = 0ull;
+    if (warp == 0) tmem_alloc(tmem_ptr, UMMA_TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp >= 2) {
+        // ---- stage this thread's query row into TMEM: lane m, columns [0, pitch/2) ----
+        const int qd = warp & 3;
+        const int m = qd * 32 + lane;
+        const uint4* qrow = reinterpret_cast<const uint4*>(p.qlow + (size_t)m * p.pitch);
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(qd * 32) << 16);
+        for (int c0 = 0; c0 < (p.pitch >> 1); c0 += 32) {
+            uint32_t v[32];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const uint4 t = qrow[(c0 >> 2) + i];
+                v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+            }
+            tmem_st32(lane_addr + (uint32_t)c0, v);
+        }
+        tmem_st_wait();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+
+    if (warp == 0) {
+        // ---------------- TMA producer ----------------
+        if (lane == 0) {
+            int s = 0;
+            uint32_t ph = 0;
+            for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+                const int row0 = (int)(t * TILE_N);
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    mbar_wait(&empty[s], ph ^ 1u);
+                    mbar_arrive_expect_tx(&full[s], STAGE_BYTES);
+                    tma_load_2d(ring + (size_t)s * STAGE_BYTES, &tmap, kb * 64, row0, &full[s]);
+                    if (++s == p.stages) { s = 0; ph ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ---------------- MMA issuer (one thread) ----------------
+        // instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 [4,6)=1,
+        // a/b_format [7,10)/[10,13) (0 F16, 1 BF16), K-major A and B, N>>3 at [17,23), M>>4 at [24,29)
+        const uint32_t fmt = p.is_bf16 ? 1u : 0u;
+        const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(TILE_N >> 3) << 17) | ((uint32_t)(UMMA_M >> 4) << 24);
+        int s = 0, it = 0;
+        uint32_t ph = 0;
+        for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+            const int b = it & 1;
+            const uint32_t aph = (uint32_t)(it >> 1) & 1u;
+            mbar_wait(&tmem_empty[b], aph ^ 1u);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + D_OFF + (uint32_t)(b * TILE_N);
+            for (int kb = 0; kb < kblocks; ++kb) {
+                mbar_wait(&full[s], ph);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t sb = smem_u32(ring + (size_t)s * STAGE_BYTES);
+#pragma unroll
+                    for (int k4 = 0; k4 < 4; ++k4) {
+                        const uint64_t bdesc = umma_desc_sw128(sb + (uint32_t)k4 * 32u);
+                        const uint32_t a_tmem = tmem_base + (uint32_t)(kb * 32 + k4 * 8);
+                        umma_ts_f16(d_tmem, a_tmem, bdesc, idesc, (kb | k4) != 0 ? 1u : 0u);
+                    }
+                    umma_commit(&empty[s]);                    // frees the smem stage when these MMAs retire
+                    if (kb == kblocks - 1) umma_commit(&tmem_full[b]);
+                }
+                __syncwarp();
+                if (++s == p.stages) { s = 0; ph ^= 1u; }
+            }
+        }
+    } else {
+        // ---------------- epilogue: one thread per query ----------------
+        const int qd = warp & 3;
+        const int m = qd * 32 + lane;
+        const bool qvalid = m < p.nq;
+        u64* mylist = lists + m;
+        float* wnorm = snorm + (warp - 2) * TILE_N;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(qd * 32) << 16) + D_OFF;
+        float thr = -INFINITY;
+        int it = 0;
+        for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+            const int b = it & 1;
+            const uint32_t aph = (uint32_t)(it >> 1) & 1u;
+            const long long row0 = t * TILE_N;
+            const int nvalid = (int)((p.n_rows - row0 < TILE_N) ? (p.n_rows - row0) : TILE_N);
+            if (p.l2) {
+                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < TILE_N / 32; ++i) {
+                    const int c = lane + 32 * i;
+                    wnorm[c] = (c < nvalid) ? p.xnorm[row0 + c] : 0.f;
+                }
+                __syncwarp();
+            }
+            mbar_wait(&tmem_full[b], aph);
+            tc_fence_after();
+#pragma unroll 1
+            for (int c = 0; c < TILE_N; c += 32) {
+                uint32_t v[32];
+                __syncwarp();
+                tmem_ld32(lane_addr + (uint32_t)(b * TILE_N + c), v);
+                tmem_ld_wait();
+                if (c + 32 == TILE_N) {
+                    // accumulator fully read: hand the TMEM buffer back to the MMA warp
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tmem_empty[b]);
+                }
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    float s = __uint_as_float(v[j]);
+                    if (p.l2) s = fmaf(2.f, s, -wnorm[c + j]);
+                    if (qvalid && (c + j) < nvalid && s >= thr)
+                        thr = umma_topk_insert(mylist, p.k, s, (uint32_t)(row0 + c + j), thr);
+                }
+            }
+        }
+        if (qvalid) {
+            const size_t o = (size_t)blockIdx.x * p.nq_total + p.q0 + m;
+            int n = 0;
+            for (int j = 0; j < p.k; ++j) {
+                const u64 key = mylist[j * UMMA_M];
+                if (key) p.cand[o * p.k + n++] = key;
+            }
+            p.cand_cnt[o] = n;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == 0) tmem_dealloc(tmem_base, UMMA_TMEM_COLS);
+}
+
+// fp32 queries -> [128-padded, pitch] 16-bit, zero padded
+__global__ void pack_queries_kernel(const float* __restrict__ q, long long nq, int d, int pitch, long long nq_pad,
+                                    int is_bf16, uint16_t* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nq_pad * pitch) return;
+    const long long r = i / pitch;
+    const int c = (int)(i - r * pitch);
+    float v = (r < nq && c < d) ? q[r * d + c] : 0.f;
+    uint16_t o;
+    if (is_bf16) { __nv_bfloat16 h = __float2bfloat16_rn(v); o = *reinterpret_cast<uint16_t*>(&h); }
+    else { __half h = __float2half_rn(v); o = *reinterpret_cast<uint16_t*>(&h); }
+    out[i] = o;
+}
+
+// ---------------- host side ----------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct UmmaState {
+    CUtensorMap tmap;
+    bool valid = false;
+    const void* x = nullptr;
+    long long n = 0;
+    int tile_n = 0;
+    DevBuf qlow;
+    void invalidate() { valid = false; }
+    void release() { qlow.release(); valid = false; }
+};
+
+static inline int umma_tile_n(int pitch) { return pitch <= 512 ? 128 : 64; }
+
+static inline bool umma_eligible(int storage, int d, int pitch, long long nq, int k) {
+    (void)d;
+    return (storage == PRS_F16 || storage == PRS_BF16) && pitch <= 768 && k <= UMMA_MAX_K && nq >= 8;
+}
+
+static inline int umma_make_tmap(UmmaState& st, const void* x, long long n, int pitch, int storage, int tile_n) {
+    if (st.valid && st.x == x && st.n == n && st.tile_n == tile_n) return 0;
+    static PFN_encodeTiled encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        PRS_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (!fn || qres != cudaDriverEntryPointSuccess) { set_error("cuTensorMapEncodeTiled not available from the driver"); return PRS_ECUDA; }
+        encode = (PFN_encodeTiled)fn;
+    }
+    const cuuint64_t dims[2] = {(cuuint64_t)pitch, (cuuint64_t)n};
+    const cuuint64_t strides[1] = {(cuuint64_t)pitch * 2};
+    const cuuint32_t box[2] = {64, (cuuint32_t)tile_n};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = encode(&st.tmap, storage == PRS_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
+                        const_cast<void*>(x), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return PRS_ECUDA; }
+    st.valid = true; st.x = x; st.n = n; st.tile_n = tile_n;
+    return 0;
+}
+
+static inline int search_umma(UmmaState& st, const void* x, const float* xnorm, long long n, int d, int pitch, int storage,
+                              int metric, int sm_count, const float* qf, long long nq, int k, DevBuf& cand, DevBuf& cand_cnt,
+                              int* parts_out, cudaStream_t stream) {
+    const int tile_n = umma_tile_n(pitch);
+    if (n > 0x7FFFFFFFll - tile_n) { set_error("tcgen05 path: more than 2^31 rows per shard"); return PRS_EUNSUP; }
+    int rc;
+    if ((rc = umma_make_tmap(st, x, n, pitch, storage, tile_n))) return rc;
+    const long long nq_pad = (nq + UMMA_M - 1) / UMMA_M * UMMA_M;
+    if ((rc = st.qlow.ensure((size_t)nq_pad * pitch * 2))) return rc;
+    {
+        const long long tot = nq_pad * pitch;
+        pack_queries_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>(qf, nq, d, pitch, nq_pad, storage == PRS_BF16,
+                                                                               (uint16_t*)st.qlow.p);
+        PRS_LAUNCH_CHECK();
+    }
+    const long long n_tiles = (n + tile_n - 1) / tile_n;
+    const int grid = (int)std::min<long long>(sm_count, n_tiles);
+    if ((rc = cand.ensure((size_t)grid * nq * k * 8))) return rc;
+    if ((rc = cand_cnt.ensure((size_t)grid * nq * 4))) return rc;
+    const size_t stage_bytes = (size_t)tile_n * 128;
+    const size_t fixed = (size_t)UMMA_MAX_K * UMMA_M * 8 + 4 * (size_t)tile_n * 4 + (2 * UMMA_MAX_STAGES + 4) * 8 + 16;
+    int stages = (int)((200 * 1024 - fixed) / stage_bytes);
+    if (stages > UMMA_MAX_STAGES) stages = UMMA_MAX_STAGES;
+    const size_t smem = 1024 + (size_t)stages * stage_bytes + fixed;
+    for (long long q0 = 0; q0 < nq; q0 += UMMA_M) {
+        UmmaParams p;
+        p.qlow = (const uint16_t*)st.qlow.p + (size_t)q0 * pitch;
+        p.xnorm = xnorm; p.n_rows = n; p.pitch = pitch;
+        p.nq = (int)std::min<long long>(UMMA_M, nq - q0);
+        p.k = k; p.l2 = metric == PRS_METRIC_L2; p.stages = stages; p.is_bf16 = storage == PRS_BF16;
+        p.nq_total = (int)nq; p.q0 = (int)q0;
+        p.cand = (u64*)cand.p; p.cand_cnt = (int*)cand_cnt.p;
+        if (tile_n == 128) {
+            PRS_CUDA(cudaFuncSetAttribute(flat_scan_umma_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            flat_scan_umma_kernel<128><<<grid, UMMA_THREADS, smem, stream>>>(st.tmap, p);
+        } else {
+            PRS_CUDA(cudaFuncSetAttribute(flat_scan_umma_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            flat_scan_umma_kernel<64><<<grid, UMMA_THREADS, smem, stream>>>(st.tmap, p);
+        }
+        PRS_LAUNCH_CHECK();
+    }
+    *parts_out = grid;
+    return 0;
+}
+
+}  // namespace prs

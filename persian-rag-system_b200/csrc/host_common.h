@@ -1,0 +1,68 @@
+// host_common.h -- host-side helpers shared by the translation units of libprs.so
+#pragma once
+#include <cuda_runtime.h>
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "../../include/prs.h"
+
+namespace prs {
+
+void set_error(const char* fmt, ...);
+extern std::atomic<long long> g_launches;
+
+#define PRS_CUDA(expr)                                                                        \
+    do {                                                                                      \
+        cudaError_t _e = (expr);                                                              \
+        if (_e != cudaSuccess) {                                                              \
+            prs::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return PRS_ECUDA;                                                                 \
+        }                                                                                     \
+    } while (0)
+
+#define PRS_LAUNCH_CHECK()                                                                    \
+    do {                                                                                      \
+        prs::g_launches.fetch_add(1, std::memory_order_relaxed);                              \
+        cudaError_t _e = cudaGetLastError();                                                  \
+        if (_e != cudaSuccess) {                                                              \
+            prs::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return PRS_ECUDA;                                                                 \
+        }                                                                                     \
+    } while (0)
+
+// sets the device for the current scope and restores the previous one
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; prev = -1; }
+        if (cudaSetDevice(dev) != cudaSuccess) ok = false;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+// grow-only device buffer
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    int ensure(size_t need) {
+        if (need <= bytes) return 0;
+        if (p) cudaFree(p);
+        p = nullptr; bytes = 0;
+        size_t want = need + need / 4;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            e = cudaMalloc(&p, need);
+            want = need;
+        }
+        if (e != cudaSuccess) { cudaGetLastError(); set_error("cudaMalloc(%zu) failed: %s", need, cudaGetErrorString(e)); p = nullptr; return PRS_ENOMEM; }
+        bytes = want;
+        return 0;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+};
+
+}  // namespace prs

@@ -1,0 +1,192 @@
+"""faiss-shaped flat index on top of libprs (C ABI: include/prs.h).
+
+Mirrors exactly the faiss surface the reference touches:
+  faiss.IndexFlatL2(d)            src/create_embeddings.py:130, scripts/phase3_pdf_chunking.py:47
+  index.add(x)                    src/create_embeddings.py:133
+  index.search(x, k) -> (D, I)    src/retrieval.py:102
+  index.ntotal / index.d          src/retrieval.py:56, src/create_embeddings.py:286
+  faiss.write_index / read_index  src/create_embeddings.py:136, src/retrieval.py:55
+plus the knobs the B200 engine adds: `storage` (fp32 exact-parity / fp16 / bf16 throughput),
+device-resident tensors in and out (no host hop between the encoder and the search), and a
+global-id offset for row shards.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import numpy as np
+
+from . import _lib
+from ._lib import BF16, F16, F32, METRIC_INNER_PRODUCT, METRIC_L2, PrsError, check
+
+_STORAGE = {"fp32": F32, "float32": F32, "f32": F32, F32: F32,
+            "fp16": F16, "float16": F16, "f16": F16, "half": F16, F16: F16,
+            "bf16": BF16, "bfloat16": BF16, BF16: BF16}
+_STORAGE_NAME = {F32: "fp32", F16: "fp16", BF16: "bf16"}
+
+
+def _is_tensor(x) -> bool:
+    return hasattr(x, "data_ptr") and hasattr(x, "is_cuda")
+
+
+def _torch_dtype_code(t):
+    import torch
+    code = {torch.float32: F32, torch.float16: F16, torch.bfloat16: BF16}.get(t.dtype)
+    if code is None:
+        raise PrsError(_lib.EINVAL, f"unsupported tensor dtype {t.dtype}")
+    return code
+
+
+def _default_device() -> int:
+    import sys
+    if "torch" in sys.modules:
+        torch = sys.modules["torch"]
+        try:
+            if torch.cuda.is_available():
+                return int(torch.cuda.current_device())
+        except Exception:
+            pass
+    return int(os.environ.get("LOCAL_RANK", "0")) if os.environ.get("PRS_DEVICE_FROM_LOCAL_RANK") else 0
+
+
+class FlatIndex:
+    """Exact (brute-force) dense index resident in HBM."""
+
+    def __init__(self, d: int, metric: int = METRIC_L2, storage="fp32", device: int | None = None, _handle=None):
+        self._h = ctypes.c_void_p()
+        self._L = _lib.lib()
+        if _handle is not None:
+            self._h = _handle
+        else:
+            if storage not in _STORAGE:
+                raise PrsError(_lib.EINVAL, f"unknown storage {storage!r}")
+            dev = _default_device() if device is None else int(device)
+            check(self._L.prs_index_create(int(d), int(metric), _STORAGE[storage], dev, ctypes.byref(self._h)))
+        self.device = _default_device() if device is None else int(device)
+        self.is_trained = True
+
+    # ---- faiss attributes ----
+    @property
+    def d(self) -> int:
+        return int(self._L.prs_index_d(self._h))
+
+    @property
+    def ntotal(self) -> int:
+        return int(self._L.prs_index_ntotal(self._h))
+
+    @property
+    def metric_type(self) -> int:
+        return int(self._L.prs_index_metric(self._h))
+
+    @property
+    def storage(self) -> str:
+        return _STORAGE_NAME[int(self._L.prs_index_storage(self._h))]
+
+    @property
+    def last_path(self) -> str:
+        return {0: "none", 1: "cuda-core", 2: "tcgen05"}[int(self._L.prs_index_last_path(self._h))]
+
+    def set_path(self, path) -> None:
+        """'auto' | 'cuda-core' | 'tcgen05' (tests and benchmarks)."""
+        code = {"auto": 0, "cuda-core": 1, "tcgen05": 2, 0: 0, 1: 1, 2: 2}[path]
+        check(self._L.prs_index_set_path(self._h, code))
+
+    def set_id_offset(self, offset: int) -> None:
+        check(self._L.prs_index_set_id_offset(self._h, int(offset)))
+
+    def reserve(self, n_total: int) -> None:
+        check(self._L.prs_index_reserve(self._h, int(n_total)))
+
+    # ---- faiss methods ----
+    def add(self, x) -> None:
+        if _is_tensor(x):
+            import torch
+            if not x.is_cuda:
+                return self.add(x.detach().float().numpy())
+            if x.dim() != 2 or x.shape[1] != self.d:
+                raise PrsError(_lib.EINVAL, f"add: expected [n, {self.d}], got {tuple(x.shape)}")
+            x = x.contiguous()
+            st = torch.cuda.current_stream(x.device).cuda_stream
+            check(self._L.prs_index_add_device(self._h, ctypes.c_void_p(x.data_ptr()), _torch_dtype_code(x),
+                                               int(x.shape[0]), ctypes.c_void_p(st)))
+            return
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        if x.ndim != 2 or x.shape[1] != self.d:
+            raise PrsError(_lib.EINVAL, f"add: expected [n, {self.d}], got {x.shape}")
+        check(self._L.prs_index_add_host(self._h, x.ctypes.data_as(ctypes.c_void_p), int(x.shape[0])))
+
+    def search(self, x, k: int):
+        """numpy in -> (D float32 [nq,k], I int64 [nq,k]) numpy out (faiss contract);
+        CUDA torch tensor in -> torch tensors out, asynchronous on the current stream."""
+        k = int(k)
+        if _is_tensor(x) and x.is_cuda:
+            import torch
+            if x.dim() != 2 or x.shape[1] != self.d:
+                raise PrsError(_lib.EINVAL, f"search: expected [nq, {self.d}], got {tuple(x.shape)}")
+            x = x.contiguous()
+            nq = int(x.shape[0])
+            D = torch.empty((nq, k), dtype=torch.float32, device=x.device)
+            I = torch.empty((nq, k), dtype=torch.int64, device=x.device)
+            st = torch.cuda.current_stream(x.device).cuda_stream
+            check(self._L.prs_index_search_device(self._h, ctypes.c_void_p(x.data_ptr()), _torch_dtype_code(x), nq, k,
+                                                  ctypes.c_void_p(D.data_ptr()), ctypes.c_void_p(I.data_ptr()),
+                                                  ctypes.c_void_p(st)))
+            return D, I
+        if _is_tensor(x):
+            x = x.detach().float().numpy()
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        if x.ndim != 2 or x.shape[1] != self.d:
+            raise PrsError(_lib.EINVAL, f"search: expected [nq, {self.d}], got {x.shape}")
+        nq = int(x.shape[0])
+        D = np.empty((nq, k), dtype=np.float32)
+        I = np.empty((nq, k), dtype=np.int64)
+        check(self._L.prs_index_search_host(self._h, x.ctypes.data_as(ctypes.c_void_p), nq, k,
+                                            D.ctypes.data_as(ctypes.c_void_p), I.ctypes.data_as(ctypes.c_void_p)))
+        return D, I
+
+    def search_into(self, q_ptr: int, nq: int, k: int, D_ptr: int, I_ptr: int) -> None:
+        """Raw host-pointer search (pinned buffers in benchmarks): no allocation per call."""
+        check(self._L.prs_index_search_host(self._h, ctypes.c_void_p(q_ptr), int(nq), int(k),
+                                            ctypes.c_void_p(D_ptr), ctypes.c_void_p(I_ptr)))
+
+    def reconstruct_n(self, i0: int = 0, n: int | None = None) -> np.ndarray:
+        n = self.ntotal - i0 if n is None else n
+        out = np.empty((n, self.d), dtype=np.float32)
+        check(self._L.prs_index_reconstruct_host(self._h, int(i0), int(n), out.ctypes.data_as(ctypes.c_void_p)))
+        return out
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None) is not None and self._h.value:
+                self._L.prs_index_free(self._h)
+                self._h = ctypes.c_void_p()
+        except Exception:
+            pass
+
+
+def IndexFlatL2(d: int, storage="fp32", device: int | None = None) -> FlatIndex:
+    """faiss.IndexFlatL2(d) -- src/create_embeddings.py:130"""
+    return FlatIndex(d, METRIC_L2, storage, device)
+
+
+def IndexFlatIP(d: int, storage="fp32", device: int | None = None) -> FlatIndex:
+    """faiss.IndexFlatIP(d)"""
+    return FlatIndex(d, METRIC_INNER_PRODUCT, storage, device)
+
+
+def write_index(index: FlatIndex, path: str) -> None:
+    """faiss.write_index(index, path) -- src/create_embeddings.py:136.  fp32 storage writes faiss's
+    byte-exact IndexFlat file."""
+    check(index._L.prs_index_write(index._h, os.fsencode(path)))
+
+
+def read_index(path: str, storage="fp32", device: int | None = None) -> FlatIndex:
+    """faiss.read_index(path) -- src/retrieval.py:55"""
+    if storage not in _STORAGE:
+        raise PrsError(_lib.EINVAL, f"unknown storage {storage!r}")
+    L = _lib.lib()
+    h = ctypes.c_void_p()
+    dev = _default_device() if device is None else int(device)
+    check(L.prs_index_read(os.fsencode(path), _STORAGE[storage], dev, ctypes.byref(h)))
+    return FlatIndex(0, _handle=h, device=dev)

@@ -1,0 +1,305 @@
+"""GPU parity: flat dense search through the C ABI (ctypes) vs the CPU oracle.
+
+fp32 storage is the exact-parity mode: id lists identical to the oracle, distances within 1e-5
+relative (summation order differs).  fp16/bf16 storage is checked tie-aware against the fp32
+oracle run on the STORED (rounded) rows with the north-star tolerance 1e-3 relative.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+RTOL_F32 = 1e-5          # north_star: <= 1e-5 for fp32
+RTOL_16 = 1e-3           # north_star: <= 1e-3 relative for fp16/bf16 storage
+
+
+@pytest.fixture(scope="module")
+def P():
+    import persian_rag_system_b200 as P
+    assert P.lib().prs_device_arch(0) == 100, P._lib.last_error()
+    return P
+
+
+def _round_to(x, storage):
+    import torch
+    t = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32))
+    if storage == "fp16":
+        return t.half().float().numpy()
+    if storage == "bf16":
+        return t.bfloat16().float().numpy()
+    return x.astype(np.float32)
+
+
+def _check_exact(D, I, x, q, k, metric, what):
+    Dr, Ir = O.flat_search_c(x, q, k, metric, form=1)
+    S = O.flat_scores_f64(x, q, metric)
+    flips = 0
+    for r in range(q.shape[0]):
+        flips += O.check_topk_against_scores(I[r], D[r], S[r], k, metric == O.METRIC_IP, rtol=RTOL_F32, atol=1e-6,
+                                             what=f"{what} q{r}")
+    return flips, Ir
+
+
+# ------------------------------------------------------------------ the reference's own indices
+@pytest.mark.parametrize("metric", [O.METRIC_L2, O.METRIC_IP])
+def test_golden_indices_fp32_ids_identical(P, gold_dir, golden_indices, metric):
+    g = np.load(os.path.join(gold_dir, "flat_golden.npz"))
+    tag = "l2" if metric == O.METRIC_L2 else "ip"
+    for t, f in enumerate(g["files"].tolist()):
+        x, _ = golden_indices[f]
+        idx = P.FlatIndex(x.shape[1], metric, "fp32")
+        idx.add(x)
+        assert idx.ntotal == x.shape[0] and idx.d == x.shape[1]
+        q = g[f"q_{t}"]
+        for k in (1, 5, 10, 20):
+            D, I = idx.search(q, k)
+            assert D.dtype == np.float32 and I.dtype == np.int64 and D.shape == (64, k)
+            assert np.array_equal(I, g[f"{tag}_I_{t}_{k}"]), f"{f} k={k}: id lists differ from the oracle"
+            np.testing.assert_allclose(D, g[f"{tag}_D_{t}_{k}"], rtol=RTOL_F32, atol=1e-6)
+        # the reference only ever searches one query at a time (src/retrieval.py:98-102)
+        for r in range(8):
+            D1, I1 = idx.search(q[r:r + 1], 5)
+            assert np.array_equal(I1[0], g[f"{tag}_I_{t}_5"][r])
+        assert idx.last_path == "cuda-core"
+
+
+def test_read_index_of_reference_file_and_self_search(P, gold_dir):
+    d = os.path.join(gold_dir, "indices")
+    for f in os.listdir(d):
+        idx = P.read_index(os.path.join(d, f))
+        x, metric = O.read_faiss_flat(os.path.join(d, f))
+        assert idx.metric_type == metric == P.METRIC_L2 and idx.ntotal == x.shape[0]
+        D, I = idx.search(x, 1)
+        assert (I[:, 0] == np.arange(x.shape[0])).all() and (D[:, 0] == 0).all()
+        assert np.array_equal(idx.reconstruct_n(0, idx.ntotal), x)
+
+
+def test_write_index_is_byte_exact_faiss_file(P, gold_dir, tmp_path):
+    d = os.path.join(gold_dir, "indices")
+    for f in os.listdir(d):
+        idx = P.read_index(os.path.join(d, f))
+        out = tmp_path / f
+        P.write_index(idx, str(out))
+        assert open(out, "rb").read() == open(os.path.join(d, f), "rb").read()
+    # IP index gets fourcc IxFI and round-trips
+    x = np.random.default_rng(0).standard_normal((10, 32)).astype(np.float32)
+    ip = P.IndexFlatIP(32)
+    ip.add(x)
+    P.write_index(ip, str(tmp_path / "ip.index"))
+    assert open(tmp_path / "ip.index", "rb").read()[:4] == b"IxFI"
+    x2, m2 = O.read_faiss_flat(str(tmp_path / "ip.index"))
+    assert m2 == O.METRIC_IP and np.array_equal(x2, x)
+
+
+# ------------------------------------------------------------------ shapes and edge cases
+@pytest.mark.parametrize("n,d,nq,k", [(1, 8, 1, 1), (3, 5, 2, 5), (257, 100, 3, 7), (1000, 384, 1, 10),
+                                      (1000, 384, 17, 10), (4099, 512, 9, 100), (2500, 768, 5, 33),
+                                      (5000, 64, 4, 1024), (300, 1000, 2, 3)])
+@pytest.mark.parametrize("metric", [O.METRIC_L2, O.METRIC_IP])
+def test_random_fp32_exact(P, n, d, nq, k, metric):
+    rng = np.random.default_rng(n * 31 + d)
+    x = rng.standard_normal((n, d)).astype(np.float32)
+    q = rng.standard_normal((nq, d)).astype(np.float32)
+    idx = P.FlatIndex(d, metric, "fp32")
+    idx.add(x[: n // 2])
+    idx.add(x[n // 2:])                      # growth path
+    D, I = idx.search(q, k)
+    flips, Ir = _check_exact(D, I, x, q, k, metric, f"n{n} d{d}")
+    assert flips == 0 and np.array_equal(I, Ir)
+
+
+def test_empty_index_and_padding(P):
+    idx = P.IndexFlatL2(16)
+    D, I = idx.search(np.zeros((2, 16), np.float32), 3)
+    assert (I == -1).all() and (D == np.finfo(np.float32).max).all()
+    ip = P.IndexFlatIP(16)
+    D, I = ip.search(np.zeros((1, 16), np.float32), 2)
+    assert (I == -1).all() and (D == -np.finfo(np.float32).max).all()
+    idx.add(np.eye(2, 16, dtype=np.float32))
+    D, I = idx.search(np.eye(1, 16, dtype=np.float32), 4)
+    assert I[0].tolist() == [0, 1, -1, -1] and D[0, 0] == 0 and D[0, 1] == 2 and D[0, 2] == np.finfo(np.float32).max
+    D, I = idx.search(np.zeros((0, 16), np.float32), 4)
+    assert D.shape == (0, 4)
+
+
+def test_exact_duplicates_tie_order_is_id_ascending(P):
+    rng = np.random.default_rng(3)
+    base = rng.standard_normal((5, 48)).astype(np.float32)
+    x = np.concatenate([base, base, base])           # every row appears 3 times
+    for metric in (O.METRIC_L2, O.METRIC_IP):
+        idx = P.FlatIndex(48, metric)
+        idx.add(x)
+        D, I = idx.search(base, 3)
+        for r in range(5):
+            assert I[r].tolist() == [r, r + 5, r + 10]
+
+
+def test_error_codes(P):
+    idx = P.IndexFlatL2(8)
+    idx.add(np.zeros((4, 8), np.float32))
+    with pytest.raises(P.PrsError) as e:
+        idx.search(np.zeros((1, 9), np.float32), 1)          # dimension mismatch (faiss asserts)
+    assert e.value.code == -1
+    with pytest.raises(P.PrsError):
+        idx.search(np.zeros((1, 8), np.float32), 0)
+    with pytest.raises(P.PrsError):
+        idx.search(np.zeros((1, 8), np.float32), 1025)
+    with pytest.raises(P.PrsError):
+        idx.add(np.zeros((1, 7), np.float32))
+    with pytest.raises(P.PrsError) as e:
+        P.read_index("/nonexistent/file.index")
+    assert e.value.code == -3
+
+
+# ------------------------------------------------------------------ 16-bit storage, both kernel families
+@pytest.mark.parametrize("storage", ["fp16", "bf16"])
+@pytest.mark.parametrize("path", ["cuda-core", "tcgen05"])
+@pytest.mark.parametrize("metric", [O.METRIC_L2, O.METRIC_IP])
+@pytest.mark.parametrize("n,d,nq,k", [(4000, 384, 8, 10), (9000, 768, 64, 10), (3001, 512, 130, 5), (700, 100, 33, 16)])
+def test_16bit_storage_vs_oracle(P, storage, path, metric, n, d, nq, k):
+    rng = np.random.default_rng(n + d + nq)
+    x = rng.standard_normal((n, d)).astype(np.float32)
+    x /= np.linalg.norm(x, axis=1, keepdims=True)
+    q = rng.standard_normal((nq, d)).astype(np.float32)
+    q /= np.linalg.norm(q, axis=1, keepdims=True)
+    idx = P.FlatIndex(d, metric, storage)
+    idx.add(x)
+    idx.set_path(path)
+    D, I = idx.search(q, k)
+    assert idx.last_path == path
+    xs = _round_to(x, storage)
+    # the tensor-core path also rounds the queries to the storage type
+    qs = _round_to(q, storage) if path == "tcgen05" else q
+    S = O.flat_scores_f64(xs, qs, metric)
+    flips = 0
+    for r in range(nq):
+        flips += O.check_topk_against_scores(I[r], D[r], S[r], k, metric == O.METRIC_IP, rtol=RTOL_16, atol=2e-5,
+                                             what=f"{storage}/{path} q{r}")
+    # and against fp32 queries (what a caller sees) with the north-star tolerance
+    S32 = O.flat_scores_f64(xs, q, metric)
+    for r in range(nq):
+        O.check_topk_against_scores(I[r], D[r], S32[r], k, metric == O.METRIC_IP, rtol=RTOL_16, atol=2e-3 if storage == "bf16" else 3e-4,
+                                    what=f"{storage}/{path} vs fp32 queries q{r}")
+    assert flips <= nq * k * 0.05
+
+
+@pytest.mark.parametrize("storage", ["fp16", "bf16"])
+def test_16bit_container_roundtrip(P, storage, tmp_path):
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal((77, 96)).astype(np.float32)
+    idx = P.FlatIndex(96, P.METRIC_L2, storage)
+    idx.add(x)
+    p = str(tmp_path / "h.index")
+    P.write_index(idx, p)
+    assert open(p, "rb").read()[:4] == (b"PRSh" if storage == "fp16" else b"PRSb")
+    assert os.path.getsize(p) == 45 + 2 * 77 * 96
+    back = P.read_index(p, storage=storage)
+    assert np.array_equal(back.reconstruct_n(), _round_to(x, storage))
+    q = rng.standard_normal((3, 96)).astype(np.float32)
+    assert np.array_equal(back.search(q, 5)[1], idx.search(q, 5)[1])
+
+
+def test_auto_path_selection(P):
+    rng = np.random.default_rng(6)
+    x = rng.standard_normal((2048, 256)).astype(np.float32)
+    idx = P.FlatIndex(256, P.METRIC_IP, "fp16")
+    idx.add(x)
+    idx.search(rng.standard_normal((1, 256)).astype(np.float32), 10)
+    assert idx.last_path == "cuda-core"           # bandwidth-bound small batch
+    idx.search(rng.standard_normal((64, 256)).astype(np.float32), 10)
+    assert idx.last_path == "tcgen05"             # the scan is a real GEMM
+    idx.search(rng.standard_normal((64, 256)).astype(np.float32), 100)
+    assert idx.last_path == "cuda-core"           # k beyond the in-smem lists
+
+
+# ------------------------------------------------------------------ device tensors in / out
+def test_device_tensor_api_matches_host_api(P):
+    import torch
+    rng = np.random.default_rng(8)
+    x = rng.standard_normal((3000, 384)).astype(np.float32)
+    q = rng.standard_normal((12, 384)).astype(np.float32)
+    a = P.IndexFlatL2(384)
+    a.add(x)
+    b = P.IndexFlatL2(384)
+    b.add(torch.from_numpy(x).cuda())
+    Dh, Ih = a.search(q, 10)
+    Dd, Id = b.search(torch.from_numpy(q).cuda(), 10)
+    assert Dd.is_cuda and Id.dtype == torch.int64
+    assert np.array_equal(Id.cpu().numpy(), Ih) and np.array_equal(Dd.cpu().numpy(), Dh)
+    # fp16 query tensors are accepted
+    Dq, Iq = b.search(torch.from_numpy(q).cuda().half(), 10)
+    S = O.flat_scores_f64(x, torch.from_numpy(q).half().float().numpy(), O.METRIC_L2)
+    for r in range(12):
+        O.check_topk_against_scores(Iq[r].cpu().numpy(), Dq[r].cpu().numpy(), S[r], 10, False, rtol=RTOL_F32, atol=1e-5)
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        D2, I2 = b.search(torch.from_numpy(q).cuda(), 10)
+    s.synchronize()
+    assert np.array_equal(I2.cpu().numpy(), Ih)
+
+
+def test_concurrent_readers(P):
+    """gradio_luncher.py:361 runs up to 10 threads against one retriever: search must be re-entrant."""
+    import threading
+    rng = np.random.default_rng(9)
+    x = rng.standard_normal((5000, 128)).astype(np.float32)
+    qs = rng.standard_normal((10, 4, 128)).astype(np.float32)
+    idx = P.IndexFlatL2(128)
+    idx.add(x)
+    want = [O.flat_search_c(x, qs[t], 5, O.METRIC_L2, form=1)[1] for t in range(10)]
+    got = [None] * 10
+
+    def work(t):
+        for _ in range(5):
+            got[t] = idx.search(qs[t], 5)[1]
+
+    th = [threading.Thread(target=work, args=(t,)) for t in range(10)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    for t in range(10):
+        assert np.array_equal(got[t], want[t])
+
+
+# ------------------------------------------------------------------ BASELINE sizes: size-independent properties
+def test_full_size_1m_x_768_properties(P):
+    """configs[1]: 1M x 768.  Generated on device; checked by (a) planted neighbours: a query equal
+    to corpus row r must return r first with distance ~0; (b) oracle parity on the 64 queries
+    restricted to a 100k-row window around the planted rows via sharded == unsharded reasoning:
+    the global top-k restricted to the window equals the window's own top-k."""
+    import torch
+    n, d, k = 1_000_000, 768, 10
+    g = torch.Generator(device="cuda").manual_seed(1234)
+    x = torch.randn((n, d), generator=g, device="cuda", dtype=torch.float32)
+    x = torch.nn.functional.normalize(x, dim=1)
+    rows = torch.arange(0, 64, device="cuda") * 15_625 + 7
+    q = x[rows].clone()
+    for storage, path in (("fp16", "cuda-core"), ("fp16", "tcgen05"), ("bf16", "tcgen05"), ("fp32", "cuda-core")):
+        idx = P.FlatIndex(d, P.METRIC_IP, storage)
+        idx.add(x)
+        idx.set_path(path)
+        qq = q if path == "tcgen05" else q[:4]
+        D, I = idx.search(qq, k)
+        I = I.cpu().numpy()
+        D = D.cpu().numpy()
+        assert (I[:, 0] == rows[: qq.shape[0]].cpu().numpy()).all(), (storage, path)
+        assert np.all(np.abs(D[:, 0] - 1.0) < (1e-2 if storage == "bf16" else 2e-3))
+        assert (np.diff(D, axis=1) <= 0).all()
+        # window check against the oracle: every returned id inside the first 100k rows must be in
+        # the oracle's top-k of that window, in the same relative order (tie-aware)
+        xs = x[:100_000].to({"fp16": torch.float16, "bf16": torch.bfloat16, "fp32": torch.float32}[storage]).float().cpu().numpy()
+        qs = qq.cpu().numpy()
+        if path == "tcgen05":
+            qs = _round_to(qs, storage)
+        S = xs.astype(np.float64) @ qs.astype(np.float64).T
+        for r in range(qq.shape[0]):
+            inside = I[r][I[r] < 100_000]
+            if inside.size == 0:
+                continue
+            kth = D[r, -1]
+            better = np.nonzero(S[:, r] > kth + 2e-3)[0]
+            assert set(better.tolist()) <= set(inside.tolist()), (storage, path, r)
+        del idx

@@ -1,0 +1,148 @@
+"""CPU: pins the oracle (oracle/) against every fixture the reference ships for the path and
+against independent float64 brute force.  No GPU, no product code."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+
+REF_FAISS = "/root/reference/results/faiss"
+
+
+def test_manifest_matches_committed_indices(gold_dir):
+    man = json.load(open(os.path.join(gold_dir, "index_manifest.json")))
+    assert len(man) == 14                                  # the reference ships 14 IndexFlatL2 files
+    for f in os.listdir(os.path.join(gold_dir, "indices")):
+        b = open(os.path.join(gold_dir, "indices", f), "rb").read()
+        assert hashlib.sha256(b).hexdigest() == man[f]["sha256"]
+        assert len(b) == 45 + 4 * man[f]["ntotal"] * man[f]["d"] == man[f]["bytes"]
+        assert man[f]["fourcc"] == "IxF2" and man[f]["metric"] == 1      # finding 1: L2, not IP
+
+
+def test_index_file_roundtrip_is_byte_exact(gold_dir, tmp_path):
+    for f in os.listdir(os.path.join(gold_dir, "indices")):
+        src = os.path.join(gold_dir, "indices", f)
+        x, metric = O.read_faiss_flat(src)
+        dst = tmp_path / f
+        O.write_faiss_flat(str(dst), x, metric)
+        assert open(src, "rb").read() == open(dst, "rb").read()
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_FAISS), reason="reference tree only exists in the build container")
+def test_all_14_reference_indices_parse_and_self_search():
+    for f in sorted(os.listdir(REF_FAISS)):
+        x, metric = O.read_faiss_flat(os.path.join(REF_FAISS, f))
+        assert metric == O.METRIC_L2
+        D, I = O.flat_search_c(x, x, 1, O.METRIC_L2)
+        assert (I[:, 0] == np.arange(x.shape[0])).all(), f      # no duplicate rows: nearest neighbour is itself
+        assert (D[:, 0] == 0).all()
+
+
+def test_c_heap_equals_full_sort_and_float64(golden_indices):
+    rng = np.random.default_rng(0)
+    for name, (x, _) in golden_indices.items():
+        q = (x[rng.integers(0, x.shape[0], 7)] + 0.05 * rng.standard_normal((7, x.shape[1]))).astype(np.float32)
+        for metric in (O.METRIC_L2, O.METRIC_IP):
+            for k in (1, 5, 20, x.shape[0] + 3):
+                D, I = O.flat_search_c(x, q, k, metric, form=1)
+                Ds, Is = O.flat_search_c_sort(x, q, k, metric)
+                assert np.array_equal(I, Is) and np.array_equal(D, Ds)
+                S = O.flat_scores_f64(x, q, metric)
+                for r in range(q.shape[0]):
+                    O.check_topk_against_scores(I[r], D[r], S[r], k, metric == O.METRIC_IP, rtol=2e-6, atol=1e-6,
+                                                what=f"{name} q{r} k{k}")
+
+
+def test_expanded_form_and_numpy_restatement_agree(golden_indices):
+    rng = np.random.default_rng(1)
+    x, _ = golden_indices["multilingual-e5-base_drugs_word_chunks.index"]
+    q = rng.standard_normal((25, x.shape[1])).astype(np.float32)
+    q /= np.linalg.norm(q, axis=1, keepdims=True)
+    D1, I1 = O.flat_search_c(x, q, 10, O.METRIC_L2, form=0)          # nq >= 20 -> expanded, like faiss
+    D2, I2 = O.flat_search_np(x, q, 10, O.METRIC_L2, form=2, block=50)
+    O.check_topk_lists(I2, D2, I1, D1, rtol=1e-4, atol=1e-6)
+    D3, I3 = O.flat_search_np(x, q, 10, O.METRIC_IP, block=37)
+    D4, I4 = O.flat_search_c(x, q, 10, O.METRIC_IP)
+    O.check_topk_lists(I3, D3, I4, D4, rtol=1e-5, atol=1e-6)
+
+
+def test_flat_golden_vectors(gold_dir, golden_indices):
+    g = np.load(os.path.join(gold_dir, "flat_golden.npz"))
+    for t, f in enumerate(g["files"].tolist()):
+        x, _ = golden_indices[f]
+        q = g[f"q_{t}"]
+        for k in (1, 5, 10, 20):
+            D, I = O.flat_search_c(x, q, k, O.METRIC_L2, form=1)
+            assert np.array_equal(I, g[f"l2_I_{t}_{k}"]) and np.array_equal(D, g[f"l2_D_{t}_{k}"])
+            D, I = O.flat_search_c(x, q, k, O.METRIC_IP)
+            assert np.array_equal(I, g[f"ip_I_{t}_{k}"]) and np.array_equal(D, g[f"ip_D_{t}_{k}"])
+
+
+def test_k_larger_than_n_pads_with_minus_one():
+    x = np.eye(3, 8, dtype=np.float32)
+    D, I = O.flat_search_c(x, x[:1], 5, O.METRIC_L2)
+    assert I[0].tolist() == [0, 1, 2, -1, -1] and D[0, 3] == np.finfo(np.float32).max
+    D, I = O.flat_search_c(x, x[:1], 5, O.METRIC_IP)
+    assert I[0].tolist() == [0, 1, 2, -1, -1] and D[0, 3] == -np.finfo(np.float32).max
+
+
+def test_recorded_reference_retrievals_invariants(gold_dir):
+    """results/phase4_rag_evaluation_results.json: the only (id, distance, score) records the
+    reference ships.  They pin: ascending squared-L2, score == 1/(1+distance), id <-> row."""
+    g = json.load(open(os.path.join(gold_dir, "phase4_records.json")))
+    assert len(g["questions"]) == 10 and len(g["chunks"]) == 29
+    nonempty = [r for r in g["records"] if r["retrieved"]]
+    assert len(nonempty) == 20                              # distiluse-ft x {word, sentence} x 10 questions
+    for r in nonempty:
+        d = [x["distance"] for x in r["retrieved"]]
+        assert d == sorted(d) and len(d) == 5
+        for x in r["retrieved"]:
+            assert x["similarity_score"] == pytest.approx(O.dense_similarity(x["distance"]), rel=1e-7)
+            kind, _, row = x["id"].rpartition("_chunk_")
+            assert kind in ("word", "sentence") and 0 <= int(row) < 126
+
+
+def test_bm25_restatement_properties(gold_dir, golden_texts):
+    chunks, queries = golden_texts
+    texts = [c["text"] for c in chunks]
+    bm = O.BM25OkapiOracle([t.split() for t in texts])
+    S = np.stack([bm.get_scores(q.split()) for q in queries])
+    assert np.array_equal(S, np.load(os.path.join(gold_dir, "bm25_golden.npz"))["scores"])
+    # repeated query tokens add repeatedly; unknown tokens add nothing
+    tok = texts[0].split()[3]
+    assert np.array_equal(bm.get_scores([tok, tok]), 2 * bm.get_scores([tok]))
+    assert not bm.get_scores(["not-a-token-of-the-corpus"]).any()
+    # the recorded questions share almost no token with the reversed-glyph chunks (finding 6), so their
+    # score vectors are dominated by exact zeros (ties); the queries cut from the chunks are not
+    assert (S[:10] != 0).mean() < 0.25 and (S[10:] != 0).mean() > 0.5
+
+
+def test_tfidf_golden_from_sklearn(gold_dir, golden_texts):
+    chunks, queries = golden_texts
+    texts = [c["text"] for c in chunks]
+    tg = json.load(open(os.path.join(gold_dir, "tfidf_golden.json")))
+    vec, mat = O.tfidf_fit(texts)
+    assert vec.get_feature_names_out().tolist() == tg["features"]
+    gold = np.load(os.path.join(gold_dir, "tfidf_golden.npz"))
+    S = np.stack([O.tfidf_scores(vec, mat, q) for q in queries])
+    np.testing.assert_allclose(S, gold["scores"], rtol=0, atol=1e-15)
+
+
+def test_pool_oracle_matches_torch_golden(gold_dir):
+    g = np.load(os.path.join(gold_dir, "pool_golden.npz"))
+    np.testing.assert_allclose(O.mean_pool_normalize(g["hidden"], g["mask"], False), g["pooled"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(O.mean_pool_normalize(g["hidden"], g["mask"], True), g["normalized"], rtol=1e-5, atol=1e-6)
+
+
+def test_tie_rules():
+    s = np.array([0.0, 1.0, 0.0, 1.0, 0.0])
+    assert O.argsort_topk_canonical(s, 4).tolist() == [3, 1, 4, 2]          # (score desc, id desc)
+    v, i = O.canonical_topk(s.astype(np.float32), 4, largest=True)
+    assert i.tolist() == [1, 3, 0, 2]                                        # dense: (score desc, id asc)
+    # tie-aware checker accepts a different order inside a tie group and rejects a real miss
+    O.check_topk_against_scores([3, 1, 2, 4], [1, 1, 0, 0], s, 4, True, rtol=1e-6)
+    with pytest.raises(AssertionError):
+        O.check_topk_against_scores([3, 0, 2, 4], [1, 0, 0, 0], s, 4, True, rtol=1e-6)

@@ -1,0 +1,181 @@
+"""GPU: the drop-in RetrievalSystem end to end (same calls a user of src/retrieval.py makes),
+Hit@K / MRR equality with the oracle pipeline, hybrid fusion, and the sharded merge."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def P():
+    import persian_rag_system_b200 as P
+    assert P.lib().prs_device_arch(0) == 100, P._lib.last_error()
+    return P
+
+
+class FakeEncoder:
+    """Stands in for SentenceTransformer (absent here): deterministic text -> vector."""
+
+    def __init__(self, table, d):
+        self.table, self.d = table, d
+
+    def encode(self, sentences, device=None, **_):
+        out = np.zeros((len(sentences), self.d), np.float32)
+        for i, s in enumerate(sentences):
+            out[i] = self.table[s]
+        return out
+
+
+@pytest.fixture(scope="module")
+def world(gold_dir, golden_indices, golden_texts, tmp_path_factory):
+    """A 125-chunk corpus in the reference's CSV schema (src/chunking.py:45-53) whose row i is
+    `word_chunk_i`, the reference's shipped MiniLM-ft index as its dense index, and queries that are
+    seeded perturbations of corpus rows (relevance label = the perturbed row)."""
+    import pandas as pd
+    chunks_known, _ = golden_texts
+    f = "paraphrase-multilingual-MiniLM-L12-v2_finetuned_drugs_word_chunks.index"
+    x, _ = golden_indices[f]
+    n = x.shape[0]
+    rng = np.random.default_rng(77)
+    vocab = sorted({w for c in chunks_known for w in c["text"].split()})
+    texts = [" ".join(rng.choice(vocab, size=int(rng.integers(40, 150)))) for _ in range(n)]
+    rows = [{"id": f"word_chunk_{i}", "text": texts[i], "start_word": i * 125, "end_word": i * 125 + 150,
+             "num_words": len(texts[i].split()), "chunk_type": "word_based", "overlap_words": 25} for i in range(n)]
+    tmp = tmp_path_factory.mktemp("world")
+    csv = str(tmp / "drugs_word_chunks.csv")
+    pd.DataFrame(rows).to_csv(csv, index=False, encoding="utf-8")
+    g = np.load(os.path.join(gold_dir, "flat_golden.npz"))
+    q = g["q_0"]
+    queries, table, relevant = [], {}, {}
+    for i in range(q.shape[0]):
+        words = texts[i % n].split()
+        text = " ".join(words[3:9])
+        text = f"{text} #{i}"
+        queries.append({"id": f"q{i}", "question": text})
+        table[text] = q[i]
+        relevant[f"q{i}"] = [f"word_chunk_{i % n}"] if i % 3 else []          # some queries have no labels
+    return dict(csv=csv, index=os.path.join(gold_dir, "indices", f), x=x, q=q, texts=texts, queries=queries,
+                table=table, relevant=relevant, rows=rows)
+
+
+def test_dense_retriever_matches_reference_semantics(P, world):
+    r = P.RetrievalSystem(method="dense", encoder=FakeEncoder(world["table"], 384))
+    assert r.retrieve("x") == []                                     # not ready yet (src/retrieval.py:224-226)
+    assert r.load_chunks_and_index(world["csv"], world["index"]) is True
+    assert r.faiss_index.ntotal == 125 and r.is_ready
+    Dr, Ir = O.flat_search_c(world["x"], world["q"], 5, O.METRIC_L2, form=1)
+    for i, qd in enumerate(world["queries"][:20]):
+        res = r.retrieve(qd["question"], top_k=5)
+        assert [c["id"] for c, _ in res] == [f"word_chunk_{j}" for j in Ir[i]]
+        for (c, s), dist in zip(res, Dr[i]):
+            assert s == pytest.approx(1 / (1 + dist), rel=1e-5)      # src/retrieval.py:108
+        ctx, meta = r.get_contexts_for_rag(qd["question"], top_k=5, max_context_length=2000)
+        want_ctx, want_meta = O.pack_contexts(res, 2000)
+        assert ctx == want_ctx and [m["chunk_id"] for m in meta] == [m["chunk_id"] for m in want_meta]
+        assert sum(len(c) for c in ctx) <= 2000 + 3
+
+
+def test_missing_index_is_skipped_like_the_reference(P, world):
+    r = P.RetrievalSystem(method="dense", encoder=FakeEncoder(world["table"], 384))
+    assert r.load_chunks_and_index(world["csv"], "/no/such.index") is True      # src/retrieval.py:52 silently skips
+    assert r.retrieve(world["queries"][0]["question"]) == []                      # :94-95
+    assert P.RetrievalSystem(method="bm25").load_chunks_and_index("/no/such.csv") is False
+
+
+def test_dimension_mismatch_returns_empty_list(P, world):
+    """results/phase4_rag_evaluation_results.json:999-1060: wrong-d queries -> exception -> []."""
+    r = P.RetrievalSystem(method="dense", encoder=FakeEncoder({k: np.zeros(512, np.float32) for k in world["table"]}, 512))
+    assert r.load_chunks_and_index(world["csv"], world["index"])
+    assert r.retrieve(world["queries"][0]["question"], 5) == []
+
+
+def test_hit_at_k_and_mrr_identical_to_oracle_pipeline(P, world):
+    r = P.RetrievalSystem(method="dense", encoder=FakeEncoder(world["table"], 384))
+    assert r.load_chunks_and_index(world["csv"], world["index"])
+    got = r.evaluate_retrieval_quality(world["queries"], world["relevant"])
+    _, Ir = O.flat_search_c(world["x"], world["q"], 10, O.METRIC_L2, form=1)
+    ids = {qd["id"]: [f"word_chunk_{j}" for j in Ir[i]] for i, qd in enumerate(world["queries"])}
+    want = O.retrieval_quality(ids, world["queries"], world["relevant"])
+    assert got == want and 0 < got["hit_at_1"] <= got["hit_at_5"] <= 1 and got["mrr"] > 0
+
+
+@pytest.mark.parametrize("method", ["bm25", "tfidf"])
+def test_sparse_retrievers_match_oracle(P, world, method):
+    r = P.RetrievalSystem(method=method)
+    assert r.load_chunks_and_index(world["csv"])
+    texts = world["texts"]
+    if method == "bm25":
+        bm = O.BM25OkapiOracle([t.split() for t in texts])
+        score_fn = lambda q: bm.get_scores(q.split())
+    else:
+        vec, mat = O.tfidf_fit(texts)
+        score_fn = lambda q: O.tfidf_scores(vec, mat, q)
+    for qd in world["queries"][:16]:
+        sc = score_fn(qd["question"])
+        res = r.retrieve(qd["question"], top_k=10)
+        want = O.argsort_topk_canonical(sc, 10)
+        assert [c["id"] for c, _ in res] == [f"word_chunk_{j}" for j in want]
+        assert [float(s) for _, s in res] == [float(v) for v in sc[want]]
+    ids = {qd["id"]: [c["id"] for c, _ in r.retrieve(qd["question"], 10)] for qd in world["queries"]}
+    assert r.evaluate_retrieval_quality(world["queries"], world["relevant"]) == O.retrieval_quality(ids, world["queries"], world["relevant"])
+
+
+def test_hybrid_matches_reference_fusion(P, world):
+    r = P.RetrievalSystem(method="hybrid", encoder=FakeEncoder(world["table"], 384))
+    assert r.load_chunks_and_index(world["csv"], world["index"])
+    bm = O.BM25OkapiOracle([t.split() for t in world["texts"]])
+    chunks = r.chunks
+    for i, qd in enumerate(world["queries"][:12]):
+        Dr, Ir = O.flat_search_c(world["x"], world["q"][i:i + 1], 10, O.METRIC_L2, form=1)
+        dense = [(chunks[j], 1 / (1 + d)) for d, j in zip(Dr[0], Ir[0])]
+        sc = bm.get_scores(qd["question"].split())
+        sparse = [(chunks[j], sc[j]) for j in O.argsort_topk_canonical(sc, 10)]
+        want = O.hybrid_fuse(dense, sparse, 5)
+        got = r.retrieve(qd["question"], top_k=5)
+        assert [c["id"] for c, _ in got] == [c["id"] for c, _ in want]
+        np.testing.assert_allclose([s for _, s in got], [s for _, s in want], rtol=1e-6)
+
+
+def test_multi_model_retrieval(P, world):
+    m = P.MultiModelRetrieval(["models/a-model"], encoders={"a-model": FakeEncoder(world["table"], 384)})
+    m.setup_retrievers(world["csv"], {"a-model": world["index"]})
+    out = m.compare_retrieval_performance(world["queries"], world["relevant"])
+    assert set(out) == {"a-model"} and out["a-model"]["total_queries"] == len(world["queries"])
+    m.cleanup_all()
+    assert m.retrievers == {}
+
+
+# ------------------------------------------------------------------ row sharding (emulated on one device)
+@pytest.mark.parametrize("G", [2, 3, 8])
+@pytest.mark.parametrize("metric", [O.METRIC_L2, O.METRIC_IP])
+def test_sharded_equals_unsharded(P, G, metric):
+    """G shards as G sub-indices on one device + the same merge kernel the
+    multi-GPU path runs after ncclAllGather.  Sharded == unsharded bit for bit, ties included."""
+    import torch
+    from persian_rag_system_b200.sharded import merge_topk, shard_bounds
+    rng = np.random.default_rng(G)
+    base = rng.standard_normal((1500, 64)).astype(np.float32)
+    x = np.concatenate([base, base[:300], base[:100]])          # duplicates across shards -> ties on global id
+    n = x.shape[0]
+    q = np.concatenate([base[:40] + 0.01 * rng.standard_normal((40, 64)).astype(np.float32), base[:8]])
+    k = 10
+    whole = P.FlatIndex(64, metric)
+    whole.add(x)
+    Dw, Iw = whole.search(q, k)
+    Dp, Ip = [], []
+    for g in range(G):
+        lo, hi = shard_bounds(n, G, g)
+        sh = P.FlatIndex(64, metric)
+        sh.add(x[lo:hi])
+        sh.set_id_offset(lo)
+        D, I = sh.search(torch.from_numpy(q).cuda(), k)
+        Dp.append(D)
+        Ip.append(I)
+    D, I = merge_topk(torch.stack(Dp), torch.stack(Ip), largest=metric == O.METRIC_IP)
+    assert np.array_equal(I.cpu().numpy(), Iw) and np.array_equal(D.cpu().numpy(), Dw)
+    Dr, Ir = O.flat_search_c(x, q, k, metric, form=1)
+    assert np.array_equal(Iw, Ir)

@@ -1,0 +1,163 @@
+"""GPU parity: BM25 / TF-IDF scoring + top-k and the pooling epilogue vs the CPU oracle."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def P():
+    import persian_rag_system_b200 as P
+    assert P.lib().prs_device_arch(0) == 100, P._lib.last_error()
+    return P
+
+
+# ------------------------------------------------------------------ BM25
+def test_bm25_on_reference_chunks_bit_exact(P, gold_dir, golden_texts):
+    chunks, queries = golden_texts
+    texts = [c["text"] for c in chunks]
+    gold = np.load(os.path.join(gold_dir, "bm25_golden.npz"))["scores"]       # oracle scores [nq, n]
+    bm = P.BM25Index([t.split() for t in texts])
+    n = len(texts)
+    for k in (1, 5, 10, n, n + 5):
+        S, I = bm.search([q.split() for q in queries], k)
+        for r in range(len(queries)):
+            want = O.argsort_topk_canonical(gold[r], k)
+            kk = min(k, n)
+            assert I[r, :kk].tolist() == want.tolist(), f"q{r} k{k}"
+            assert np.array_equal(S[r, :kk], gold[r][want])                    # float64, bit for bit
+            assert (I[r, kk:] == -1).all()
+            # and it is a valid answer to what the reference computes (unstable argsort, finding 6)
+            ref = O.argsort_topk_reference(gold[r], k)
+            assert np.array_equal(np.sort(gold[r][ref])[::-1], S[r, :kk])
+
+
+def test_bm25_fp32_weights_within_tolerance(P, gold_dir, golden_texts):
+    chunks, queries = golden_texts
+    texts = [c["text"] for c in chunks]
+    gold = np.load(os.path.join(gold_dir, "bm25_golden.npz"))["scores"]
+    bm = P.BM25Index([t.split() for t in texts], dtype="float32")
+    S, I = bm.search([q.split() for q in queries], 10)
+    for r in range(len(queries)):
+        O.check_topk_against_scores(I[r], S[r], gold[r], 10, True, rtol=1e-5, atol=1e-9, what=f"q{r}")
+
+
+def test_bm25_random_corpus_vs_oracle(P):
+    rng = np.random.default_rng(11)
+    vocab = [f"w{i}" for i in range(3000)]
+    p = 1.0 / np.arange(1, 3001) ** 1.07
+    p /= p.sum()
+    docs = [[vocab[j] for j in rng.choice(3000, size=int(rng.integers(1, 200)), p=p)] for _ in range(20011)]
+    qs = [[vocab[j] for j in rng.choice(3000, size=int(rng.integers(1, 9)), p=p)] for _ in range(24)] + [["zzz"], []]
+    bm = P.BM25Index(docs)
+    ob = O.BM25OkapiOracle(docs)
+    S, I = bm.search(qs, 10)
+    for r, q in enumerate(qs):
+        sc = ob.get_scores(q)
+        O.check_topk_against_scores(I[r], S[r], sc, 10, True, rtol=1e-5, atol=1e-12, what=f"q{r}")
+        assert np.array_equal(S[r], sc[I[r]])                                   # exact float64 scores
+    # no query token matches: every doc scores 0, order is id descending (stable argsort reversed)
+    assert I[-1].tolist() == list(range(20010, 20000, -1)) and I[-2].tolist() == I[-1].tolist()
+    assert bm.index.last_postings > 0
+
+
+# ------------------------------------------------------------------ TF-IDF
+def test_tfidf_on_reference_chunks_bit_exact_vs_sklearn(P, gold_dir, golden_texts):
+    chunks, queries = golden_texts
+    texts = [c["text"] for c in chunks]
+    gold = np.load(os.path.join(gold_dir, "tfidf_golden.npz"))["scores"]      # sklearn cosine_similarity
+    tf = P.TfidfIndex(texts, max_features=10000, ngram_range=(1, 2))
+    for k in (1, 5, 10):
+        S, I = tf.search(queries, k)
+        for r in range(len(queries)):
+            want = O.argsort_topk_canonical(gold[r], k)
+            assert I[r].tolist() == want.tolist(), f"q{r} k{k}"
+            assert np.array_equal(S[r], gold[r][want])
+
+
+def test_tfidf_random_text_vs_sklearn(P):
+    rng = np.random.default_rng(12)
+    words = ["".join(chr(0x0627 + int(c)) for c in rng.integers(0, 30, size=int(rng.integers(2, 7)))) for _ in range(800)]
+    texts = [" ".join(rng.choice(words, size=int(rng.integers(5, 120)))) for _ in range(700)]
+    queries = [" ".join(rng.choice(words, size=int(rng.integers(1, 8)))) for _ in range(16)]
+    vec, mat = O.tfidf_fit(texts)             # > 10000 (1,2)-gram features: max_features pruning is exercised
+    tf = P.TfidfIndex(texts)
+    assert tf.vocabulary_ == {k: int(v) for k, v in vec.vocabulary_.items()}
+    S, I = tf.search(queries, 10)
+    for r, q in enumerate(queries):
+        sc = O.tfidf_scores(vec, mat, q)
+        O.check_topk_against_scores(I[r], S[r], sc, 10, True, rtol=1e-5, atol=1e-12, what=f"q{r}")
+
+
+def test_sparse_raw_csr_api_large_docs_multi_tile(P):
+    """> 8192 docs (several accumulator tiles, several CTAs per query) and a stop-word-like term."""
+    rng = np.random.default_rng(13)
+    n_docs, n_terms = 50_000, 500
+    rows = []
+    for dct in range(n_docs):
+        t = np.unique(np.concatenate([[0], rng.integers(1, n_terms, size=int(rng.integers(1, 12)))]))
+        rows.append(t)
+    indptr = np.zeros(n_docs + 1, np.int64)
+    indptr[1:] = np.cumsum([len(r) for r in rows])
+    indices = np.concatenate(rows).astype(np.int32)
+    vals = rng.random(indices.shape[0]).astype(np.float32) + 0.1
+    sp = P.SparseIndex(indptr, indices, vals, n_terms)
+    assert sp.ndocs == n_docs and sp.nnz == indices.shape[0]
+    q_terms = np.array([0, 7, 7, 499, 1000, 3, 0], np.int32)          # 1000 is out of vocabulary
+    q_indptr = np.array([0, 5, 7], np.int64)
+    q_w = np.array([1.0, 0.5, 0.5, 2.0, 9.0, 1.0, 0.25])
+    S, I = sp.search(q_indptr, q_terms, q_w, 20)
+    import scipy.sparse as ssp
+    M = ssp.csr_matrix((vals.astype(np.float64), indices, indptr), shape=(n_docs, n_terms)).tocsc()
+    for r in range(2):
+        sc = np.zeros(n_docs)
+        for e in range(q_indptr[r], q_indptr[r + 1]):
+            if q_terms[e] < n_terms:
+                sc += q_w[e] * M[:, q_terms[e]].toarray().ravel()
+        O.check_topk_against_scores(I[r], S[r], sc, 20, True, rtol=1e-6, atol=1e-12, what=f"q{r}")
+        assert np.array_equal(S[r], sc[I[r]])
+
+
+# ------------------------------------------------------------------ pooling epilogue
+def test_pool_golden(P, gold_dir):
+    import torch
+    g = np.load(os.path.join(gold_dir, "pool_golden.npz"))
+    h = torch.from_numpy(g["hidden"]).cuda()
+    m = torch.from_numpy(g["mask"]).cuda()
+    out = P.mean_pool_normalize(h, m, False).cpu().numpy()
+    np.testing.assert_allclose(out, g["pooled"], rtol=1e-5, atol=1e-6)
+    out = P.mean_pool_normalize(h, m, True).cpu().numpy()
+    np.testing.assert_allclose(out, g["normalized"], rtol=1e-5, atol=1e-6)
+    assert not np.isnan(out).any()                       # the fully-masked row (len 0) stays finite
+
+
+@pytest.mark.parametrize("B,T,H,dtype", [(1, 128, 384, "float32"), (32, 128, 768, "float16"), (16, 512, 768, "bfloat16"), (3, 7, 512, "float32")])
+def test_pool_random_vs_torch(P, B, T, H, dtype):
+    import torch
+    g = torch.Generator(device="cuda").manual_seed(B * T + H)
+    h = torch.randn((B, T, H), generator=g, device="cuda").to(getattr(torch, dtype))
+    lens = torch.randint(1, T + 1, (B,), generator=g, device="cuda")
+    mask = (torch.arange(T, device="cuda")[None, :] < lens[:, None]).to(torch.int64)
+    me = mask.unsqueeze(-1).float()
+    pooled = (h.float() * me).sum(1) / me.sum(1).clamp(min=1e-9)
+    for normalize in (False, True):
+        want = torch.nn.functional.normalize(pooled, p=2, dim=1) if normalize else pooled
+        got = P.mean_pool_normalize(h, mask, normalize)
+        torch.testing.assert_close(got, want, rtol=1e-5, atol=1e-5)
+
+
+def test_pool_then_search_stays_on_device(P):
+    """f-3: encoder output -> pool/normalise kernel -> flat search, no host hop in between."""
+    import torch
+    g = torch.Generator(device="cuda").manual_seed(21)
+    corpus_h = torch.randn((500, 16, 384), generator=g, device="cuda")
+    cmask = torch.ones((500, 16), dtype=torch.int64, device="cuda")
+    emb = P.mean_pool_normalize(corpus_h, cmask, True)
+    idx = P.IndexFlatL2(384)
+    idx.add(emb)
+    D, I = idx.search(P.mean_pool_normalize(corpus_h[:9], cmask[:9], True), 1)
+    assert I[:, 0].tolist() == list(range(9)) and float(D.abs().max()) < 1e-6
