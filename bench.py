@@ -1,0 +1,422 @@
+#!/usr/bin/env python
+"""bench.py -- QPS @ k=10 of the exact flat search (the hot path of src/retrieval.py:102) on B200.
+
+Workload (BASELINE.json configs[1]): multilingual-e5-base shape, d = 768, 1 M synthetic unit-norm
+chunks, cosine == inner product, k = 10, fp16 storage / fp32 accumulate.  One STEP = one batch of
+`--batch` queries (default 64, the top of the north-star's bandwidth-bound range) searched against
+the whole corpus: scan + fused top-k + merge.  The corpus (1.536 GB) is 12x the 126 MB L2, so every
+step streams it from HBM ("inputs larger than L2"); when a shard is smaller than 4x L2 (N > 2 GPUs)
+the L2 is flushed between steps and steps are timed one by one.
+
+  python bench.py [--gpus N --steps K --warmup W]          this engine (libprs.so), one rank per GPU
+  python bench.py --impl reference [...]                   the CPU implementation on the host cores
+
+N > 1 (torchrun): STRONG scaling -- the same 1 M rows are row-sharded over the ranks, every rank
+scans its block, the [B, k] lists are all-gathered over NVLink and merged on the device
+(SURVEY.md 8e).  value = queries answered per second by the whole job.
+
+JSON keys beyond the base contract: `roofline` (scan kernel, HBM bound, timed with CUDA events on
+the launching stream inside the timed region), `cpu_baseline` (oracle port timed on the host cores,
+rank 0, N = 1), `e2e` (same metric through the C-ABI host entry point, pinned host buffers, copies
+inside the timed region), `sweep` (batch 1..1024, device-resident, outside the K timed steps).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+
+METRIC_NAME = "QPS @k=10, 1M x 768 corpus (exact flat search)"
+L2_BYTES = 126 * 1024 * 1024
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--rows", type=int, default=1_000_000)
+    ap.add_argument("--d", type=int, default=768)
+    ap.add_argument("--k", type=int, default=10)
+    ap.add_argument("--batch", type=int, default=64)
+    ap.add_argument("--storage", default="fp16", choices=["fp16", "bf16", "fp32"])
+    ap.add_argument("--metric", default="ip", choices=["ip", "l2"])
+    ap.add_argument("--path", default="auto", choices=["auto", "cuda-core", "tcgen05"])
+    ap.add_argument("--no-sweep", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sweep-out", default="")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        j = json.load(open(p))
+        return float(j["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, copy read+write)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.rows = []
+        self.proc = None
+        self.gpu = gpu_index
+        self.on = False
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+        except Exception:
+            self.proc = None
+            return
+        threading.Thread(target=self._read, daemon=True).start()
+        time.sleep(0.35)
+
+    def _read(self):
+        for line in self.proc.stdout:
+            if self.on:
+                self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+
+    def summary(self):
+        sm, mx, reasons = [], 0.0, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx = max(mx, float(r[2]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU leg: the oracle port (faiss IndexFlat restated: sgemm blocks + threshold/heap), all host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_search_timed(x32, q, k, metric_code, budget_s, min_reps=1):
+    from oracle import oracle as O
+    O.flat_search_np_threshold(x32[: min(len(x32), 131072)], q, k, metric_code)       # warm BLAS threads
+    times, res = [], None
+    t_all = time.perf_counter()
+    while len(times) < min_reps or (time.perf_counter() - t_all) < budget_s:
+        t0 = time.perf_counter()
+        res = O.flat_search_np_threshold(x32, q, k, metric_code)
+        times.append(time.perf_counter() - t0)
+        if len(times) >= 50:
+            break
+    return times, res
+
+
+def run_reference(a):
+    """--impl reference: faiss-cpu is not installable here (no wheel, no network), so the reference
+    arm is the oracle port of faiss IndexFlat.search on the host cores, same config and metric."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    from oracle import oracle as O
+    metric_code = O.METRIC_IP if a.metric == "ip" else O.METRIC_L2
+    g = torch.Generator().manual_seed(1234)
+    x = torch.randn(a.rows, a.d, generator=g)
+    x /= x.norm(dim=1, keepdim=True)
+    if a.storage != "fp32":
+        x = x.to(torch.float16 if a.storage == "fp16" else torch.bfloat16).float()
+    x32 = x.numpy()
+    gq = torch.Generator().manual_seed(4321)
+    Q = torch.randn(a.warmup + a.steps, a.batch, a.d, generator=gq)
+    Q /= Q.norm(dim=2, keepdim=True)
+    Q = Q.numpy()
+    for w in range(a.warmup):
+        O.flat_search_np_threshold(x32, Q[w], a.k, metric_code)
+    t0 = time.perf_counter()
+    for s in range(a.steps):
+        O.flat_search_np_threshold(x32, Q[a.warmup + s], a.k, metric_code)
+    dt = time.perf_counter() - t0
+    qps = a.steps * a.batch / dt
+    cores = host_threads()
+    sample = f"full workload per step: {a.batch} queries x {a.rows} x {a.d} fp32 rows, k={a.k}"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC_NAME, "value": qps, "unit": "queries/s", "n_gpus": a.gpus,
+        "steps": a.steps, "warmup": a.warmup, "ms_per_step": dt / a.steps * 1e3, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(a, a.gpus),
+        "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port", "sample": sample,
+                         "note": "faiss-cpu/rank_bm25 wheels absent; numpy+OpenBLAS restatement of faiss IndexFlat.search"},
+        "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def workload_config(a, world):
+    return {"workload": f"configs[1]: multilingual-e5-base shape d={a.d}, {a.rows} synthetic unit-norm chunks, "
+                        f"exact {'cosine/IP' if a.metric == 'ip' else 'L2'} search, k={a.k}, 1xB200",
+            "rows": a.rows, "d": a.d, "k": a.k, "batch": a.batch, "storage": a.storage, "metric": a.metric,
+            "sharding": f"rows/{world}" if world > 1 else "none",
+            "cache": "inputs larger than L2 (corpus shard vs 126 MB L2)"}
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def run_b200(a):
+    import torch
+    import torch.distributed as dist
+    import persian_rag_system_b200 as P
+    from persian_rag_system_b200.sharded import ShardedFlatIndex, shard_bounds
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device: libprs has no CPU path"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    L = P.lib()
+    metric_code = P.METRIC_INNER_PRODUCT if a.metric == "ip" else P.METRIC_L2
+    tdt = {"fp16": torch.float16, "bf16": torch.bfloat16, "fp32": torch.float32}[a.storage]
+    es = 4 if a.storage == "fp32" else 2
+
+    # ---- corpus: on-device Philox, unit-norm rows in fp32, cast to storage ----
+    lo, hi = shard_bounds(a.rows, world, rank)
+    n_local = hi - lo
+    sh = ShardedFlatIndex(a.d, metric_code, a.storage, device=local)
+    idx = sh.local
+    idx.reserve(n_local)
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    slab = max(1, (256 << 20) // (a.d * 4))
+    added = 0
+    while added < n_local:
+        c = min(slab, n_local - added)
+        xb = torch.randn(c, a.d, generator=gen, device=dev)
+        xb /= xb.norm(dim=1, keepdim=True)
+        idx.add(xb.to(tdt))
+        added += c
+    del xb
+    sh.offset, sh.ntotal_global = lo, a.rows
+    idx.set_id_offset(lo)
+    idx.set_path(a.path)
+    torch.cuda.synchronize()
+
+    gq = torch.Generator(device=dev).manual_seed(4321)              # same queries on every rank
+    nbatches = a.warmup + a.steps
+    Qd = torch.randn(nbatches, a.batch, a.d, generator=gq, device=dev)
+    Qd /= Qd.norm(dim=2, keepdim=True)
+    Qh = torch.empty((nbatches, a.batch, a.d), dtype=torch.float32).pin_memory()
+    Qh.copy_(Qd)
+    Dh = torch.empty((a.batch, a.k), dtype=torch.float32).pin_memory()
+    Ih = torch.empty((a.batch, a.k), dtype=torch.int64).pin_memory()
+
+    pitch = (a.d + 63) // 64 * 64
+    shard_bytes = n_local * pitch * es
+    flush = shard_bytes < 4 * L2_BYTES
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if flush else None
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_device(i):
+        return sh.search(Qd[i], a.k)
+
+    # ---- device-resident throughput: `value` ----
+    for w in range(a.warmup):
+        step_device(w)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    idx.set_timing(True)
+    idx.scan_time()
+    launches0 = L.prs_launch_count()
+    sampler.on = True
+    barrier()
+    if not flush:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for s in range(a.steps):
+            step_device(a.warmup + s)
+        e1.record()
+        barrier()
+        dev_ms = e0.elapsed_time(e1)
+    else:
+        evs = []
+        for s in range(a.steps):
+            flush_buf.fill_(s & 0xFF)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            step_device(a.warmup + s)
+            e1.record()
+            evs.append((e0, e1))
+        barrier()
+        dev_ms = sum(x.elapsed_time(y) for x, y in evs)
+    sampler.on = False
+    launches = L.prs_launch_count() - launches0
+    scan_ms, scan_launches = idx.scan_time()
+    idx.set_timing(False)
+    last_path = idx.last_path
+
+    # ---- end to end through the host entry point: pinned host queries in, host (D, I) out ----
+    def step_e2e(i):
+        if world == 1:
+            idx.search_into(Qh[i].data_ptr(), a.batch, a.k, Dh.data_ptr(), Ih.data_ptr())
+        else:
+            qd = Qh[i].to(dev, non_blocking=True)
+            D, I = sh.search(qd, a.k)
+            Dh.copy_(D, non_blocking=True)
+            Ih.copy_(I, non_blocking=True)
+            torch.cuda.synchronize()
+
+    for w in range(a.warmup):
+        step_e2e(w)
+    barrier()
+    t0 = time.perf_counter()
+    for s in range(a.steps):
+        if flush:
+            flush_buf.fill_(s & 0xFF)
+        step_e2e(a.warmup + s)
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+    if rank == 0:
+        sampler.stop()
+    last_I = Ih.numpy().copy()
+    last_D = Dh.numpy().copy()
+
+    # max over ranks
+    t = torch.tensor([dev_ms, e2e_ms, scan_ms / max(scan_launches, 1)], dtype=torch.float64, device=dev)
+    cnt = torch.tensor([launches], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    dev_ms, e2e_ms, scan_avg_ms = (float(v) for v in t.tolist())
+    launches = int(cnt.item())
+
+    qps = a.steps * a.batch / (dev_ms * 1e-3)
+    qps_e2e = a.steps * a.batch / (e2e_ms * 1e-3)
+    peak, peak_src = peaks()
+    alg_bytes = n_local * a.d * es + (4 * n_local if a.metric == "l2" else 0)
+    achieved = alg_bytes / (scan_avg_ms * 1e-3) / 1e9 if scan_avg_ms > 0 else 0.0
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")          # per-launch dram bytes from the committed ncu capture
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get(f"{a.storage}_{a.rows // world}x{a.d}_b{a.batch}_{last_path}")
+        except Exception:
+            traffic = None
+
+    out = {
+        "metric": METRIC_NAME, "value": qps, "unit": "queries/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": dev_ms / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": {"fp16": "f16 storage, f32 accumulate", "bf16": "bf16 storage, f32 accumulate", "fp32": "f32"}[a.storage],
+        "data": "synthetic", "config": workload_config(a, world), "kernel_path": last_path,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic, "peak_source": peak_src, "kernel": "flat_scan_umma_kernel" if last_path == "tcgen05" else "flat_scan_simt_kernel",
+                     "bytes_per_launch": alg_bytes, "avg_launch_ms": scan_avg_ms, "launches_timed": scan_launches,
+                     "frac_of_nominal_8TBs": achieved / 8000.0,
+                     "share_of_step": scan_avg_ms * (scan_launches / max(a.steps, 1)) / (dev_ms / a.steps)},
+        "e2e": {"value": qps_e2e, "unit": "queries/s", "h2d_bytes_per_step": a.batch * a.d * 4,
+                "d2h_bytes_per_step": a.batch * a.k * 12, "ms_per_step": e2e_ms / a.steps,
+                "api": "prs_index_search_host (pinned host q, D, I)" if world == 1 else "ShardedFlatIndex.search with pinned H2D/D2H"},
+        "gpu_launches": launches,
+        "l2_flush_between_steps": bool(flush),
+    }
+
+    if rank == 0:
+        out["clocks"] = sampler.summary()
+
+    # ---- batch sweep (device resident, 1 GPU): the B = 1..1024 picture of configs[1] ----
+    if world == 1 and not a.no_sweep:
+        sweep = []
+        for B in (1, 2, 4, 8, 16, 32, 64, 128, 256, 512, 1024):
+            q = torch.randn(B, a.d, generator=gq, device=dev)
+            q /= q.norm(dim=1, keepdim=True)
+            for _ in range(3):
+                idx.search(q, a.k)
+            iters = 20 if B <= 256 else 8
+            torch.cuda.synchronize()
+            idx.set_timing(True); idx.scan_time()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(iters):
+                idx.search(q, a.k)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / iters
+            sms, sn = idx.scan_time()
+            idx.set_timing(False)
+            gbs = alg_bytes / (ms * 1e-3) / 1e9
+            sweep.append({"batch": B, "ms": round(ms, 4), "qps": round(B / (ms * 1e-3), 1), "path": idx.last_path,
+                          "corpus_gbs": round(gbs, 1), "frac_hbm": round(gbs / peak, 4),
+                          "scan_ms": round(sms / iters, 4), "tflops": round(2.0 * n_local * a.d * B / (ms * 1e-3) / 1e12, 2)})
+        out["sweep"] = sweep
+        if a.sweep_out:
+            json.dump(sweep, open(a.sweep_out, "w"), indent=1)
+
+    # ---- CPU baseline beside it (rank 0, N = 1): oracle port on the same corpus and queries ----
+    if world == 1 and rank == 0 and not a.no_cpu_baseline:
+        from oracle import oracle as O
+        x32 = idx.reconstruct_n(0, n_local)                       # the stored (rounded) rows, as fp32
+        qlast = Qh[nbatches - 1].numpy()
+        times, (Dc, Ic) = cpu_search_timed(x32, qlast, a.k, O.METRIC_IP if a.metric == "ip" else O.METRIC_L2, budget_s=12.0)
+        cpu_qps = a.batch / float(np.median(times))
+        out["cpu_baseline"] = {"value": cpu_qps, "unit": "queries/s", "cores": host_threads(), "kind": "port",
+                               "sample": f"{len(times)} x (1 batch of {a.batch} queries over all {n_local} rows, fp32), median",
+                               "ms_per_batch": float(np.median(times)) * 1e3,
+                               "note": "faiss-cpu wheel absent: numpy/OpenBLAS restatement of faiss IndexFlat.search"}
+        # parity of the timed GPU result (last e2e step) against the CPU port: ids identical except ties within 1e-3
+        try:
+            qh = torch.from_numpy(qlast).to(tdt).float().numpy() if last_path == "tcgen05" else qlast
+            if last_path == "tcgen05":
+                Dc, Ic = O.flat_search_np_threshold(x32, qh, a.k, O.METRIC_IP if a.metric == "ip" else O.METRIC_L2)
+            flips = O.check_topk_lists(last_I, last_D, Ic, Dc, rtol=1e-3, atol=2e-5, what="bench parity")
+            out["parity"] = {"queries": a.batch, "k": a.k, "id_positions_differing_within_tie_tolerance": int(flips),
+                             "identical_lists": bool(np.array_equal(last_I, Ic))}
+        except AssertionError as e:
+            out["parity"] = {"error": str(e)[:300]}
+
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)
+
+
+if __name__ == "__main__":
+    main()

@@ -96,6 +96,13 @@ int prs_index_set_path(prs_index* idx, int path);
 /* which family the last search on this index used (1 or 2), and its main kernel's name */
 int prs_index_last_path(const prs_index* idx);
 
+/* bench instrumentation (bench.py's roofline): while enabled, every launch of the scan kernel
+ * (the dominant kernel of a search) is bracketed by CUDA events on the launching stream.
+ * prs_index_scan_time synchronises them, returns the summed device time and the number of
+ * launches since the previous call, and resets both. */
+int prs_index_set_timing(prs_index* idx, int enable);
+int prs_index_scan_time(prs_index* idx, double* total_ms, int64_t* launches);
+
 /* copy rows [i0, i0+n) back as float32 (index.reconstruct_n) */
 int prs_index_reconstruct_host(prs_index* idx, int64_t i0, int64_t n, float* out);
 

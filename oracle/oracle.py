@@ -170,13 +170,63 @@ def flat_search_np(x, q, k: int, metric: int = METRIC_L2, form: int = 2, block: 
     return D, I
 
 
+def flat_search_np_threshold(x, q, k: int, metric: int = METRIC_L2, block: int = 65536,
+                             x_sqnorm: np.ndarray | None = None):
+    """Same result as flat_search_np (expanded form), organised the way faiss's nq >= 20 path is
+    (exhaustive_inner_product_blas / exhaustive_L2sqr_blas): one sgemm per corpus block (all BLAS
+    threads), then each score is compared with the query's current k-th best and only the rare
+    survivors touch the heap.  This is the CPU baseline bench.py times ("port")."""
+    x = np.asarray(x)
+    q = np.ascontiguousarray(q, dtype=np.float32)
+    n, d = x.shape
+    nq = q.shape[0]
+    largest = metric == METRIC_IP
+    fill = -np.finfo(np.float32).max if largest else np.finfo(np.float32).max
+    D = np.full((nq, k), fill, np.float32)
+    I = np.full((nq, k), -1, np.int64)
+    thr = np.full(nq, np.inf, np.float32)            # key = -ip or +l2; admit when key <= thr
+    bv = [np.empty(0, np.float32) for _ in range(nq)]
+    bi = [np.empty(0, np.int64) for _ in range(nq)]
+    qn = (q * q).sum(1) if metric == METRIC_L2 else None
+    for b0 in range(0, n, block):
+        xb = x[b0:b0 + block]
+        if xb.dtype != np.float32:
+            xb = xb.astype(np.float32)
+        s = q @ xb.T
+        if metric == METRIC_L2:
+            xn = (xb * xb).sum(1) if x_sqnorm is None else x_sqnorm[b0:b0 + block]
+            s = qn[:, None] + xn[None, :] - 2.0 * s
+            np.maximum(s, 0.0, out=s)
+            key = s
+        else:
+            key = -s
+        # survivors per query: one vectorised compare + count, then index only the rows that have any
+        mask = key <= thr[:, None]
+        for i in np.nonzero(mask.any(axis=1))[0]:
+            c = np.nonzero(mask[i])[0]
+            v = np.concatenate([bv[i], s[i, c]])
+            ii = np.concatenate([bi[i], c.astype(np.int64) + b0])
+            bv[i], bi[i] = canonical_topk(v, k, largest, ii)
+            if bv[i].shape[0] == k:
+                thr[i] = -bv[i][-1] if largest else bv[i][-1]
+    for i in range(nq):
+        m = bv[i].shape[0]
+        D[i, :m] = bv[i]
+        I[i, :m] = bi[i]
+    return D, I
+
+
 def flat_scores_f64(x, q, metric: int = METRIC_L2) -> np.ndarray:
     """Full [nq, n] score matrix in float64 (ground truth for tie-aware checks; small inputs)."""
     x = np.asarray(x, dtype=np.float64)
     q = np.asarray(q, dtype=np.float64)
     if metric == METRIC_IP:
         return q @ x.T
-    return ((q[:, None, :] - x[None, :, :]) ** 2).sum(-1)
+    if x.shape[0] * q.shape[0] * x.shape[1] <= 2e7:
+        return ((q[:, None, :] - x[None, :, :]) ** 2).sum(-1)
+    # large inputs: expanded form in float64 (cancellation error ~1e-16 * norms, far below tolerance)
+    s = (q * q).sum(1)[:, None] + (x * x).sum(1)[None, :] - 2.0 * (q @ x.T)
+    return np.maximum(s, 0.0)
 
 
 # --------------------------------------------------------------------------------------

@@ -153,6 +153,7 @@ struct prs_index {
     bool ws_used = false;
     DevBuf lists, cand, cand_cnt, qf32, qnorm, qlow, hD, hI, hQ, stage;
     UmmaState umma;
+    ScanTimer timer;
 };
 
 static int index_grow(prs_index* idx, long long n_total) {
@@ -285,7 +286,9 @@ static int search_simt(prs_index* idx, const float* qf, int q_stride, long long 
         p.lists = (u64*)idx->lists.p; p.cand = (u64*)idx->cand.p; p.cand_cnt = (int*)idx->cand_cnt.p;
         p.nq_total = (int)nq; p.q0 = (int)done; p.sortn = sortn;
         const size_t smem = 512 + qbytes + (size_t)stages * tile_bytes;
+        idx->timer.begin(st);
         if ((rc = launch_simt(idx->storage, idx->metric == PRS_METRIC_L2, QB, R, p, grid, smem, st))) return rc;
+        idx->timer.end(st);
         done += QB;
     }
     return launch_merge(idx, grid, nq, k, idx->metric == PRS_METRIC_L2 ? 1 : 0, nullptr, D, I, st);
@@ -334,7 +337,7 @@ static int search_device_impl(prs_index* idx, const void* q, int qdtype, long lo
         PRS_LAUNCH_CHECK();
         int parts = 0;
         if ((rc = search_umma(idx->umma, idx->x, idx->xnorm, idx->n, idx->d, idx->pitch, idx->storage, idx->metric, idx->sm_count,
-                              qf, nq, k, idx->cand, idx->cand_cnt, &parts, st))) return rc;
+                              qf, nq, k, idx->cand, idx->cand_cnt, &parts, st, &idx->timer))) return rc;
         return launch_merge(idx, parts, nq, k, idx->metric == PRS_METRIC_L2 ? 2 : 0, (const float*)idx->qnorm.p, D, I, st);
     }
     idx->last_path = 1;
@@ -443,6 +446,22 @@ int prs_index_set_path(prs_index* idx, int path) {
     if (!idx || path < 0 || path > 2) { set_error("set_path: bad arguments"); return PRS_EINVAL; }
     idx->path_force = path;
     return 0;
+}
+
+int prs_index_set_timing(prs_index* idx, int enable) {
+    if (!idx) { set_error("null index"); return PRS_EINVAL; }
+    std::lock_guard<std::mutex> lock(idx->mu);
+    idx->timer.enabled = enable != 0;
+    return 0;
+}
+int prs_index_scan_time(prs_index* idx, double* total_ms, int64_t* launches) {
+    if (!idx || !total_ms || !launches) { set_error("scan_time: bad arguments"); return PRS_EINVAL; }
+    DeviceGuard g(idx->device);
+    std::lock_guard<std::mutex> lock(idx->mu);
+    long long n = 0;
+    int rc = idx->timer.collect(total_ms, &n);
+    *launches = n;
+    return rc;
 }
 
 int prs_index_search_device(prs_index* idx, const void* q, int qdtype, int64_t nq, int k, float* D, int64_t* I, void* stream) {

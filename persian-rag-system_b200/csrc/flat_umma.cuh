@@ -348,7 +348,7 @@ static inline int umma_make_tmap(UmmaState& st, const void* x, long long n, int 
 
 static inline int search_umma(UmmaState& st, const void* x, const float* xnorm, long long n, int d, int pitch, int storage,
                               int metric, int sm_count, const float* qf, long long nq, int k, DevBuf& cand, DevBuf& cand_cnt,
-                              int* parts_out, cudaStream_t stream) {
+                              int* parts_out, cudaStream_t stream, ScanTimer* timer = nullptr) {
     const int tile_n = umma_tile_n(pitch);
     if (n > 0x7FFFFFFFll - tile_n) { set_error("tcgen05 path: more than 2^31 rows per shard"); return PRS_EUNSUP; }
     int rc;
@@ -378,6 +378,7 @@ static inline int search_umma(UmmaState& st, const void* x, const float* xnorm, 
         p.k = k; p.l2 = metric == PRS_METRIC_L2; p.stages = stages; p.is_bf16 = storage == PRS_BF16;
         p.nq_total = (int)nq; p.q0 = (int)q0;
         p.cand = (u64*)cand.p; p.cand_cnt = (int*)cand_cnt.p;
+        if (timer) timer->begin(stream);
         if (tile_n == 128) {
             PRS_CUDA(cudaFuncSetAttribute(flat_scan_umma_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             flat_scan_umma_kernel<128><<<grid, UMMA_THREADS, smem, stream>>>(st.tmap, p);
@@ -385,6 +386,7 @@ static inline int search_umma(UmmaState& st, const void* x, const float* xnorm, 
             PRS_CUDA(cudaFuncSetAttribute(flat_scan_umma_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             flat_scan_umma_kernel<64><<<grid, UMMA_THREADS, smem, stream>>>(st.tmap, p);
         }
+        if (timer) timer->end(stream);
         PRS_LAUNCH_CHECK();
     }
     *parts_out = grid;

@@ -6,6 +6,8 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <utility>
+#include <vector>
 
 #include "../../include/prs.h"
 
@@ -63,6 +65,35 @@ struct DevBuf {
         return 0;
     }
     void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+};
+
+// bench instrumentation: brackets the dominant (scan) kernel launches with CUDA events on the
+// launching stream; collect() synchronises them and returns the summed device time.
+struct ScanTimer {
+    bool enabled = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev;
+    void begin(cudaStream_t st) {
+        if (!enabled) return;
+        cudaEvent_t a, b;
+        cudaEventCreate(&a); cudaEventCreate(&b);
+        cudaEventRecord(a, st);
+        ev.emplace_back(a, b);
+    }
+    void end(cudaStream_t st) { if (enabled && !ev.empty()) cudaEventRecord(ev.back().second, st); }
+    int collect(double* total_ms, long long* launches) {
+        double tot = 0.0;
+        for (auto& e : ev) {
+            float ms = 0.f;
+            cudaError_t r = cudaEventSynchronize(e.second);
+            if (r == cudaSuccess) r = cudaEventElapsedTime(&ms, e.first, e.second);
+            cudaEventDestroy(e.first); cudaEventDestroy(e.second);
+            if (r != cudaSuccess) { ev.clear(); set_error("scan timer: %s", cudaGetErrorString(r)); return PRS_ECUDA; }
+            tot += ms;
+        }
+        *total_ms = tot; *launches = (long long)ev.size();
+        ev.clear();
+        return 0;
+    }
 };
 
 }  // namespace prs

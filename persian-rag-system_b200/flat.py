@@ -92,6 +92,16 @@ class FlatIndex:
         code = {"auto": 0, "cuda-core": 1, "tcgen05": 2, 0: 0, 1: 1, 2: 2}[path]
         check(self._L.prs_index_set_path(self._h, code))
 
+    def set_timing(self, enable: bool) -> None:
+        """Bracket every scan-kernel launch with CUDA events on its stream (bench instrumentation)."""
+        check(self._L.prs_index_set_timing(self._h, 1 if enable else 0))
+
+    def scan_time(self):
+        """(summed scan-kernel device time in ms, launches) since the previous call; synchronises."""
+        ms, n = ctypes.c_double(0.0), ctypes.c_int64(0)
+        check(self._L.prs_index_scan_time(self._h, ctypes.byref(ms), ctypes.byref(n)))
+        return float(ms.value), int(n.value)
+
     def set_id_offset(self, offset: int) -> None:
         check(self._L.prs_index_set_id_offset(self._h, int(offset)))
 
