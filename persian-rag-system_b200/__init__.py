@@ -7,6 +7,7 @@ sm_100a CUDA in `csrc/`, reached through the C ABI in `include/prs.h` (ctypes). 
 CPU compute path in this package.
 """
 from ._lib import (BF16, F16, F32, F64, MAX_K, METRIC_INNER_PRODUCT, METRIC_L2, PrsError, build, lib)
+METRIC_IP = METRIC_INNER_PRODUCT      # short alias (faiss spells it METRIC_INNER_PRODUCT)
 from .flat import FlatIndex, IndexFlatIP, IndexFlatL2, read_index, write_index
 from .sparse import BM25Index, SparseIndex, TfidfIndex
 from .pooling import mean_pool_normalize
@@ -17,5 +18,5 @@ __all__ = [
     "FlatIndex", "IndexFlatL2", "IndexFlatIP", "read_index", "write_index",
     "SparseIndex", "BM25Index", "TfidfIndex", "mean_pool_normalize",
     "RetrievalSystem", "MultiModelRetrieval", "ShardedFlatIndex",
-    "METRIC_L2", "METRIC_INNER_PRODUCT", "F32", "F16", "BF16", "F64", "MAX_K", "PrsError", "build", "lib",
+    "METRIC_L2", "METRIC_INNER_PRODUCT", "METRIC_IP", "F32", "F16", "BF16", "F64", "MAX_K", "PrsError", "build", "lib",
 ]

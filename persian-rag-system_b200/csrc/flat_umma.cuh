@@ -43,6 +43,7 @@ struct UmmaParams {
     int nq_total, q0;
     u64* cand;              // [grid][nq_total][k]
     int* cand_cnt;          // [grid][nq_total]
+    uint32_t* boot;         // [grid][128] ord(best score of the CTA's first tile) + 1 counter; zeroed per launch
 };
 
 // ---------------- PTX wrappers (tcgen05 / TMA) ----------------
@@ -109,7 +110,7 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
 __device__ __noinline__ float umma_topk_insert(u64* list, int k, float s, uint32_t id, float thr) {
     const u64 key = make_key<PRS_TIE_LOW_ID>(s, id);
     u64 last = list[(k - 1) * UMMA_M];
-    if (key <= last) return thr;
+    if (key <= last) return thr;   // thr >= own k-th already
     int pos = k - 1;
     while (pos > 0) {
         const u64 up = list[(pos - 1) * UMMA_M];
@@ -226,13 +227,46 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) flat_scan_umma_kernel(const _
         }
     } else {
         // ---------------- epilogue: one thread per query ----------------
+        // Queries are spread over the four lane quarters (query i -> TMEM lane (i&3)*32 + (i>>2)) so
+        // that a partly filled pass loads the four epilogue warps evenly.
         const int qd = warp & 3;
         const int m = qd * 32 + lane;
-        const bool qvalid = m < p.nq;
+        const int qi = (lane << 2) | qd;
+        const bool qvalid = qi < p.nq;
         u64* mylist = lists + m;
         float* wnorm = snorm + (warp - 2) * TILE_N;
         const uint32_t lane_addr = tmem_base + ((uint32_t)(qd * 32) << 16) + D_OFF;
-        float thr = -INFINITY;
+        const int G = (int)gridDim.x;
+        float thr_boot = -INFINITY;     // lower bound of the GLOBAL k-th best score (see bootstrap below)
+        float thr = -INFINITY;          // admission threshold = max(thr_boot, this CTA's k-th best)
+        bool boot_done = false;
+
+        // k-th largest of the first-tile maxima the CTAs have published so far.  Those are scores of
+        // distinct rows, so the value is a valid lower bound of the global k-th best: pruning with it
+        // is exact, and it removes the ~k*ln(rows per CTA / k) warm-up insertions each CTA would
+        // otherwise pay to discover the threshold on its own.
+        auto refresh_boot = [&]() {
+            const int published = (int)__ldcg(reinterpret_cast<const unsigned int*>(p.boot + (size_t)G * UMMA_M));
+            uint32_t top[UMMA_MAX_K];
+#pragma unroll
+            for (int j = 0; j < UMMA_MAX_K; ++j) top[j] = 0u;
+            for (int g = 0; g < G; ++g) {
+                uint32_t v = __ldcg(p.boot + (size_t)g * UMMA_M + m);
+#pragma unroll
+                for (int j = 0; j < UMMA_MAX_K; ++j) {
+                    const uint32_t hi = max(top[j], v);
+                    v = min(top[j], v);
+                    top[j] = hi;
+                }
+            }
+            uint32_t kth = 0u;
+#pragma unroll
+            for (int j = 0; j < UMMA_MAX_K; ++j) if (j == p.k - 1) kth = top[j];
+            if (kth) thr_boot = fmaxf(thr_boot, ord2f(kth));
+            thr = fmaxf(thr, thr_boot);
+            boot_done = published >= 4 * G;
+        };
+
         int it = 0;
         for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
             const int b = it & 1;
@@ -250,6 +284,37 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) flat_scan_umma_kernel(const _
             }
             mbar_wait(&tmem_full[b], aph);
             tc_fence_after();
+            if (it == 0) {
+                // ---- bootstrap pass over the first tile: best score per query, branch free ----
+                float mx = -INFINITY;
+#pragma unroll 1
+                for (int c = 0; c < TILE_N; c += 32) {
+                    uint32_t v[32];
+                    __syncwarp();
+                    tmem_ld32(lane_addr + (uint32_t)(b * TILE_N + c), v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        float s = __uint_as_float(v[j]);
+                        if (p.l2) s = fmaf(2.f, s, -wnorm[c + j]);
+                        if ((c + j) < nvalid) mx = fmaxf(mx, s);
+                    }
+                }
+                p.boot[(size_t)blockIdx.x * UMMA_M + m] = f2ord(mx);
+                __threadfence();
+                __syncwarp();
+                if (lane == 0) atomicAdd(reinterpret_cast<unsigned int*>(p.boot + (size_t)G * UMMA_M), 1u);
+                // bounded wait for the other CTAs (they start together and do the same work); a late
+                // CTA only weakens the bound, and the refresh below is repeated while it is incomplete
+                for (int spin = 0; spin < 40; ++spin) {
+                    if ((int)__ldcg(reinterpret_cast<const unsigned int*>(p.boot + (size_t)G * UMMA_M)) >= 4 * G) break;
+                    __nanosleep(100);
+                }
+                __threadfence();
+                refresh_boot();
+            } else if (!boot_done && (it & (it + 1)) == 0) {
+                refresh_boot();          // it = 1, 3, 7, 15, ...
+            }
 #pragma unroll 1
             for (int c = 0; c < TILE_N; c += 32) {
                 uint32_t v[32];
@@ -267,12 +332,12 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) flat_scan_umma_kernel(const _
                     float s = __uint_as_float(v[j]);
                     if (p.l2) s = fmaf(2.f, s, -wnorm[c + j]);
                     if (qvalid && (c + j) < nvalid && s >= thr)
-                        thr = umma_topk_insert(mylist, p.k, s, (uint32_t)(row0 + c + j), thr);
+                        thr = fmaxf(thr_boot, umma_topk_insert(mylist, p.k, s, (uint32_t)(row0 + c + j), thr));
                 }
             }
         }
         if (qvalid) {
-            const size_t o = (size_t)blockIdx.x * p.nq_total + p.q0 + m;
+            const size_t o = (size_t)blockIdx.x * p.nq_total + p.q0 + qi;
             int n = 0;
             for (int j = 0; j < p.k; ++j) {
                 const u64 key = mylist[j * UMMA_M];
@@ -292,9 +357,11 @@ __global__ void pack_queries_kernel(const float* __restrict__ q, long long nq, i
                                     int is_bf16, uint16_t* __restrict__ out) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nq_pad * pitch) return;
-    const long long r = i / pitch;
+    const long long r = i / pitch;                 // slot row: pass * 128 + TMEM lane
     const int c = (int)(i - r * pitch);
-    float v = (r < nq && c < d) ? q[r * d + c] : 0.f;
+    const int mm = (int)(r & 127);
+    const long long qsrc = (r & ~127ll) + (((mm & 31) << 2) | (mm >> 5));    // query held by that lane
+    float v = (qsrc < nq && c < d) ? q[qsrc * d + c] : 0.f;
     uint16_t o;
     if (is_bf16) { __nv_bfloat16 h = __float2bfloat16_rn(v); o = *reinterpret_cast<uint16_t*>(&h); }
     else { __half h = __float2half_rn(v); o = *reinterpret_cast<uint16_t*>(&h); }
@@ -312,9 +379,9 @@ struct UmmaState {
     const void* x = nullptr;
     long long n = 0;
     int tile_n = 0;
-    DevBuf qlow;
+    DevBuf qlow, boot;
     void invalidate() { valid = false; }
-    void release() { qlow.release(); valid = false; }
+    void release() { qlow.release(); boot.release(); valid = false; }
 };
 
 static inline int umma_tile_n(int pitch) { return pitch <= 512 ? 128 : 64; }
@@ -365,6 +432,8 @@ static inline int search_umma(UmmaState& st, const void* x, const float* xnorm, 
     const int grid = (int)std::min<long long>(sm_count, n_tiles);
     if ((rc = cand.ensure((size_t)grid * nq * k * 8))) return rc;
     if ((rc = cand_cnt.ensure((size_t)grid * nq * 4))) return rc;
+    const size_t boot_bytes = ((size_t)grid * UMMA_M + 32) * 4;
+    if ((rc = st.boot.ensure(boot_bytes))) return rc;
     const size_t stage_bytes = (size_t)tile_n * 128;
     const size_t fixed = (size_t)UMMA_MAX_K * UMMA_M * 8 + 4 * (size_t)tile_n * 4 + (2 * UMMA_MAX_STAGES + 4) * 8 + 16;
     int stages = (int)((200 * 1024 - fixed) / stage_bytes);
@@ -378,6 +447,8 @@ static inline int search_umma(UmmaState& st, const void* x, const float* xnorm, 
         p.k = k; p.l2 = metric == PRS_METRIC_L2; p.stages = stages; p.is_bf16 = storage == PRS_BF16;
         p.nq_total = (int)nq; p.q0 = (int)q0;
         p.cand = (u64*)cand.p; p.cand_cnt = (int*)cand_cnt.p;
+        p.boot = (uint32_t*)st.boot.p;
+        PRS_CUDA(cudaMemsetAsync(st.boot.p, 0, boot_bytes, stream));
         if (timer) timer->begin(stream);
         if (tile_n == 128) {
             PRS_CUDA(cudaFuncSetAttribute(flat_scan_umma_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
