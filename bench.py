@@ -68,49 +68,63 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons DURING the timed regions, read through NVML (the library behind
+    nvidia-smi; nvidia_ml_py) from a thread every ~2 ms -- the timed region of a default run is only
+    tens of milliseconds long, too short for `nvidia-smi -lms`."""
 
-    def __init__(self, gpu_index: int):
-        self.rows = []
-        self.proc = None
-        self.gpu = gpu_index
-        self.on = False
+    def __init__(self, cuda_index: int):
+        self.rows, self.on, self.stop_flag, self.h, self.mx = [], False, False, None, None
+        try:
+            import pynvml
+            import torch
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            try:
+                uuid = "GPU-" + str(torch.cuda.get_device_properties(cuda_index).uuid)
+                self.h = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode() if bytes is not str else uuid)
+            except Exception:
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(cuda_index)
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception as e:                      # no NVML: report that, do not invent numbers
+            self.err = repr(e)
+            self.h = None
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
-        except Exception:
-            self.proc = None
+        if self.h is None:
             return
-        threading.Thread(target=self._read, daemon=True).start()
-        time.sleep(0.35)
+        self.t = threading.Thread(target=self._run, daemon=True)
+        self.t.start()
 
-    def _read(self):
-        for line in self.proc.stdout:
+    def _run(self):
+        nv = self.nv
+        while not self.stop_flag:
             if self.on:
-                self.rows.append([c.strip() for c in line.split(",")])
+                try:
+                    mhz = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                    try:
+                        rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                    except Exception:
+                        rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                    self.rows.append((float(mhz), int(rs)))
+                except Exception:
+                    pass
+            time.sleep(0.002)
 
     def stop(self):
-        if self.proc:
-            time.sleep(0.15)
-            self.proc.terminate()
+        self.stop_flag = True
 
     def summary(self):
-        sm, mx, reasons = [], 0.0, set()
-        for r in self.rows:
-            try:
-                sm.append(float(r[1])); mx = max(mx, float(r[2]))
-            except Exception:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        if self.h is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "error": getattr(self, "err", "no NVML")}
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        reasons = sorted(n for n, bit in names.items() if any(r & bit for _, r in self.rows))
+        sm = [m for m, _ in self.rows]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.mx, "reasons": reasons,
+                "samples": len(sm), "source": "NVML, sampled every ~2 ms during the timed regions"}
 
 
 def host_threads():
@@ -300,6 +314,7 @@ def run_b200(a):
     for w in range(a.warmup):
         step_e2e(w)
     barrier()
+    sampler.on = True
     t0 = time.perf_counter()
     for s in range(a.steps):
         if flush:
@@ -307,6 +322,7 @@ def run_b200(a):
         step_e2e(a.warmup + s)
     barrier()
     e2e_ms = (time.perf_counter() - t0) * 1e3
+    sampler.on = False
     if rank == 0:
         sampler.stop()
     last_I = Ih.numpy().copy()

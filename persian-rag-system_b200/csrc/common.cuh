@@ -173,6 +173,24 @@ __device__ __forceinline__ int block_topk_stream(Fetch fetch, long long total, i
     return cnt < k ? cnt : k;
 }
 
+// ---------------------------------------------------------------------------------------------
+// HBM layout of 16-bit corpora ("T64"): blocks of 64 rows, each block contiguous (64 * pitch * 2
+// bytes).  Inside a block the data is k-block-major -- [pitch/64 k-blocks][64 rows][128 bytes] --
+// and the eight 16-byte chunks of every 128-byte row piece are stored pre-swizzled
+// (chunk ^ (row & 7)), i.e. exactly the image a 128-byte-swizzle TMA tensor load would leave in
+// shared memory.  One plain bulk copy of a contiguous k-block range is then directly consumable
+// by tcgen05.mma (K-major, SWIZZLE_128B descriptor), every byte of a DRAM page is used by the
+// same copy, and no tensor map is needed.
+// ---------------------------------------------------------------------------------------------
+constexpr int BLK_ROWS = 64;
+constexpr int KBLOCK_BYTES = BLK_ROWS * 128;       // one k-block (64 elements) of one row block
+// byte offset of the 16-byte chunk `chunk` (8 elements) of row `row`; pitch in elements (multiple of 64)
+__host__ __device__ __forceinline__ size_t t64_offset(long long row, int chunk, int pitch) {
+    const int r = (int)(row & (BLK_ROWS - 1));
+    return (size_t)(row >> 6) * ((size_t)BLK_ROWS * pitch * 2) + (size_t)(chunk >> 3) * KBLOCK_BYTES + (size_t)r * 128 +
+           (size_t)((((chunk & 7) ^ (r & 7))) << 4);
+}
+
 __host__ __device__ inline int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 
 // ---------------------------------------------------------------------------------------------

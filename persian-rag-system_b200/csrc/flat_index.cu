@@ -64,6 +64,32 @@ __global__ void ingest_rows_kernel(const TI* __restrict__ in, long long n, int d
     if (lane == 0) norm[row] = acc;
 }
 
+// 16-bit storage: same, but rows go into the T64 layout (common.cuh).  One warp per row, one
+// 16-byte chunk (8 elements) per lane and step.
+template <typename TI, typename TO>
+__global__ void ingest_rows_t64_kernel(const TI* __restrict__ in, long long n, int d, int pitch, long long row0,
+                                       unsigned char* __restrict__ out, float* __restrict__ norm) {
+    const long long i = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (i >= n) return;
+    const long long row = row0 + i;
+    float acc = 0.f;
+    for (int ch = lane; ch < (pitch >> 3); ch += 32) {
+        __align__(16) TO o[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int c = ch * 8 + e;
+            o[e] = from_f32<TO>(c < d ? to_f32<TI>(in[i * d + c]) : 0.f);
+            const float f = to_f32<TO>(o[e]);
+            acc = fmaf(f, f, acc);
+        }
+        *reinterpret_cast<uint4*>(out + t64_offset(row, ch, pitch)) = *reinterpret_cast<const uint4*>(o);
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) norm[row] = acc;
+}
+
 template <typename TI>
 __global__ void to_f32_kernel(const TI* __restrict__ in, long long n, float* __restrict__ out) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -77,7 +103,8 @@ __global__ void reconstruct_kernel(const TS* __restrict__ x, long long i0, long 
     if (i >= n * d) return;
     const long long r = i / d;
     const int c = (int)(i - r * d);
-    out[i] = to_f32<TS>(x[(i0 + r) * pitch + c]);
+    if (sizeof(TS) == 4) out[i] = to_f32<TS>(x[(i0 + r) * pitch + c]);
+    else out[i] = to_f32<TS>(*reinterpret_cast<const TS*>(reinterpret_cast<const unsigned char*>(x) + t64_offset(i0 + r, c >> 3, pitch) + (c & 7) * 2));
 }
 
 __global__ void fill_empty_kernel(float* D, long long* I, long long n, float dv) {
@@ -157,6 +184,7 @@ struct prs_index {
 };
 
 static int index_grow(prs_index* idx, long long n_total) {
+    if (idx->storage != PRS_F32) n_total = (n_total + BLK_ROWS - 1) / BLK_ROWS * BLK_ROWS;   // whole T64 blocks
     if (n_total <= idx->cap_rows) return 0;
     const size_t es = elem_size(idx->storage);
     void* nx = nullptr;
@@ -166,8 +194,10 @@ static int index_grow(prs_index* idx, long long n_total) {
     if (e != cudaSuccess) { cudaGetLastError(); set_error("cudaMalloc(%zu bytes) for corpus failed: %s", xb, cudaGetErrorString(e)); return PRS_ENOMEM; }
     e = cudaMalloc(&nn, (size_t)n_total * 4 + 256);
     if (e != cudaSuccess) { cudaGetLastError(); cudaFree(nx); set_error("cudaMalloc for norms failed: %s", cudaGetErrorString(e)); return PRS_ENOMEM; }
+    if (idx->storage != PRS_F32) PRS_CUDA(cudaMemset(nx, 0, xb ? xb : 256));   // rows of a partial block read as zeros
     if (idx->n > 0) {
-        PRS_CUDA(cudaMemcpy(nx, idx->x, (size_t)idx->n * idx->pitch * es, cudaMemcpyDeviceToDevice));
+        const long long used = idx->storage != PRS_F32 ? (idx->n + BLK_ROWS - 1) / BLK_ROWS * BLK_ROWS : idx->n;
+        PRS_CUDA(cudaMemcpy(nx, idx->x, (size_t)used * idx->pitch * es, cudaMemcpyDeviceToDevice));
         PRS_CUDA(cudaMemcpy(nn, idx->xnorm, (size_t)idx->n * 4, cudaMemcpyDeviceToDevice));
     }
     if (idx->x) cudaFree(idx->x);
@@ -186,8 +216,8 @@ static int ingest_dispatch(prs_index* idx, const void* x, long long n, cudaStrea
     float* nrm = idx->xnorm + idx->n;
     switch (idx->storage) {
         case PRS_F32: ingest_rows_kernel<TI, float><<<grid, wpb * 32, 0, st>>>((const TI*)x, n, idx->d, idx->pitch, (float*)dst, nrm); break;
-        case PRS_F16: ingest_rows_kernel<TI, __half><<<grid, wpb * 32, 0, st>>>((const TI*)x, n, idx->d, idx->pitch, (__half*)dst, nrm); break;
-        default: ingest_rows_kernel<TI, __nv_bfloat16><<<grid, wpb * 32, 0, st>>>((const TI*)x, n, idx->d, idx->pitch, (__nv_bfloat16*)dst, nrm); break;
+        case PRS_F16: ingest_rows_t64_kernel<TI, __half><<<grid, wpb * 32, 0, st>>>((const TI*)x, n, idx->d, idx->pitch, idx->n, (unsigned char*)idx->x, idx->xnorm); break;
+        default: ingest_rows_t64_kernel<TI, __nv_bfloat16><<<grid, wpb * 32, 0, st>>>((const TI*)x, n, idx->d, idx->pitch, idx->n, (unsigned char*)idx->x, idx->xnorm); break;
     }
     PRS_LAUNCH_CHECK();
     return 0;
@@ -242,7 +272,7 @@ static int launch_merge(prs_index* idx, int parts, long long nq, int k, int out_
 static int search_simt(prs_index* idx, const float* qf, int q_stride, long long nq, int k, float* D, int64_t* I, cudaStream_t st) {
     const int es = elem_size(idx->storage);
     const int row_bytes = idx->pitch * es;
-    if ((long long)SIMT_NW * row_bytes > 64 * 1024) {
+    if ((long long)(idx->storage != PRS_F32 ? BLK_ROWS : SIMT_NW) * row_bytes > 100 * 1024) {
         set_error("flat scan: d=%d too large for the shared-memory tile (row of %d bytes)", idx->d, row_bytes);
         return PRS_EUNSUP;
     }
@@ -253,11 +283,17 @@ static int search_simt(prs_index* idx, const float* qf, int q_stride, long long 
     int rc;
     long long done = 0;
     // workspace is sized for the widest group; every group uses the same grid
+    const bool tiled = idx->storage != PRS_F32;
     int R0 = 4;
-    while (R0 > 1 && (SIMT_NW * R0 * row_bytes > 48 * 1024 || R0 * qb_max > 32)) R0 >>= 1;
+    while (R0 > 1 && ((!tiled && SIMT_NW * R0 * row_bytes > 48 * 1024) || R0 * qb_max > 32)) R0 >>= 1;
+    // tile geometry: fp32 rows are row-major (any multiple of NW*R rows); 16-bit corpora are in the
+    // T64 layout, so a tile is a whole number of 64-row blocks
+    auto tile_rows_for = [&](int R) -> int {
+        if (tiled) return BLK_ROWS * std::max(1, 32768 / (BLK_ROWS * row_bytes));
+        return SIMT_NW * R * std::max(1, 32768 / (SIMT_NW * R * row_bytes));
+    };
     {
-        const int m = std::max(1, 32768 / (SIMT_NW * R0 * row_bytes));
-        const int tile_rows = SIMT_NW * R0 * m;
+        const int tile_rows = tile_rows_for(R0);
         const long long n_tiles = (idx->n + tile_rows - 1) / tile_rows;
         grid = (int)std::min<long long>(idx->sm_count, n_tiles);
     }
@@ -272,11 +308,10 @@ static int search_simt(prs_index* idx, const float* qf, int q_stride, long long 
         p.q_stride = q_stride; p.nq = QB; p.k = k; p.cap = cap;
         // R and tile geometry are fixed per search (R0) so that `grid` and the workspace agree
         const int R = R0;
-        const int m = std::max(1, 32768 / (SIMT_NW * R * row_bytes));
-        p.tile_rows = SIMT_NW * R * m;
+        p.tile_rows = tile_rows_for(R);
         const size_t qbytes = (((size_t)QB * idx->pitch * 4) + 127) & ~(size_t)127;
         const size_t tile_bytes = (size_t)p.tile_rows * row_bytes;
-        int stages = (int)((200 * 1024 - 512 - qbytes) / tile_bytes);
+        int stages = (int)((226 * 1024 - 512 - qbytes) / tile_bytes);
         if (stages > SIMT_MAX_STAGES) stages = SIMT_MAX_STAGES;
         if (stages < 2 || (size_t)stages * tile_bytes < (size_t)sortn * 8) {
             set_error("flat scan: cannot fit the pipeline in shared memory (d=%d, k=%d)", idx->d, k);
@@ -314,6 +349,20 @@ static int search_device_impl(prs_index* idx, const void* q, int qdtype, long lo
         return 0;
     }
     int rc;
+    int path = idx->path_force;
+    if (path == 0) path = umma_eligible(idx->storage, idx->d, idx->pitch, nq, k) ? 2 : 1;
+    if (path == 2) {
+        if (!umma_eligible(idx->storage, idx->d, idx->pitch, nq, k)) {
+            set_error("tcgen05 path needs fp16/bf16 storage, d <= 768 and k <= %d (storage=%d, d=%d, k=%d)", UMMA_MAX_K, idx->storage, idx->d, k);
+            return PRS_EUNSUP;
+        }
+        idx->last_path = 2;
+        if ((rc = idx->qnorm.ensure((size_t)nq * 4))) return rc;
+        int parts = 0;
+        if ((rc = search_umma(idx->umma, idx->x, idx->xnorm, idx->n, idx->d, idx->pitch, idx->storage, idx->metric, idx->sm_count,
+                              q, qdtype, nq, k, (float*)idx->qnorm.p, idx->cand, idx->cand_cnt, &parts, st, &idx->timer))) return rc;
+        return launch_merge(idx, parts, nq, k, idx->metric == PRS_METRIC_L2 ? 2 : 0, (const float*)idx->qnorm.p, D, I, st);
+    }
     const float* qf = (const float*)q;
     if (qdtype != PRS_F32) {
         const long long tot = nq * idx->d;
@@ -323,22 +372,6 @@ static int search_device_impl(prs_index* idx, const void* q, int qdtype, long lo
         else { set_error("search: unsupported query dtype %d", qdtype); return PRS_EINVAL; }
         PRS_LAUNCH_CHECK();
         qf = (const float*)idx->qf32.p;
-    }
-    int path = idx->path_force;
-    if (path == 0) path = umma_eligible(idx->storage, idx->d, idx->pitch, nq, k) ? 2 : 1;
-    if (path == 2) {
-        if (!umma_eligible(idx->storage, idx->d, idx->pitch, 8, k)) {
-            set_error("tcgen05 path needs fp16/bf16 storage and k <= %d (storage=%d, k=%d)", UMMA_MAX_K, idx->storage, k);
-            return PRS_EUNSUP;
-        }
-        idx->last_path = 2;
-        if ((rc = idx->qnorm.ensure((size_t)nq * 4))) return rc;
-        qnorm_kernel<<<(unsigned)nq, 32, 0, st>>>(qf, idx->d, idx->d, (float*)idx->qnorm.p);
-        PRS_LAUNCH_CHECK();
-        int parts = 0;
-        if ((rc = search_umma(idx->umma, idx->x, idx->xnorm, idx->n, idx->d, idx->pitch, idx->storage, idx->metric, idx->sm_count,
-                              qf, nq, k, idx->cand, idx->cand_cnt, &parts, st, &idx->timer))) return rc;
-        return launch_merge(idx, parts, nq, k, idx->metric == PRS_METRIC_L2 ? 2 : 0, (const float*)idx->qnorm.p, D, I, st);
     }
     idx->last_path = 1;
     return search_simt(idx, qf, idx->d, nq, k, D, I, st);

@@ -147,6 +147,7 @@ template <typename T, int QB, int R, bool L2>
 __global__ void __launch_bounds__(SIMT_THREADS, 1) flat_scan_simt_kernel(const SimtParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr int VEC = Vec16<T>::N;
+    constexpr bool TILED = (VEC == 8);                // 16-bit corpora are stored in the T64 layout (common.cuh)
     constexpr int NACC = R * QB;
     constexpr int P = Log2<NACC>::v;
     static_assert(NACC <= 32, "at most 32 (row, query) accumulators per lane");
@@ -195,7 +196,8 @@ __global__ void __launch_bounds__(SIMT_THREADS, 1) flat_scan_simt_kernel(const S
             for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
                 mbar_wait(&empty[s], ph ^ 1u);
                 const long long row0 = t * p.tile_rows;
-                const long long rows = (p.n_rows - row0 < p.tile_rows) ? (p.n_rows - row0) : p.tile_rows;
+                long long rows = (p.n_rows - row0 < p.tile_rows) ? (p.n_rows - row0) : p.tile_rows;
+                if (TILED) rows = (rows + BLK_ROWS - 1) / BLK_ROWS * BLK_ROWS;        // whole row blocks
                 const uint32_t bytes = (uint32_t)(rows * row_bytes);
                 mbar_arrive_expect_tx(&full[s], bytes);
                 bulk_g2s(tiles + (size_t)s * tile_bytes, xg + (size_t)row0 * row_bytes, bytes, &full[s]);
@@ -227,8 +229,10 @@ __global__ void __launch_bounds__(SIMT_THREADS, 1) flat_scan_simt_kernel(const S
                     if (col < p.pitch) {
                         float xv[R][VEC];
 #pragma unroll
-                        for (int r = 0; r < R; ++r)
-                            Vec16<T>::load(tile + (size_t)(rg * R + r) * row_bytes + (size_t)chunk * 16, xv[r]);
+                        for (int r = 0; r < R; ++r) {
+                            if (TILED) Vec16<T>::load(tile + t64_offset(rg * R + r, chunk, p.pitch), xv[r]);
+                            else Vec16<T>::load(tile + (size_t)(rg * R + r) * row_bytes + (size_t)chunk * 16, xv[r]);
+                        }
 #pragma unroll
                         for (int qq = 0; qq < QB; ++qq) {
                             float qv[VEC];

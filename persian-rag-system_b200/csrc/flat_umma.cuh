@@ -8,8 +8,9 @@
 //   A  = the query block, converted to the storage type once, RESIDENT IN TENSOR MEMORY for the
 //        whole kernel (tcgen05.st, one TMEM lane per query).  Shared memory therefore holds
 //        nothing but the streaming ring, and the MMA never re-reads queries from smem or L2.
-//   B  = corpus rows, K-major, streamed HBM -> smem by TMA (cp.async.bulk.tensor.2d, 128-byte
-//        swizzle) in K-blocks of 64 elements through an mbarrier ring.
+//   B  = corpus rows, K-major.  The corpus sits in HBM in the T64 layout (common.cuh): 64-row
+//        blocks, k-block-major, pre-swizzled, so each pipeline stage is ONE contiguous bulk copy
+//        (cp.async.bulk, SASS UBLKCP) of `kbs` k-blocks (8 KB each) through an mbarrier ring.
 //   D  = fp32 accumulators in TMEM, double buffered (2 x TILE_N columns).
 //   epilogue (4 warps, one thread per query): tcgen05.ld its lane's TILE_N scores, apply the L2
 //        bias (2 q.x - ||x||^2), compare with the thread's k-th best, and on the rare hit insert
@@ -17,13 +18,11 @@
 //        HBM; each CTA emits one sorted top-k per query (cand[cta][query][k]).
 //
 // TMEM budget (512 columns): A uses pitch/2 columns (two 16-bit values per column), D uses
-// 2*TILE_N.  pitch <= 512 -> TILE_N = 128; pitch <= 768 -> TILE_N = 64.
+// 2*TILE_N = 128 (TILE_N = 64 = one row block), so pitch <= 768.
 //
 // Warp roles (192 threads): warp 0 = TMA producer + TMEM allocator, warp 1 = MMA issuer,
 // warps 2..5 = epilogue (TMEM lane quarter = warp % 4).
 #pragma once
-#include <cuda.h>
-
 #include "common.cuh"
 #include "host_common.h"
 
@@ -36,10 +35,11 @@ constexpr int UMMA_MAX_STAGES = 24;
 constexpr int UMMA_TMEM_COLS = 512;
 
 struct UmmaParams {
-    const uint16_t* qlow;   // [128, pitch] 16-bit queries of this pass (zero padded)
+    const unsigned char* x; // corpus, T64 layout
+    const uint16_t* qlow;   // [128, pitch] 16-bit queries of this pass, slot ordered (zero padded)
     const float* xnorm;     // [n_rows] squared norms of the stored rows
     long long n_rows;
-    int pitch, nq, k, l2, stages, is_bf16;
+    int pitch, nq, k, l2, stages, is_bf16, kbs;   // kbs: k-blocks per pipeline stage
     int nq_total, q0;
     u64* cand;              // [grid][nq_total][k]
     int* cand_cnt;          // [grid][nq_total]
@@ -68,11 +68,6 @@ __device__ __forceinline__ void umma_ts_f16(uint32_t d_tmem, uint32_t a_tmem, ui
         "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, {%5, %6, %7, %8}, p;\n\t}"
         ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(0), "r"(0), "r"(0), "r"(0)
         : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tmap, int x, int y, uint64_t* bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-        ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(x), "r"(y), "r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile(
@@ -124,9 +119,10 @@ __device__ __noinline__ float umma_topk_insert(u64* list, int k, float s, uint32
 }
 
 template <int TILE_N>
-__global__ void __launch_bounds__(UMMA_THREADS, 1) flat_scan_umma_kernel(const __grid_constant__ CUtensorMap tmap, const UmmaParams p) {
+__global__ void __launch_bounds__(UMMA_THREADS, 1) flat_scan_umma_kernel(const UmmaParams p) {
+    static_assert(TILE_N == BLK_ROWS, "one MMA tile == one T64 row block");
     extern __shared__ unsigned char umma_smem_raw[];
-    constexpr uint32_t STAGE_BYTES = TILE_N * 128;
+    const uint32_t STAGE_BYTES = (uint32_t)p.kbs * KBLOCK_BYTES;
     constexpr uint32_t D_OFF = UMMA_TMEM_COLS - 2 * TILE_N;     // accumulator columns at the top
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -143,6 +139,7 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) flat_scan_umma_kernel(const _
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
     const int kblocks = p.pitch >> 6;
+    const int kstages = kblocks / p.kbs;           // pipeline stages per tile
     const long long n_tiles = (p.n_rows + TILE_N - 1) / TILE_N;
 
     if (tid == 0) {
@@ -157,38 +154,20 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) flat_scan_umma_kernel(const _
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
 
-    if (warp >= 2) {
-        // ---- stage this thread's query row into TMEM: lane m, columns [0, pitch/2) ----
-        const int qd = warp & 3;
-        const int m = qd * 32 + lane;
-        const uint4* qrow = reinterpret_cast<const uint4*>(p.qlow + (size_t)m * p.pitch);
-        const uint32_t lane_addr = tmem_base + ((uint32_t)(qd * 32) << 16);
-        for (int c0 = 0; c0 < (p.pitch >> 1); c0 += 32) {
-            uint32_t v[32];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const uint4 t = qrow[(c0 >> 2) + i];
-                v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
-            }
-            tmem_st32(lane_addr + (uint32_t)c0, v);
-        }
-        tmem_st_wait();
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-
+    // The producer starts streaming at once; the epilogue warps stage the queries into TMEM
+    // meanwhile and release the MMA warp through named barrier 2 (128 + 32 threads).
     if (warp == 0) {
         // ---------------- TMA producer ----------------
         if (lane == 0) {
             int s = 0;
             uint32_t ph = 0;
+            const size_t blk_bytes = (size_t)BLK_ROWS * p.pitch * 2;
             for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-                const int row0 = (int)(t * TILE_N);
-                for (int kb = 0; kb < kblocks; ++kb) {
+                const unsigned char* src = p.x + (size_t)t * blk_bytes;
+                for (int ks = 0; ks < kstages; ++ks) {
                     mbar_wait(&empty[s], ph ^ 1u);
                     mbar_arrive_expect_tx(&full[s], STAGE_BYTES);
-                    tma_load_2d(ring + (size_t)s * STAGE_BYTES, &tmap, kb * 64, row0, &full[s]);
+                    bulk_g2s(ring + (size_t)s * STAGE_BYTES, src + (size_t)ks * STAGE_BYTES, STAGE_BYTES, &full[s]);
                     if (++s == p.stages) { s = 0; ph ^= 1u; }
                 }
             }
@@ -201,25 +180,30 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) flat_scan_umma_kernel(const _
         const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(TILE_N >> 3) << 17) | ((uint32_t)(UMMA_M >> 4) << 24);
         int s = 0, it = 0;
         uint32_t ph = 0;
+        named_bar_sync(2, 160);                               // queries are in TMEM
+        tc_fence_after();
         for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
             const int b = it & 1;
             const uint32_t aph = (uint32_t)(it >> 1) & 1u;
             mbar_wait(&tmem_empty[b], aph ^ 1u);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + D_OFF + (uint32_t)(b * TILE_N);
-            for (int kb = 0; kb < kblocks; ++kb) {
+            for (int ks = 0; ks < kstages; ++ks) {
                 mbar_wait(&full[s], ph);
                 tc_fence_after();
                 if (lane == 0) {
                     const uint32_t sb = smem_u32(ring + (size_t)s * STAGE_BYTES);
+                    for (int kbi = 0; kbi < p.kbs; ++kbi) {
+                        const int kb = ks * p.kbs + kbi;
 #pragma unroll
-                    for (int k4 = 0; k4 < 4; ++k4) {
-                        const uint64_t bdesc = umma_desc_sw128(sb + (uint32_t)k4 * 32u);
-                        const uint32_t a_tmem = tmem_base + (uint32_t)(kb * 32 + k4 * 8);
-                        umma_ts_f16(d_tmem, a_tmem, bdesc, idesc, (kb | k4) != 0 ? 1u : 0u);
+                        for (int k4 = 0; k4 < 4; ++k4) {
+                            const uint64_t bdesc = umma_desc_sw128(sb + (uint32_t)kbi * KBLOCK_BYTES + (uint32_t)k4 * 32u);
+                            const uint32_t a_tmem = tmem_base + (uint32_t)(kb * 32 + k4 * 8);
+                            umma_ts_f16(d_tmem, a_tmem, bdesc, idesc, (kb | k4) != 0 ? 1u : 0u);
+                        }
                     }
                     umma_commit(&empty[s]);                    // frees the smem stage when these MMAs retire
-                    if (kb == kblocks - 1) umma_commit(&tmem_full[b]);
+                    if (ks == kstages - 1) umma_commit(&tmem_full[b]);
                 }
                 __syncwarp();
                 if (++s == p.stages) { s = 0; ph ^= 1u; }
@@ -236,6 +220,23 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) flat_scan_umma_kernel(const _
         u64* mylist = lists + m;
         float* wnorm = snorm + (warp - 2) * TILE_N;
         const uint32_t lane_addr = tmem_base + ((uint32_t)(qd * 32) << 16) + D_OFF;
+        {
+            // stage this thread's query row into TMEM: lane m, columns [0, pitch/2)
+            const uint4* qrow = reinterpret_cast<const uint4*>(p.qlow + (size_t)m * p.pitch);
+            const uint32_t a_addr = tmem_base + ((uint32_t)(qd * 32) << 16);
+            for (int c0 = 0; c0 < (p.pitch >> 1); c0 += 32) {
+                uint32_t v[32];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const uint4 t4 = __ldg(&qrow[(c0 >> 2) + i]);
+                    v[4 * i] = t4.x; v[4 * i + 1] = t4.y; v[4 * i + 2] = t4.z; v[4 * i + 3] = t4.w;
+                }
+                tmem_st32(a_addr + (uint32_t)c0, v);
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            named_bar_sync(2, 160);
+        }
         const int G = (int)gridDim.x;
         float thr_boot = -INFINITY;     // lower bound of the GLOBAL k-th best score (see bootstrap below)
         float thr = -INFINITY;          // admission threshold = max(thr_boot, this CTA's k-th best)
@@ -352,111 +353,100 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) flat_scan_umma_kernel(const _
     if (warp == 0) tmem_dealloc(tmem_base, UMMA_TMEM_COLS);
 }
 
-// fp32 queries -> [128-padded, pitch] 16-bit, zero padded
-__global__ void pack_queries_kernel(const float* __restrict__ q, long long nq, int d, int pitch, long long nq_pad,
-                                    int is_bf16, uint16_t* __restrict__ out) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nq_pad * pitch) return;
-    const long long r = i / pitch;                 // slot row: pass * 128 + TMEM lane
-    const int c = (int)(i - r * pitch);
+// One launch per search: queries (fp32 / fp16 / bf16) -> [128-padded, pitch] 16-bit rows in TMEM-slot
+// order, zero padded; ||q~||^2 of the ROUNDED query (what the expanded L2 form needs); and the
+// bootstrap array of the scan kernel zeroed.  One warp per slot row.
+template <typename TQ>
+__global__ void prep_queries_kernel(const TQ* __restrict__ q, long long nq, int d, int pitch, long long nq_pad,
+                                    int is_bf16, uint16_t* __restrict__ out, float* __restrict__ qnorm,
+                                    uint32_t* __restrict__ boot, long long boot_words) {
+    const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (long long i = gtid; i < boot_words; i += (long long)gridDim.x * blockDim.x) boot[i] = 0u;
+    const long long r = gtid >> 5;                 // slot row: pass * 128 + TMEM lane
+    const int lane = threadIdx.x & 31;
+    if (r >= nq_pad) return;
     const int mm = (int)(r & 127);
     const long long qsrc = (r & ~127ll) + (((mm & 31) << 2) | (mm >> 5));    // query held by that lane
-    float v = (qsrc < nq && c < d) ? q[qsrc * d + c] : 0.f;
-    uint16_t o;
-    if (is_bf16) { __nv_bfloat16 h = __float2bfloat16_rn(v); o = *reinterpret_cast<uint16_t*>(&h); }
-    else { __half h = __float2half_rn(v); o = *reinterpret_cast<uint16_t*>(&h); }
-    out[i] = o;
+    float acc = 0.f;
+    for (int c = lane; c < pitch; c += 32) {
+        float v = 0.f;
+        if (qsrc < nq && c < d) {
+            const TQ t = q[qsrc * d + c];
+            if constexpr (sizeof(TQ) == 4) v = (float)t;
+            else v = (float)t;
+        }
+        uint16_t o;
+        float back;
+        if (is_bf16) { __nv_bfloat16 h = __float2bfloat16_rn(v); o = *reinterpret_cast<uint16_t*>(&h); back = __bfloat162float(h); }
+        else { __half h = __float2half_rn(v); o = *reinterpret_cast<uint16_t*>(&h); back = __half2float(h); }
+        out[r * pitch + c] = o;
+        acc = fmaf(back, back, acc);
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0 && qsrc < nq) qnorm[qsrc] = acc;
 }
 
 // ---------------- host side ----------------
-typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
 struct UmmaState {
-    CUtensorMap tmap;
-    bool valid = false;
-    const void* x = nullptr;
-    long long n = 0;
-    int tile_n = 0;
     DevBuf qlow, boot;
-    void invalidate() { valid = false; }
-    void release() { qlow.release(); boot.release(); valid = false; }
+    void invalidate() {}
+    void release() { qlow.release(); boot.release(); }
 };
-
-static inline int umma_tile_n(int pitch) { return pitch <= 512 ? 128 : 64; }
 
 static inline bool umma_eligible(int storage, int d, int pitch, long long nq, int k) {
     (void)d;
-    return (storage == PRS_F16 || storage == PRS_BF16) && pitch <= 768 && k <= UMMA_MAX_K && nq >= 8;
+    return (storage == PRS_F16 || storage == PRS_BF16) && pitch <= 768 && k <= UMMA_MAX_K && nq >= 1;
 }
 
-static inline int umma_make_tmap(UmmaState& st, const void* x, long long n, int pitch, int storage, int tile_n) {
-    if (st.valid && st.x == x && st.n == n && st.tile_n == tile_n) return 0;
-    static PFN_encodeTiled encode = nullptr;
-    if (!encode) {
-        void* fn = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        PRS_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
-        if (!fn || qres != cudaDriverEntryPointSuccess) { set_error("cuTensorMapEncodeTiled not available from the driver"); return PRS_ECUDA; }
-        encode = (PFN_encodeTiled)fn;
-    }
-    const cuuint64_t dims[2] = {(cuuint64_t)pitch, (cuuint64_t)n};
-    const cuuint64_t strides[1] = {(cuuint64_t)pitch * 2};
-    const cuuint32_t box[2] = {64, (cuuint32_t)tile_n};
-    const cuuint32_t estr[2] = {1, 1};
-    CUresult r = encode(&st.tmap, storage == PRS_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
-                        const_cast<void*>(x), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return PRS_ECUDA; }
-    st.valid = true; st.x = x; st.n = n; st.tile_n = tile_n;
-    return 0;
-}
-
+// q: [nq, d] device, dtype qdtype.  qnorm: [nq] device out.  cand/cand_cnt: per-CTA lists out.
 static inline int search_umma(UmmaState& st, const void* x, const float* xnorm, long long n, int d, int pitch, int storage,
-                              int metric, int sm_count, const float* qf, long long nq, int k, DevBuf& cand, DevBuf& cand_cnt,
-                              int* parts_out, cudaStream_t stream, ScanTimer* timer = nullptr) {
-    const int tile_n = umma_tile_n(pitch);
-    if (n > 0x7FFFFFFFll - tile_n) { set_error("tcgen05 path: more than 2^31 rows per shard"); return PRS_EUNSUP; }
+                              int metric, int sm_count, const void* q, int qdtype, long long nq, int k, float* qnorm,
+                              DevBuf& cand, DevBuf& cand_cnt, int* parts_out, cudaStream_t stream, ScanTimer* timer = nullptr) {
+    if (n > 0x7FFFFFFFll - BLK_ROWS) { set_error("tcgen05 path: more than 2^31 rows per shard"); return PRS_EUNSUP; }
     int rc;
-    if ((rc = umma_make_tmap(st, x, n, pitch, storage, tile_n))) return rc;
     const long long nq_pad = (nq + UMMA_M - 1) / UMMA_M * UMMA_M;
+    const long long n_tiles = (n + BLK_ROWS - 1) / BLK_ROWS;
+    const int grid = (int)std::min<long long>(sm_count, n_tiles);
+    const long long boot_words = (long long)grid * UMMA_M + 32;
+    const long long passes = nq_pad / UMMA_M;
     if ((rc = st.qlow.ensure((size_t)nq_pad * pitch * 2))) return rc;
+    if ((rc = st.boot.ensure((size_t)boot_words * passes * 4))) return rc;
     {
-        const long long tot = nq_pad * pitch;
-        pack_queries_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>(qf, nq, d, pitch, nq_pad, storage == PRS_BF16,
-                                                                               (uint16_t*)st.qlow.p);
+        const unsigned blocks = (unsigned)((nq_pad * 32 + 255) / 256);
+        const int bf = storage == PRS_BF16;
+        uint16_t* out = (uint16_t*)st.qlow.p;
+        uint32_t* boot = (uint32_t*)st.boot.p;
+        switch (qdtype) {
+            case PRS_F32: prep_queries_kernel<float><<<blocks, 256, 0, stream>>>((const float*)q, nq, d, pitch, nq_pad, bf, out, qnorm, boot, boot_words * passes); break;
+            case PRS_F16: prep_queries_kernel<__half><<<blocks, 256, 0, stream>>>((const __half*)q, nq, d, pitch, nq_pad, bf, out, qnorm, boot, boot_words * passes); break;
+            case PRS_BF16: prep_queries_kernel<__nv_bfloat16><<<blocks, 256, 0, stream>>>((const __nv_bfloat16*)q, nq, d, pitch, nq_pad, bf, out, qnorm, boot, boot_words * passes); break;
+            default: set_error("search: unsupported query dtype %d", qdtype); return PRS_EINVAL;
+        }
         PRS_LAUNCH_CHECK();
     }
-    const long long n_tiles = (n + tile_n - 1) / tile_n;
-    const int grid = (int)std::min<long long>(sm_count, n_tiles);
     if ((rc = cand.ensure((size_t)grid * nq * k * 8))) return rc;
     if ((rc = cand_cnt.ensure((size_t)grid * nq * 4))) return rc;
-    const size_t boot_bytes = ((size_t)grid * UMMA_M + 32) * 4;
-    if ((rc = st.boot.ensure(boot_bytes))) return rc;
-    const size_t stage_bytes = (size_t)tile_n * 128;
-    const size_t fixed = (size_t)UMMA_MAX_K * UMMA_M * 8 + 4 * (size_t)tile_n * 4 + (2 * UMMA_MAX_STAGES + 4) * 8 + 16;
-    int stages = (int)((200 * 1024 - fixed) / stage_bytes);
+    const int kblocks = pitch >> 6;
+    const int kbs = (kblocks % 2 == 0) ? 2 : 1;                     // 16 KB stages when the k-block count is even
+    const size_t stage_bytes = (size_t)kbs * KBLOCK_BYTES;
+    const size_t fixed = (size_t)UMMA_MAX_K * UMMA_M * 8 + 4 * (size_t)BLK_ROWS * 4 + (2 * UMMA_MAX_STAGES + 4) * 8 + 16;
+    int stages = (int)((226 * 1024 - 1024 - fixed) / stage_bytes);
     if (stages > UMMA_MAX_STAGES) stages = UMMA_MAX_STAGES;
     const size_t smem = 1024 + (size_t)stages * stage_bytes + fixed;
+    PRS_CUDA(cudaFuncSetAttribute(flat_scan_umma_kernel<BLK_ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     for (long long q0 = 0; q0 < nq; q0 += UMMA_M) {
         UmmaParams p;
+        p.x = (const unsigned char*)x;
         p.qlow = (const uint16_t*)st.qlow.p + (size_t)q0 * pitch;
         p.xnorm = xnorm; p.n_rows = n; p.pitch = pitch;
         p.nq = (int)std::min<long long>(UMMA_M, nq - q0);
-        p.k = k; p.l2 = metric == PRS_METRIC_L2; p.stages = stages; p.is_bf16 = storage == PRS_BF16;
+        p.k = k; p.l2 = metric == PRS_METRIC_L2; p.stages = stages; p.is_bf16 = storage == PRS_BF16; p.kbs = kbs;
         p.nq_total = (int)nq; p.q0 = (int)q0;
         p.cand = (u64*)cand.p; p.cand_cnt = (int*)cand_cnt.p;
-        p.boot = (uint32_t*)st.boot.p;
-        PRS_CUDA(cudaMemsetAsync(st.boot.p, 0, boot_bytes, stream));
+        p.boot = (uint32_t*)st.boot.p + (size_t)(q0 / UMMA_M) * boot_words;
         if (timer) timer->begin(stream);
-        if (tile_n == 128) {
-            PRS_CUDA(cudaFuncSetAttribute(flat_scan_umma_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            flat_scan_umma_kernel<128><<<grid, UMMA_THREADS, smem, stream>>>(st.tmap, p);
-        } else {
-            PRS_CUDA(cudaFuncSetAttribute(flat_scan_umma_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            flat_scan_umma_kernel<64><<<grid, UMMA_THREADS, smem, stream>>>(st.tmap, p);
-        }
+        flat_scan_umma_kernel<BLK_ROWS><<<grid, UMMA_THREADS, smem, stream>>>(p);
         if (timer) timer->end(stream);
         PRS_LAUNCH_CHECK();
     }

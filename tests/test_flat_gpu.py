@@ -191,6 +191,29 @@ def test_16bit_storage_vs_oracle(P, storage, path, metric, n, d, nq, k):
 
 
 @pytest.mark.parametrize("storage", ["fp16", "bf16"])
+@pytest.mark.parametrize("d", [40, 128, 384])
+def test_16bit_t64_layout_incremental_add_and_reconstruct(P, storage, d):
+    """16-bit corpora live in HBM in the T64 block layout: rows added in ragged pieces (crossing 64-row
+    block boundaries, growing the buffer) must reconstruct exactly and search like a single add."""
+    rng = np.random.default_rng(d)
+    x = rng.standard_normal((333, d)).astype(np.float32)
+    a = P.FlatIndex(d, P.METRIC_L2, storage)
+    for lo, hi in [(0, 1), (1, 63), (63, 65), (65, 200), (200, 333)]:
+        a.add(x[lo:hi])
+    b = P.FlatIndex(d, P.METRIC_L2, storage)
+    b.add(x)
+    xs = _round_to(x, storage)
+    assert np.array_equal(a.reconstruct_n(0, 333), xs) and np.array_equal(b.reconstruct_n(5, 100), xs[5:105])
+    q = x[[0, 62, 63, 64, 199, 332]] + 0.01
+    for path in ("tcgen05", "cuda-core"):
+        a.set_path(path); b.set_path(path)
+        Da, Ia = a.search(q, 7)
+        Db, Ib = b.search(q, 7)
+        assert np.array_equal(Ia, Ib) and np.array_equal(Da, Db)
+        assert Ia[:, 0].tolist() == [0, 62, 63, 64, 199, 332]
+
+
+@pytest.mark.parametrize("storage", ["fp16", "bf16"])
 def test_16bit_container_roundtrip(P, storage, tmp_path):
     rng = np.random.default_rng(5)
     x = rng.standard_normal((77, 96)).astype(np.float32)
@@ -212,9 +235,13 @@ def test_auto_path_selection(P):
     idx = P.FlatIndex(256, P.METRIC_IP, "fp16")
     idx.add(x)
     idx.search(rng.standard_normal((1, 256)).astype(np.float32), 10)
-    assert idx.last_path == "cuda-core"           # bandwidth-bound small batch
+    assert idx.last_path == "tcgen05"             # 16-bit corpora stream through the tensor pipe at any batch
     idx.search(rng.standard_normal((64, 256)).astype(np.float32), 10)
-    assert idx.last_path == "tcgen05"             # the scan is a real GEMM
+    assert idx.last_path == "tcgen05"
+    f32 = P.FlatIndex(256, P.METRIC_IP, "fp32")
+    f32.add(x)
+    f32.search(rng.standard_normal((64, 256)).astype(np.float32), 10)
+    assert f32.last_path == "cuda-core"           # fp32 storage is the exact-parity CUDA-core scan
     idx.search(rng.standard_normal((64, 256)).astype(np.float32), 100)
     assert idx.last_path == "cuda-core"           # k beyond the in-smem lists
 
