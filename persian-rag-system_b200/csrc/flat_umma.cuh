@@ -40,6 +40,7 @@ struct UmmaParams {
     const float* xnorm;     // [n_rows] squared norms of the stored rows
     long long n_rows;
     int pitch, nq, k, l2, stages, is_bf16, kbs;   // kbs: k-blocks per pipeline stage
+    int dbg;                // experiments only (PRS_UMMA_DEBUG): 1 no bootstrap+no inserts, 2 epilogue releases without reading, 4 no MMA
     int nq_total, q0;
     u64* cand;              // [grid][nq_total][k]
     int* cand_cnt;          // [grid][nq_total]
@@ -101,7 +102,7 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
 }
 
 // thread-private sorted (descending) list of k keys, stride UMMA_M between entries.
-// Returns the new admission threshold.
+// Returns the new admission threshold.  (Superseded by the register-resident list in the kernel.)
 __device__ __noinline__ float umma_topk_insert(u64* list, int k, float s, uint32_t id, float thr) {
     const u64 key = make_key<PRS_TIE_LOW_ID>(s, id);
     u64 last = list[(k - 1) * UMMA_M];
@@ -130,8 +131,7 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) flat_scan_umma_kernel(const U
     const uint32_t raw = smem_u32(umma_smem_raw);
     unsigned char* base = umma_smem_raw + (((raw + 1023u) & ~1023u) - raw);
     unsigned char* ring = base;
-    u64* lists = reinterpret_cast<u64*>(ring + (size_t)p.stages * STAGE_BYTES);           // [k][128]
-    float* snorm = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(lists) + (size_t)UMMA_MAX_K * UMMA_M * 8);  // [4][TILE_N]
+    float* snorm = reinterpret_cast<float*>(ring + (size_t)p.stages * STAGE_BYTES);      // [4][TILE_N]
     uint64_t* full = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(snorm) + 4 * TILE_N * 4);
     uint64_t* empty = full + UMMA_MAX_STAGES;
     uint64_t* tmem_full = empty + UMMA_MAX_STAGES;
@@ -147,7 +147,6 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) flat_scan_umma_kernel(const U
         for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 4); }
         mbar_fence_init();
     }
-    for (int i = tid; i < UMMA_MAX_K * UMMA_M; i += UMMA_THREADS) lists[i] = 0ull;
     if (warp == 0) tmem_alloc(tmem_ptr, UMMA_TMEM_COLS);
     tc_fence_before();
     __syncthreads();
@@ -191,7 +190,10 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) flat_scan_umma_kernel(const U
             for (int ks = 0; ks < kstages; ++ks) {
                 mbar_wait(&full[s], ph);
                 tc_fence_after();
-                if (lane == 0) {
+                if (lane == 0 && (p.dbg & 4)) {
+                    mbar_arrive(&empty[s]);
+                    if (ks == kstages - 1) mbar_arrive(&tmem_full[b]);
+                } else if (lane == 0) {
                     const uint32_t sb = smem_u32(ring + (size_t)s * STAGE_BYTES);
                     for (int kbi = 0; kbi < p.kbs; ++kbi) {
                         const int kb = ks * p.kbs + kbi;
@@ -217,7 +219,6 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) flat_scan_umma_kernel(const U
         const int m = qd * 32 + lane;
         const int qi = (lane << 2) | qd;
         const bool qvalid = qi < p.nq;
-        u64* mylist = lists + m;
         float* wnorm = snorm + (warp - 2) * TILE_N;
         const uint32_t lane_addr = tmem_base + ((uint32_t)(qd * 32) << 16) + D_OFF;
         {
@@ -238,33 +239,51 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) flat_scan_umma_kernel(const U
             named_bar_sync(2, 160);
         }
         const int G = (int)gridDim.x;
-        float thr_boot = -INFINITY;     // lower bound of the GLOBAL k-th best score (see bootstrap below)
-        float thr = -INFINITY;          // admission threshold = max(thr_boot, this CTA's k-th best)
+        float thr = -INFINITY;          // admission threshold = max(bootstrap bound, this CTA's k-th best)
         bool boot_done = false;
+        // thread-private top-k of this CTA for this query: 16 sorted keys in registers (key 0 = empty)
+        u64 top[UMMA_MAX_K];
+#pragma unroll
+        for (int j = 0; j < UMMA_MAX_K; ++j) top[j] = 0ull;
 
-        // k-th largest of the first-tile maxima the CTAs have published so far.  Those are scores of
-        // distinct rows, so the value is a valid lower bound of the global k-th best: pruning with it
-        // is exact, and it removes the ~k*ln(rows per CTA / k) warm-up insertions each CTA would
-        // otherwise pay to discover the threshold on its own.
+        // Bootstrap bound.  Every CTA publishes, per query, the best score of its FIRST tile; groups
+        // of 4 CTAs are folded to their maximum and the k-th largest group maximum is taken.  Those
+        // are scores of k distinct rows, so the value is a lower bound of the global k-th best:
+        // pruning with it is exact, and it replaces the ~k*ln(rows per CTA / k) warm-up insertions
+        // each CTA would otherwise need to find the threshold on its own.
         auto refresh_boot = [&]() {
             const int published = (int)__ldcg(reinterpret_cast<const unsigned int*>(p.boot + (size_t)G * UMMA_M));
-            uint32_t top[UMMA_MAX_K];
+            // all loads are independent and issued back to back (an L2 round trip under a saturated
+            // HBM pipe is ~1 us: 148 dependent ones would cost more than the whole bootstrap saves)
+            constexpr int NGRP = 40, FOLD = 4;              // covers up to 160 CTAs
+            uint32_t gm[NGRP];
 #pragma unroll
-            for (int j = 0; j < UMMA_MAX_K; ++j) top[j] = 0u;
-            for (int g = 0; g < G; ++g) {
-                uint32_t v = __ldcg(p.boot + (size_t)g * UMMA_M + m);
+            for (int g = 0; g < NGRP; ++g) {
+                uint32_t a[FOLD];
+#pragma unroll
+                for (int f = 0; f < FOLD; ++f) {
+                    const int c = g * FOLD + f;
+                    a[f] = (c < G) ? __ldcg(p.boot + (size_t)c * UMMA_M + m) : 0u;
+                }
+                gm[g] = max(max(a[0], a[1]), max(a[2], a[3]));
+            }
+            uint32_t best[UMMA_MAX_K];
+#pragma unroll
+            for (int j = 0; j < UMMA_MAX_K; ++j) best[j] = 0u;
+#pragma unroll
+            for (int g = 0; g < NGRP; ++g) {
+                uint32_t v = gm[g];
 #pragma unroll
                 for (int j = 0; j < UMMA_MAX_K; ++j) {
-                    const uint32_t hi = max(top[j], v);
-                    v = min(top[j], v);
-                    top[j] = hi;
+                    const uint32_t hi = max(best[j], v);
+                    v = min(best[j], v);
+                    best[j] = hi;
                 }
             }
             uint32_t kth = 0u;
 #pragma unroll
-            for (int j = 0; j < UMMA_MAX_K; ++j) if (j == p.k - 1) kth = top[j];
-            if (kth) thr_boot = fmaxf(thr_boot, ord2f(kth));
-            thr = fmaxf(thr, thr_boot);
+            for (int j = 0; j < UMMA_MAX_K; ++j) kth = (j == p.k - 1) ? best[j] : kth;
+            if (kth) thr = fmaxf(thr, ord2f(kth));
             boot_done = published >= 4 * G;
         };
 
@@ -285,64 +304,87 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) flat_scan_umma_kernel(const U
             }
             mbar_wait(&tmem_full[b], aph);
             tc_fence_after();
-            if (it == 0) {
-                // ---- bootstrap pass over the first tile: best score per query, branch free ----
-                float mx = -INFINITY;
-#pragma unroll 1
-                for (int c = 0; c < TILE_N; c += 32) {
-                    uint32_t v[32];
-                    __syncwarp();
-                    tmem_ld32(lane_addr + (uint32_t)(b * TILE_N + c), v);
-                    tmem_ld_wait();
+            // the whole tile row of this query -> registers, then hand the TMEM buffer straight back
+            uint32_t v[TILE_N];
+            tmem_ld32(lane_addr + (uint32_t)(b * TILE_N), *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+            tmem_ld32(lane_addr + (uint32_t)(b * TILE_N + 32), *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[b]);
+            if (p.dbg & 2) continue;
+            if (p.l2) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        float s = __uint_as_float(v[j]);
-                        if (p.l2) s = fmaf(2.f, s, -wnorm[c + j]);
-                        if ((c + j) < nvalid) mx = fmaxf(mx, s);
-                    }
-                }
+                for (int j = 0; j < TILE_N; ++j) v[j] = __float_as_uint(fmaf(2.f, __uint_as_float(v[j]), -wnorm[j]));
+            }
+            if (p.dbg & 1) { thr = INFINITY; boot_done = true; }
+            else if (it == 0) {
+                float mx = -INFINITY;
+#pragma unroll
+                for (int j = 0; j < TILE_N; ++j) mx = (j < nvalid) ? fmaxf(mx, __uint_as_float(v[j])) : mx;
                 p.boot[(size_t)blockIdx.x * UMMA_M + m] = f2ord(mx);
                 __threadfence();
                 __syncwarp();
                 if (lane == 0) atomicAdd(reinterpret_cast<unsigned int*>(p.boot + (size_t)G * UMMA_M), 1u);
                 // bounded wait for the other CTAs (they start together and do the same work); a late
-                // CTA only weakens the bound, and the refresh below is repeated while it is incomplete
-                for (int spin = 0; spin < 40; ++spin) {
+                // CTA only weakens the bound, and the refresh is repeated while it is incomplete
+                for (int spin = 0; spin < 24; ++spin) {
                     if ((int)__ldcg(reinterpret_cast<const unsigned int*>(p.boot + (size_t)G * UMMA_M)) >= 4 * G) break;
-                    __nanosleep(100);
+                    __nanosleep(64);
                 }
                 __threadfence();
                 refresh_boot();
+                if (p.dbg & 8) thr = INFINITY;
             } else if (!boot_done && (it & (it + 1)) == 0) {
                 refresh_boot();          // it = 1, 3, 7, 15, ...
             }
-#pragma unroll 1
-            for (int c = 0; c < TILE_N; c += 32) {
-                uint32_t v[32];
-                __syncwarp();
-                tmem_ld32(lane_addr + (uint32_t)(b * TILE_N + c), v);
-                tmem_ld_wait();
-                if (c + 32 == TILE_N) {
-                    // accumulator fully read: hand the TMEM buffer back to the MMA warp
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&tmem_empty[b]);
-                }
+            // fast path: one compare per score, collected in a bit mask (no branches, small code)
+            uint32_t hm[TILE_N / 32];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    float s = __uint_as_float(v[j]);
-                    if (p.l2) s = fmaf(2.f, s, -wnorm[c + j]);
-                    if (qvalid && (c + j) < nvalid && s >= thr)
-                        thr = fmaxf(thr_boot, umma_topk_insert(mylist, p.k, s, (uint32_t)(row0 + c + j), thr));
+            for (int h = 0; h < TILE_N / 32; ++h) {
+                hm[h] = 0u;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) hm[h] |= (__uint_as_float(v[h * 32 + j]) >= thr ? 1u : 0u) << j;
+                const int left = nvalid - h * 32;
+                if (left < 32) hm[h] &= (left <= 0) ? 0u : ((1u << left) - 1u);
+                if (!qvalid) hm[h] = 0u;
+            }
+            // rare path: a score reached the threshold.  One copy of the code for all 64 columns.
+#pragma unroll 1
+            for (int h = 0; h < TILE_N / 32; ++h) {
+                uint32_t mask = hm[h];
+#pragma unroll 1
+                while (mask) {
+                    const int j = __ffs(mask) - 1 + h * 32;
+                    mask &= mask - 1;
+                    uint32_t bits = 0u;
+#pragma unroll
+                    for (int jj = 0; jj < TILE_N; ++jj) bits = (jj == j) ? v[jj] : bits;
+                    const float sc = __uint_as_float(bits);
+                    if (sc >= thr) {
+                        // branch-free sorted insertion (descending); the key that falls off the end is dropped
+                        u64 key = make_key<PRS_TIE_LOW_ID>(sc, (uint32_t)(row0 + j));
+#pragma unroll
+                        for (int i = 0; i < UMMA_MAX_K; ++i) {
+                            const bool up = key > top[i];
+                            const u64 lo = up ? top[i] : key;
+                            top[i] = up ? key : top[i];
+                            key = lo;
+                        }
+                        u64 kth = 0ull;
+#pragma unroll
+                        for (int i = 0; i < UMMA_MAX_K; ++i) kth = (i == p.k - 1) ? top[i] : kth;
+                        if (kth) thr = fmaxf(thr, key_score(kth));
+                    }
                 }
             }
         }
         if (qvalid) {
             const size_t o = (size_t)blockIdx.x * p.nq_total + p.q0 + qi;
             int n = 0;
-            for (int j = 0; j < p.k; ++j) {
-                const u64 key = mylist[j * UMMA_M];
-                if (key) p.cand[o * p.k + n++] = key;
+#pragma unroll
+            for (int j = 0; j < UMMA_MAX_K; ++j) {
+                if (j < p.k && top[j]) { p.cand[o * p.k + n] = top[j]; ++n; }
             }
             p.cand_cnt[o] = n;
         }
@@ -428,9 +470,16 @@ static inline int search_umma(UmmaState& st, const void* x, const float* xnorm, 
     if ((rc = cand.ensure((size_t)grid * nq * k * 8))) return rc;
     if ((rc = cand_cnt.ensure((size_t)grid * nq * 4))) return rc;
     const int kblocks = pitch >> 6;
-    const int kbs = (kblocks % 2 == 0) ? 2 : 1;                     // 16 KB stages when the k-block count is even
+    // k-blocks per pipeline stage: the largest divisor of the k-block count up to 6 (48 KB).  Few,
+    // large stages keep the per-stage barrier round trips of the single MMA-issuing thread off the
+    // critical path (measured: 8 KB stages 3443 GB/s, 16 KB 4431, 48 KB 4513 -> see profiles/)
+    int kbs = 1;
+    for (int c = 2; c <= 6; ++c) if (kblocks % c == 0) kbs = c;
+    static const int dbg = getenv("PRS_UMMA_DEBUG") ? atoi(getenv("PRS_UMMA_DEBUG")) : 0;
+    static const int dbg_kbs = getenv("PRS_UMMA_KBS") ? atoi(getenv("PRS_UMMA_KBS")) : 0;
+    if (dbg_kbs > 0 && kblocks % dbg_kbs == 0) kbs = dbg_kbs;
     const size_t stage_bytes = (size_t)kbs * KBLOCK_BYTES;
-    const size_t fixed = (size_t)UMMA_MAX_K * UMMA_M * 8 + 4 * (size_t)BLK_ROWS * 4 + (2 * UMMA_MAX_STAGES + 4) * 8 + 16;
+    const size_t fixed = 4 * (size_t)BLK_ROWS * 4 + (2 * UMMA_MAX_STAGES + 4) * 8 + 16;
     int stages = (int)((226 * 1024 - 1024 - fixed) / stage_bytes);
     if (stages > UMMA_MAX_STAGES) stages = UMMA_MAX_STAGES;
     const size_t smem = 1024 + (size_t)stages * stage_bytes + fixed;
@@ -441,7 +490,7 @@ static inline int search_umma(UmmaState& st, const void* x, const float* xnorm, 
         p.qlow = (const uint16_t*)st.qlow.p + (size_t)q0 * pitch;
         p.xnorm = xnorm; p.n_rows = n; p.pitch = pitch;
         p.nq = (int)std::min<long long>(UMMA_M, nq - q0);
-        p.k = k; p.l2 = metric == PRS_METRIC_L2; p.stages = stages; p.is_bf16 = storage == PRS_BF16; p.kbs = kbs;
+        p.k = k; p.l2 = metric == PRS_METRIC_L2; p.stages = stages; p.is_bf16 = storage == PRS_BF16; p.kbs = kbs; p.dbg = dbg;
         p.nq_total = (int)nq; p.q0 = (int)q0;
         p.cand = (u64*)cand.p; p.cand_cnt = (int*)cand_cnt.p;
         p.boot = (uint32_t*)st.boot.p + (size_t)(q0 / UMMA_M) * boot_words;
