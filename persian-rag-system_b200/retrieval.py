@@ -14,6 +14,7 @@ libprs or a B200 is missing, loading fails (returns False after printing why).
 """
 from __future__ import annotations
 
+import functools
 import gc
 import os
 from typing import Any, Dict, List, Optional, Tuple
@@ -38,231 +39,214 @@ def _load_chunks_csv(chunk_file: str) -> List[Dict[str, Any]]:
     return pd.read_csv(chunk_file, encoding="utf-8").to_dict("records")
 
 
-class RetrievalSystem:
-    def __init__(self, method="dense", model_path=None, device=None, encoder=None, storage="fp32"):
-        """method: "dense" | "bm25" | "tfidf" | "hybrid" (src/retrieval.py:13-21).
+def _guarded(label: str, on_error):
+    """The reference wraps every public method in `try/except -> print -> return [] / False`
+    (src/retrieval.py:47-49,57-59,113-115,141-143,170-172,218-220).  One decorator keeps that
+    contract here; the C ABI reports failures as PrsError, which lands in the same net."""
+    def wrap(fn):
+        @functools.wraps(fn)
+        def inner(self, *args, **kwargs):
+            try:
+                return fn(self, *args, **kwargs)
+            except Exception as exc:                       # noqa: BLE001 - the reference catches everything
+                print(f"Error in {label}: {exc}")
+                return on_error() if callable(on_error) else on_error
+        return inner
+    return wrap
 
-        `encoder` (extension): any object with `.encode(list[str], device=...) -> ndarray`, used
-        instead of loading `SentenceTransformer(model_path)`.  `storage` (extension): how the
-        dense corpus is held in HBM: "fp32" (reference parity), "fp16", "bf16"."""
-        self.method = method
+
+_METHODS = ("dense", "bm25", "tfidf", "hybrid")
+
+
+class RetrievalSystem:
+    """`RetrievalSystem(method, model_path, device)` of src/retrieval.py:12-36 with the engine knobs
+    added as keyword extensions:
+
+    encoder -- any object with `.encode(list[str], device=...) -> ndarray`; used instead of loading
+               `SentenceTransformer(model_path)` (the encoders themselves are unchanged, north-star);
+    storage -- how the dense corpus is held in HBM: "fp32" (reference parity), "fp16", "bf16".
+    """
+
+    def __init__(self, method="dense", model_path=None, device=None, encoder=None, storage="fp32"):
+        self.method, self.storage = method, storage
         self.device = device or ("cuda" if _cuda_available() else "cpu")
-        self.storage = storage
-        if encoder is not None:
-            self.embedding_model = encoder
-        elif method in ["dense", "hybrid"] and model_path:
+        self.embedding_model = encoder
+        if encoder is None and method in ("dense", "hybrid") and model_path:
             print(f"Loading embedding model: {model_path}")
-            from sentence_transformers import SentenceTransformer   # unchanged encoder (north-star)
+            from sentence_transformers import SentenceTransformer
             self.embedding_model = SentenceTransformer(model_path, device=self.device)
-        else:
-            self.embedding_model = None
-        self.chunks = None
-        self.faiss_index = None
-        self.bm25_index = None
-        self.tfidf_vectorizer = None
-        self.tfidf_matrix = None
+        # attributes callers of the reference touch (src/evaluation.py:262-263, gradio launcher)
+        self.chunks = self.faiss_index = self.bm25_index = None
+        self.tfidf_vectorizer = self.tfidf_matrix = None
         self.is_ready = False
 
-    # ------------------------------------------------------------------ load (src/retrieval.py:38-90)
+    # ---------------------------------------------------------------- loading, src/retrieval.py:38-90
     def load_chunks_and_index(self, chunk_file: str, faiss_index_file: str = None):
         print(f"Loading chunks from {chunk_file}...")
         try:
-            self.chunks = _load_chunks_csv(chunk_file)
-            print(f"✓ Loaded {len(self.chunks)} chunks")
-        except Exception as e:
-            print(f"Error loading chunks: {e}")
+            records = _load_chunks_csv(chunk_file)
+        except Exception as exc:                            # noqa: BLE001
+            print(f"Error loading chunks: {exc}")
             return False
-        return self._build_indices(faiss_index_file)
+        print(f"✓ Loaded {len(records)} chunks")
+        return self.load_chunks(records, faiss_index_file)
 
     def load_chunks(self, chunks: List[Dict[str, Any]], faiss_index_file: str = None):
-        """Extension: same as load_chunks_and_index with the chunk records already in memory."""
+        """Extension: the chunk records are already in memory (row i of the index <-> chunks[i])."""
         self.chunks = list(chunks)
-        return self._build_indices(faiss_index_file)
-
-    def _build_indices(self, faiss_index_file):
-        if self.method in ["dense", "hybrid"] and faiss_index_file and os.path.exists(faiss_index_file):
+        wants_dense = self.method in ("dense", "hybrid")
+        # a missing index file is skipped silently, exactly like the reference (:52); dense retrieval
+        # then answers [] (:94-95)
+        steps = []
+        if wants_dense and faiss_index_file and os.path.exists(faiss_index_file):
+            steps.append(("FAISS index", lambda: self._open_dense(faiss_index_file)))
+        if self.method in ("bm25", "hybrid"):
+            steps.append(("BM25 index", self._build_bm25))
+        if self.method in ("tfidf", "hybrid"):
+            steps.append(("TF-IDF index", self._build_tfidf))
+        for what, build in steps:
             try:
-                print(f"Loading FAISS index from {faiss_index_file}...")
-                self.faiss_index = read_index(faiss_index_file, storage=self.storage)
-                print(f"✓ Loaded FAISS index with {self.faiss_index.ntotal} vectors")
-            except Exception as e:
-                print(f"Error loading FAISS index: {e}")
-                return False
-        if self.method in ["bm25", "hybrid"]:
-            print("Building BM25 index...")
-            try:
-                tokenized_chunks = [chunk["text"].split() for chunk in self.chunks]
-                self.bm25_index = BM25Index(tokenized_chunks)
-                print("✓ BM25 index built successfully")
-            except Exception as e:
-                print(f"Error building BM25 index: {e}")
-                return False
-        if self.method in ["tfidf", "hybrid"]:
-            print("Building TF-IDF index...")
-            try:
-                chunk_texts = [chunk["text"] for chunk in self.chunks]
-                self.tfidf_vectorizer = TfidfIndex(chunk_texts, max_features=10000, ngram_range=(1, 2))
-                self.tfidf_matrix = self.tfidf_vectorizer.index
-                print("✓ TF-IDF index built successfully")
-            except Exception as e:
-                print(f"Error building TF-IDF index: {e}")
+                build()
+            except Exception as exc:                        # noqa: BLE001
+                print(f"Error building/loading {what}: {exc}")
                 return False
         self.is_ready = True
         return True
 
-    # ------------------------------------------------------------------ dense (src/retrieval.py:92-115)
+    def _open_dense(self, path):
+        self.faiss_index = read_index(path, storage=self.storage)
+        print(f"✓ Loaded FAISS index with {self.faiss_index.ntotal} vectors into HBM ({self.storage})")
+
+    def _build_bm25(self):
+        # whitespace tokens, no lower-casing, no stop words: src/retrieval.py:66
+        self.bm25_index = BM25Index([record["text"].split() for record in self.chunks])
+        print("✓ BM25 postings on device")
+
+    def _build_tfidf(self):
+        # TfidfVectorizer(max_features=10000, stop_words=None, ngram_range=(1, 2)): src/retrieval.py:78-83
+        self.tfidf_vectorizer = TfidfIndex([record["text"] for record in self.chunks],
+                                           max_features=10000, ngram_range=(1, 2))
+        self.tfidf_matrix = self.tfidf_vectorizer.index
+        print("✓ TF-IDF postings on device")
+
+    def _rows_to_results(self, rows, scores):
+        """(row id, score) pairs -> the reference's list[(chunk_dict, score)], dropping ids outside
+        [0, len(chunks)) as src/retrieval.py:106 does."""
+        n = len(self.chunks)
+        return [(self.chunks[int(r)], s) for r, s in zip(rows, scores) if 0 <= int(r) < n]
+
+    # ---------------------------------------------------------------- dense, src/retrieval.py:92-115
+    @_guarded("dense retrieval", list)
     def retrieve_dense(self, query: str, top_k: int = 10) -> List[Tuple[Dict, float]]:
         if not self.embedding_model or not self.faiss_index:
             return []
-        try:
-            query_embedding = self.embedding_model.encode([query], device=self.device)
-            query_embedding = np.asarray(query_embedding).astype("float32")
-            distances, indices = self.faiss_index.search(query_embedding, top_k)
-            results = []
-            for distance, idx in zip(distances[0], indices[0]):
-                if idx >= 0 and idx < len(self.chunks):
-                    similarity = 1 / (1 + distance)       # squared-L2 -> score, src/retrieval.py:108
-                    results.append((self.chunks[idx], similarity))
-            return results
-        except Exception as e:
-            print(f"Error in dense retrieval: {e}")
-            return []
+        q = np.asarray(self.embedding_model.encode([query], device=self.device)).astype("float32")
+        sq_l2, rows = self.faiss_index.search(q, top_k)
+        return self._rows_to_results(rows[0], 1 / (1 + sq_l2[0]))      # score = 1/(1+d), :108
 
-    # ------------------------------------------------------------------ bm25 (src/retrieval.py:117-143)
+    @_guarded("batched dense retrieval", list)
+    def retrieve_dense_batch(self, queries: List[str], top_k: int = 10) -> List[List[Tuple[Dict, float]]]:
+        """Extension: one encoder call and ONE corpus scan for the whole list of
+        queries -- the reference loops `retrieve` per question (src/evaluation.py:273-299)."""
+        if not self.embedding_model or not self.faiss_index or not queries:
+            return [[] for _ in queries]
+        q = np.asarray(self.embedding_model.encode(list(queries), device=self.device)).astype("float32")
+        sq_l2, rows = self.faiss_index.search(q, top_k)
+        return [self._rows_to_results(rows[i], 1 / (1 + sq_l2[i])) for i in range(len(queries))]
+
+    # ---------------------------------------------------------------- sparse, src/retrieval.py:117-172
+    @_guarded("BM25 retrieval", list)
     def retrieve_bm25(self, query: str, top_k: int = 10) -> List[Tuple[Dict, float]]:
         if not self.bm25_index:
             return []
-        try:
-            scores, top_indices = self.bm25_index.get_top_k(query.split(), top_k)
-            results = []
-            for idx, score in zip(top_indices, scores):
-                if idx < len(self.chunks):
-                    results.append((self.chunks[idx], score))
-            return results
-        except Exception as e:
-            print(f"Error in BM25 retrieval: {e}")
-            return []
+        scores, rows = self.bm25_index.get_top_k(query.split(), top_k)
+        return self._rows_to_results(rows, scores)
 
-    # ------------------------------------------------------------------ tfidf (src/retrieval.py:145-172)
+    @_guarded("TF-IDF retrieval", list)
     def retrieve_tfidf(self, query: str, top_k: int = 10) -> List[Tuple[Dict, float]]:
         if not self.tfidf_vectorizer or self.tfidf_matrix is None:
             return []
-        try:
-            scores, top_indices = self.tfidf_vectorizer.get_top_k(query, top_k)
-            results = []
-            for idx, score in zip(top_indices, scores):
-                if idx < len(self.chunks):
-                    results.append((self.chunks[idx], score))
-            return results
-        except Exception as e:
-            print(f"Error in TF-IDF retrieval: {e}")
-            return []
+        scores, rows = self.tfidf_vectorizer.get_top_k(query, top_k)
+        return self._rows_to_results(rows, scores)
 
-    # ------------------------------------------------------------------ hybrid (src/retrieval.py:174-220)
+    # ---------------------------------------------------------------- hybrid, src/retrieval.py:174-220
+    @_guarded("hybrid retrieval", list)
     def retrieve_hybrid(self, query: str, top_k: int = 10, dense_weight: float = 0.6,
                         bm25_weight: float = 0.4) -> List[Tuple[Dict, float]]:
-        try:
-            dense_results = self.retrieve_dense(query, top_k * 2)
-            bm25_results = self.retrieve_bm25(query, top_k * 2)
-            fused: Dict[Any, Dict[str, Any]] = {}          # insertion order: dense hits first
-            for results, mine, weight in ((dense_results, "dense_score", dense_weight),
-                                          (bm25_results, "bm25_score", bm25_weight)):
-                if not results:
-                    continue
-                top = max(score for _, score in results)
-                for chunk, score in results:
-                    part = (score / top if top > 0 else 0) * weight
-                    slot = fused.get(chunk["id"])
-                    if slot is None:
-                        slot = fused[chunk["id"]] = {"chunk": chunk, "dense_score": 0, "bm25_score": 0}
-                    slot[mine] = part
-            final_results = [(v["chunk"], v["dense_score"] + v["bm25_score"]) for v in fused.values()]
-            final_results.sort(key=lambda pair: pair[1], reverse=True)   # stable, like the reference
-            return final_results[:top_k]
-        except Exception as e:
-            print(f"Error in hybrid retrieval: {e}")
-            return []
+        # top-2k from each retriever, each list divided by its own maximum, weighted sum keyed by
+        # chunk id; dict order = dense hits first, then BM25-only hits; stable descending sort.
+        fused: Dict[Any, list] = {}
+        for hits, weight in ((self.retrieve_dense(query, 2 * top_k), dense_weight),
+                             (self.retrieve_bm25(query, 2 * top_k), bm25_weight)):
+            if not hits:
+                continue
+            peak = max(score for _, score in hits)
+            for chunk, score in hits:
+                entry = fused.setdefault(chunk["id"], [chunk, 0])
+                entry[1] = entry[1] + (score / peak if peak > 0 else 0) * weight
+        ranked = sorted(((c, s) for c, s in fused.values()), key=lambda cs: cs[1], reverse=True)
+        return ranked[:top_k]
 
-    # ------------------------------------------------------------------ dispatcher (src/retrieval.py:222-238)
+    # ---------------------------------------------------------------- dispatcher, src/retrieval.py:222-238
     def retrieve(self, query: str, top_k: int = 10) -> List[Tuple[Dict, float]]:
         if not self.is_ready:
             print("Retrieval system is not ready. Please load chunks and index first.")
             return []
-        handler = {"dense": self.retrieve_dense, "bm25": self.retrieve_bm25,
-                   "tfidf": self.retrieve_tfidf, "hybrid": self.retrieve_hybrid}.get(self.method)
-        if handler is None:
+        if self.method not in _METHODS:
             print(f"Unknown retrieval method: {self.method}")
             return []
-        return handler(query, top_k)
+        return getattr(self, f"retrieve_{self.method}")(query, top_k)
 
-    # ------------------------------------------------------------------ RAG contexts (src/retrieval.py:240-272)
+    # ---------------------------------------------------------------- RAG contexts, src/retrieval.py:240-272
     def get_contexts_for_rag(self, query: str, top_k: int = 5,
                              max_context_length: int = 2000) -> Tuple[List[str], List[Dict]]:
-        contexts: List[str] = []
-        metadata: List[Dict] = []
-        used = 0
+        contexts, metadata, budget = [], [], max_context_length
         for chunk, score in self.retrieve(query, top_k):
             text = chunk["text"]
-            if used + len(text) > max_context_length:
-                room = max_context_length - used
-                if room <= 100:
+            if len(text) > budget:                 # does not fit: keep a truncated tail only if > 100 chars remain
+                if budget <= 100:
                     break
-                text = text[:room] + "..."
+                text = text[:budget] + "..."
             contexts.append(text)
-            metadata.append({"chunk_id": chunk["id"], "score": score,
-                             "chunk_type": chunk.get("chunk_type", "unknown"), "length": len(text)})
-            used += len(text)
-            if used >= max_context_length:
+            metadata.append(dict(chunk_id=chunk["id"], score=score,
+                                 chunk_type=chunk.get("chunk_type", "unknown"), length=len(text)))
+            budget -= len(text)
+            if budget <= 0:
                 break
         return contexts, metadata
 
-    # ------------------------------------------------------------------ Hit@K / MRR (src/retrieval.py:274-323)
+    # ---------------------------------------------------------------- Hit@K / MRR, src/retrieval.py:274-323
     def evaluate_retrieval_quality(self, test_queries: List[Dict],
                                    relevant_chunks: Dict[str, List[str]]) -> Dict[str, float]:
-        print(f"Evaluating retrieval quality on {len(test_queries)} queries...")
-        hits = {1: [], 3: [], 5: []}
-        mrr_scores = []
-        for i, query_data in enumerate(test_queries):
-            if i % 50 == 0:
-                print(f"  Processing query {i+1}/{len(test_queries)}")
-            relevant = relevant_chunks.get(query_data.get("id", str(i)), [])
-            if not relevant:
+        cuts = (1, 3, 5)
+        hit_flags = {c: [] for c in cuts}
+        reciprocal_ranks = []
+        for pos, item in enumerate(test_queries):
+            wanted = relevant_chunks.get(item.get("id", str(pos)), [])
+            if not wanted:                          # queries without labels are skipped (:291-292)
                 continue
-            retrieved_ids = [chunk["id"] for chunk, _ in self.retrieve(query_data["question"], top_k=10)]
-            for cut in hits:
-                hits[cut].append(any(cid in relevant for cid in retrieved_ids[:cut]))
-            mrr = 0.0
-            for rank, cid in enumerate(retrieved_ids, 1):
-                if cid in relevant:
-                    mrr = 1.0 / rank
-                    break
-            mrr_scores.append(mrr)
-        results = {
-            "hit_at_1": np.mean(hits[1]) if hits[1] else 0.0,
-            "hit_at_3": np.mean(hits[3]) if hits[3] else 0.0,
-            "hit_at_5": np.mean(hits[5]) if hits[5] else 0.0,
-            "mrr": np.mean(mrr_scores) if mrr_scores else 0.0,
-            "total_queries": len(test_queries),
-        }
-        print("✓ Retrieval evaluation completed")
-        print(f"  Hit@1: {results['hit_at_1']:.3f}")
-        print(f"  Hit@3: {results['hit_at_3']:.3f}")
-        print(f"  Hit@5: {results['hit_at_5']:.3f}")
-        print(f"  MRR: {results['mrr']:.3f}")
-        return results
+            got = [chunk["id"] for chunk, _ in self.retrieve(item["question"], top_k=10)]
+            for c in cuts:
+                hit_flags[c].append(any(cid in wanted for cid in got[:c]))
+            first = next((rank for rank, cid in enumerate(got, 1) if cid in wanted), None)
+            reciprocal_ranks.append(1.0 / first if first else 0.0)
+        report = {f"hit_at_{c}": (np.mean(hit_flags[c]) if hit_flags[c] else 0.0) for c in cuts}
+        report["mrr"] = np.mean(reciprocal_ranks) if reciprocal_ranks else 0.0
+        report["total_queries"] = len(test_queries)
+        print("✓ Retrieval evaluation: " + ", ".join(f"Hit@{c}={report[f'hit_at_{c}']:.3f}" for c in cuts)
+              + f", MRR={report['mrr']:.3f}")
+        return report
 
-    # ------------------------------------------------------------------ cleanup (src/retrieval.py:325-336)
+    # ---------------------------------------------------------------- cleanup, src/retrieval.py:325-336
     def cleanup(self):
-        for name in ("embedding_model", "faiss_index", "chunks"):
-            if hasattr(self, name):
-                delattr(self, name)
+        """Drop the encoder, the device index and the chunks (frees the HBM copies)."""
+        for attr in ("embedding_model", "faiss_index", "bm25_index", "tfidf_vectorizer", "tfidf_matrix", "chunks"):
+            self.__dict__.pop(attr, None)
+        self.is_ready = False
         gc.collect()
-        try:
+        if _cuda_available():
             import torch
-            if torch.cuda.is_available():
-                torch.cuda.empty_cache()
-        except Exception:
-            pass
+            torch.cuda.empty_cache()
 
 
 class MultiModelRetrieval:
