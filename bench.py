@@ -53,6 +53,7 @@ def parse():
     ap.add_argument("--storage", default="fp16", choices=["fp16", "bf16", "fp32"])
     ap.add_argument("--metric", default="ip", choices=["ip", "l2"])
     ap.add_argument("--path", default="auto", choices=["auto", "cuda-core", "tcgen05"])
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"], help="N>1: fused peer-memory exchange, or ncclAllGather + merge")
     ap.add_argument("--no-sweep", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sweep-out", default="")
@@ -194,7 +195,7 @@ def workload_config(a, world):
     return {"workload": f"configs[1]: multilingual-e5-base shape d={a.d}, {a.rows} synthetic unit-norm chunks, "
                         f"exact {'cosine/IP' if a.metric == 'ip' else 'L2'} search, k={a.k}, 1xB200",
             "rows": a.rows, "d": a.d, "k": a.k, "batch": a.batch, "storage": a.storage, "metric": a.metric,
-            "sharding": f"rows/{world}" if world > 1 else "none",
+            "sharding": f"rows/{world}, exchange={a.exchange}" if world > 1 else "none",
             "cache": "inputs larger than L2 (corpus shard vs 126 MB L2)"}
 
 
@@ -223,7 +224,7 @@ def run_b200(a):
     # ---- corpus: on-device Philox, unit-norm rows in fp32, cast to storage ----
     lo, hi = shard_bounds(a.rows, world, rank)
     n_local = hi - lo
-    sh = ShardedFlatIndex(a.d, metric_code, a.storage, device=local)
+    sh = ShardedFlatIndex(a.d, metric_code, a.storage, device=local, exchange=a.exchange, nq_cap=max(a.batch, 64), k_cap=max(a.k, 16))
     idx = sh.local
     idx.reserve(n_local)
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
@@ -420,6 +421,8 @@ def run_b200(a):
         except AssertionError as e:
             out["parity"] = {"error": str(e)[:300]}
 
+    if world > 1:
+        sh.check_exchange()
     if rank == 0:
         print(json.dumps(out))
     if world > 1:

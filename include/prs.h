@@ -125,6 +125,30 @@ int prs_merge_topk_device(const float* D_parts, const int64_t* I_parts, int npar
                           int largest, int tie_high_id, float* D, int64_t* I, int device, void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * Row-sharded search with the exchange fused into the merge kernel (one process per GPU).
+ * Each rank creates an exchange buffer, publishes its CUDA IPC handle (prs_xchg_handle_bytes()
+ * bytes), gathers the handles of all ranks of the box (any transport: torch.distributed, MPI, a
+ * file) and opens them; the buffers are then mapped peer memory over NVLink.  A sharded search is
+ * the local scan followed by ONE kernel that merges the local per-CTA lists, stores the local
+ * top-k into every peer's buffer, waits for the peers' lists and merges them: no collective
+ * launch, 12*nq*k bytes per rank pair.  It is a collective: every rank must call it the same
+ * number of times with the same nq and k, and must hold at least one row.  Results are identical
+ * on every rank and identical to the unsharded index (ties on global ids).
+ * nq_cap / k_cap bound the nq*k of one search (buffer = 2*n_ranks*nq_cap*k_cap*12 bytes).
+ * ------------------------------------------------------------------------------------- */
+typedef struct prs_xchg prs_xchg;
+int prs_xchg_create(int device, int n_ranks, int rank, int64_t nq_cap, int k_cap, prs_xchg** out);
+int prs_xchg_handle_bytes(void);
+int prs_xchg_get_handle(prs_xchg* x, void* handle_out);
+/* handles: n_ranks consecutive handles in rank order (this rank's own entry is ignored) */
+int prs_xchg_open_peers(prs_xchg* x, const void* handles);
+/* 0, or PRS_ECUDA if a search timed out waiting for a peer (synchronises the device) */
+int prs_xchg_status(prs_xchg* x);
+void prs_xchg_free(prs_xchg* x);
+int prs_index_search_sharded_device(prs_index* idx, prs_xchg* x, const void* q, int qdtype, int64_t nq, int k,
+                                    float* D, int64_t* I, void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * Sparse scoring (BM25 / TF-IDF) over an inverted index.
  * replaces: BM25Okapi(tokenized_chunks)             src/retrieval.py:67   (build)
  *           bm25_index.get_scores(query_tokens)     src/retrieval.py:127  + np.argsort(...)[::-1][:k] :130

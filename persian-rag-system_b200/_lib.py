@@ -43,6 +43,13 @@ SIGNATURES = {
     "prs_index_write": (c_int, [c_void_p, c_char_p]),
     "prs_index_read": (c_int, [c_char_p, c_int, c_int, ctypes.POINTER(c_void_p)]),
     "prs_merge_topk_device": (c_int, [c_void_p, c_void_p, c_int, c_i64, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p]),
+    "prs_xchg_create": (c_int, [c_int, c_int, c_int, c_i64, c_int, ctypes.POINTER(c_void_p)]),
+    "prs_xchg_handle_bytes": (c_int, []),
+    "prs_xchg_get_handle": (c_int, [c_void_p, c_void_p]),
+    "prs_xchg_open_peers": (c_int, [c_void_p, c_void_p]),
+    "prs_xchg_status": (c_int, [c_void_p]),
+    "prs_xchg_free": (None, [c_void_p]),
+    "prs_index_search_sharded_device": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_i64, c_int, c_void_p, c_void_p, c_void_p]),
     "prs_sparse_build": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_i64, ctypes.c_int32, c_int, ctypes.POINTER(c_void_p)]),
     "prs_sparse_free": (None, [c_void_p]),
     "prs_sparse_ndocs": (c_i64, [c_void_p]),

@@ -14,6 +14,7 @@
 #include "flat_umma.cuh"
 #include "host_common.h"
 #include "topk_merge.cuh"
+#include "xchg.cuh"
 
 namespace prs {
 
@@ -182,6 +183,34 @@ struct prs_index {
     UmmaState umma;
     ScanTimer timer;
 };
+static thread_local struct prs_xchg* t_xchg = nullptr;   // set by the calling thread for the duration of a sharded search
+
+// peer-memory exchange buffer of one rank (see xchg.cuh)
+struct prs_xchg {
+    int device = 0, G = 1, rank = 0, nq_cap = 0;
+    long long cap = 0;
+    void* base = nullptr;                 // local allocation: vals | ids | flags | status
+    size_t bytes = 0;
+    void* peer_base[XCHG_MAX_RANKS] = {};
+    bool opened[XCHG_MAX_RANKS] = {};
+    uint32_t gen = 0;
+    XchgView view{};
+    int* status = nullptr;
+};
+
+static inline size_t xchg_vals_bytes(const prs_xchg* x) { return (size_t)2 * x->G * x->cap * 4; }
+static inline size_t xchg_ids_bytes(const prs_xchg* x) { return (size_t)2 * x->G * x->cap * 8; }
+static inline size_t xchg_flags_bytes(const prs_xchg* x) { return (((size_t)2 * x->G * x->nq_cap * 4) + 255) & ~(size_t)255; }
+static void xchg_fill_view(prs_xchg* x) {
+    x->view.cap = x->cap; x->view.nq_cap = x->nq_cap; x->view.G = x->G; x->view.rank = x->rank;
+    for (int p = 0; p < x->G; ++p) {
+        unsigned char* b = (unsigned char*)x->peer_base[p];
+        x->view.ids[p] = (long long*)b;                                  // 8-byte aligned first
+        x->view.vals[p] = (float*)(b + xchg_ids_bytes(x));
+        x->view.flags[p] = (uint32_t*)(b + xchg_ids_bytes(x) + xchg_vals_bytes(x));
+    }
+    x->status = (int*)((unsigned char*)x->base + xchg_ids_bytes(x) + xchg_vals_bytes(x) + xchg_flags_bytes(x));
+}
 
 static int index_grow(prs_index* idx, long long n_total) {
     if (idx->storage != PRS_F32) n_total = (n_total + BLK_ROWS - 1) / BLK_ROWS * BLK_ROWS;   // whole T64 blocks
@@ -261,6 +290,17 @@ static int launch_merge(prs_index* idx, int parts, long long nq, int k, int out_
                         float* D, int64_t* I, cudaStream_t st) {
     const int sortn = next_pow2(k + MERGE_THREADS);
     const size_t smem = (size_t)sortn * 8 + 16;
+    if (t_xchg) {
+        prs_xchg* x = t_xchg;
+        ++x->gen;
+        PRS_CUDA(cudaFuncSetAttribute(merge_xchg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        merge_xchg_kernel<<<(unsigned)nq, MERGE_THREADS, smem, st>>>((const u64*)idx->cand.p, (const int*)idx->cand_cnt.p, parts,
+                                                                    (int)nq, k, sortn, out_mode, qnorm, idx->id_offset,
+                                                                    idx->metric == PRS_METRIC_IP ? 1 : 0, x->view, x->gen, D,
+                                                                    (long long*)I, x->status);
+        PRS_LAUNCH_CHECK();
+        return 0;
+    }
     PRS_CUDA(cudaFuncSetAttribute(merge_cand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     merge_cand_kernel<<<(unsigned)nq, MERGE_THREADS, smem, st>>>((const u64*)idx->cand.p, (const int*)idx->cand_cnt.p, parts,
                                                                 (int)nq, k, sortn, out_mode, qnorm, idx->id_offset, D,
@@ -568,6 +608,94 @@ int prs_merge_topk_device(const float* Dp, const int64_t* Ip, int nparts, int64_
                                                                                    largest, tie_high_id, D, (long long*)I);
     PRS_LAUNCH_CHECK();
     return 0;
+}
+
+// ---- row-sharded search over peer memory (xchg.cuh) ----
+int prs_xchg_create(int device, int n_ranks, int rank, int64_t nq_cap, int k_cap, prs_xchg** out) {
+    if (!out) { set_error("xchg_create: out is null"); return PRS_EINVAL; }
+    *out = nullptr;
+    if (n_ranks < 1 || n_ranks > XCHG_MAX_RANKS || rank < 0 || rank >= n_ranks || nq_cap < 1 || nq_cap > (1 << 22) ||
+        k_cap < 1 || k_cap > PRS_MAX_K) { set_error("xchg_create: bad arguments"); return PRS_EINVAL; }
+    int arch = prs_device_arch(device);
+    if (arch < 0) return arch;
+    DeviceGuard g(device);
+    prs_xchg* x = new (std::nothrow) prs_xchg();
+    if (!x) { set_error("out of host memory"); return PRS_ENOMEM; }
+    x->device = device; x->G = n_ranks; x->rank = rank; x->nq_cap = (int)nq_cap; x->cap = nq_cap * k_cap;
+    x->bytes = xchg_ids_bytes(x) + xchg_vals_bytes(x) + xchg_flags_bytes(x) + 256;
+    cudaError_t e = cudaMalloc(&x->base, x->bytes);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        set_error("xchg_create: cudaMalloc(%zu) failed: %s", x->bytes, cudaGetErrorString(e));
+        delete x;
+        return PRS_ENOMEM;
+    }
+    PRS_CUDA(cudaMemset(x->base, 0, x->bytes));
+    PRS_CUDA(cudaDeviceSynchronize());
+    x->peer_base[rank] = x->base;
+    xchg_fill_view(x);
+    *out = x;
+    return 0;
+}
+
+int prs_xchg_handle_bytes(void) { return (int)sizeof(cudaIpcMemHandle_t); }
+
+int prs_xchg_get_handle(prs_xchg* x, void* handle_out) {
+    if (!x || !handle_out) { set_error("xchg_get_handle: bad arguments"); return PRS_EINVAL; }
+    DeviceGuard g(x->device);
+    cudaIpcMemHandle_t h;
+    PRS_CUDA(cudaIpcGetMemHandle(&h, x->base));
+    memcpy(handle_out, &h, sizeof(h));
+    return 0;
+}
+
+int prs_xchg_open_peers(prs_xchg* x, const void* handles) {
+    if (!x || !handles) { set_error("xchg_open_peers: bad arguments"); return PRS_EINVAL; }
+    DeviceGuard g(x->device);
+    for (int p = 0; p < x->G; ++p) {
+        if (p == x->rank || x->opened[p]) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const unsigned char*)handles + (size_t)p * sizeof(h), sizeof(h));
+        void* ptr = nullptr;
+        PRS_CUDA(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+        x->peer_base[p] = ptr; x->opened[p] = true;
+    }
+    xchg_fill_view(x);
+    return 0;
+}
+
+int prs_xchg_status(prs_xchg* x) {
+    if (!x) { set_error("null exchange"); return PRS_EINVAL; }
+    DeviceGuard g(x->device);
+    int st = 0;
+    PRS_CUDA(cudaMemcpy(&st, x->status, sizeof(int), cudaMemcpyDeviceToHost));
+    if (st) { set_error("sharded search: timed out waiting for a peer rank's candidate lists"); return PRS_ECUDA; }
+    return 0;
+}
+
+void prs_xchg_free(prs_xchg* x) {
+    if (!x) return;
+    DeviceGuard g(x->device);
+    cudaDeviceSynchronize();
+    for (int p = 0; p < x->G; ++p) if (x->opened[p]) cudaIpcCloseMemHandle(x->peer_base[p]);
+    if (x->base) cudaFree(x->base);
+    delete x;
+}
+
+int prs_index_search_sharded_device(prs_index* idx, prs_xchg* x, const void* q, int qdtype, int64_t nq, int k,
+                                    float* D, int64_t* I, void* stream) {
+    if (!idx || !x) { set_error("sharded search: null handle"); return PRS_EINVAL; }
+    if (x->device != idx->device) { set_error("sharded search: index and exchange buffer live on different devices"); return PRS_EINVAL; }
+    if (nq < 1 || nq > x->nq_cap || k < 1 || (long long)nq * k > x->cap) {
+        set_error("sharded search: nq=%lld k=%d exceed the exchange buffer (nq_cap=%d, entries=%lld)", (long long)nq, k, x->nq_cap, x->cap);
+        return PRS_EINVAL;
+    }
+    for (int p = 0; p < x->G; ++p) if (!x->peer_base[p]) { set_error("sharded search: peer %d not opened", p); return PRS_EINVAL; }
+    DeviceGuard g(idx->device);
+    if (idx->n == 0) { set_error("sharded search: every rank must hold at least one row"); return PRS_EINVAL; }
+    struct Scope { ~Scope() { t_xchg = nullptr; } } scope;
+    t_xchg = x;               // read by launch_merge on this thread
+    return search_device_impl(idx, q, qdtype, nq, k, D, I, (cudaStream_t)stream);
 }
 
 // ---- on-disk format: faiss IndexFlat (IxF2 / IxFI), SURVEY.md 8f-2 ----

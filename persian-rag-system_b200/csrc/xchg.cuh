@@ -1,0 +1,121 @@
+// xchg.cuh -- row-sharded search: local merge + exchange over NVLink peer memory + global merge
+// in ONE kernel (replaces local merge -> 2 x ncclAllGather -> merge).
+//
+// Every rank owns an exchange buffer (cudaMalloc, shared with the other ranks of the box through
+// CUDA IPC, i.e. mapped peer memory over NVLink / NVSwitch):
+//     vals [2 slots][G ranks][cap] float      ids [2][G][cap] int64      flags [2][G][nq_cap] uint32
+// CTA q of rank r merges the per-CTA candidate lists of its local scan into the local top-k of
+// query q, STORES that list into slot[.][r] of every rank's buffer (plain st.global on mapped peer
+// pointers, 12*k bytes per peer), fences at system scope and publishes flag = generation; then it
+// waits (bounded spin, ld.acquire.sys on its OWN memory) for the G-1 other ranks' lists of the same
+// query and merges the G lists.  Only 12*nq*k bytes per rank pair cross NVLink and there is no
+// separate collective launch.  Two slots alternate by generation: a rank can only be two searches
+// ahead of another after that rank has finished reading the older slot (its next exchange kernel
+// is stream-ordered behind the read), so a slot is never overwritten while it is being read.
+#pragma once
+#include "common.cuh"
+#include "topk_merge.cuh"
+
+namespace prs {
+
+constexpr int XCHG_MAX_RANKS = 16;
+
+struct XchgView {
+    float* vals[XCHG_MAX_RANKS];          // base of rank p's vals array (peer-mapped; [rank] is local)
+    long long* ids[XCHG_MAX_RANKS];
+    uint32_t* flags[XCHG_MAX_RANKS];
+    long long cap;                        // entries per (slot, rank)
+    int nq_cap, G, rank;
+};
+
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// out_mode as in merge_cand_kernel.  largest: 1 for IP, 0 for L2 (order of the exchanged values).
+__global__ void __launch_bounds__(MERGE_THREADS) merge_xchg_kernel(
+    const u64* __restrict__ cand, const int* __restrict__ cand_cnt, int parts, int nq, int k, int sortn,
+    int out_mode, const float* __restrict__ qnorm, long long id_offset, int largest,
+    const XchgView xv, uint32_t gen, float* __restrict__ D, long long* __restrict__ I, int* __restrict__ status) {
+    extern __shared__ __align__(16) unsigned char msm[];
+    u64* buf = reinterpret_cast<u64*>(msm);
+    int* s_n = reinterpret_cast<int*>(msm + (size_t)sortn * 8);
+    const int q = blockIdx.x, tid = threadIdx.x;
+    const int G = xv.G, slot = (int)(gen & 1u);
+
+    // ---- 1. local merge over this rank's CTAs ----
+    auto fetch = [&](long long i) -> u64 {
+        const int part = (int)(i / k), j = (int)(i - (long long)part * k);
+        const size_t o = (size_t)part * nq + q;
+        return (j < cand_cnt[o]) ? cand[o * k + j] : 0ull;
+    };
+    const int n = block_topk_stream(fetch, (long long)parts * k, k, buf, sortn, s_n, tid, MERGE_THREADS, 1);
+
+    // ---- 2. push the local list into every rank's buffer (slot, my rank, query q) ----
+    const size_t ebase = ((size_t)slot * G + xv.rank) * (size_t)xv.cap + (size_t)q * k;
+    for (int j = tid; j < k; j += MERGE_THREADS) {
+        float dv;
+        long long iv;
+        if (j < n) {
+            const u64 key = buf[j];
+            const float s = key_score(key);
+            dv = out_mode == 0 ? s : (out_mode == 1 ? -s : fmaxf(0.f, qnorm[q] - s));
+            iv = (long long)key_id<PRS_TIE_LOW_ID>(key) + id_offset;
+        } else {
+            dv = out_mode == 0 ? -3.402823466e+38f : 3.402823466e+38f;
+            iv = -1;
+        }
+        for (int p = 0; p < G; ++p) {
+            xv.vals[p][ebase + j] = dv;
+            xv.ids[p][ebase + j] = iv;
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid < G) {
+        __threadfence_system();
+        st_release_sys(xv.flags[tid] + ((size_t)slot * G + xv.rank) * xv.nq_cap + q, gen);
+    }
+    // ---- 3. wait for the other ranks' lists of this query (they arrive in MY memory) ----
+    if (tid < G) {
+        const uint32_t* f = xv.flags[xv.rank] + ((size_t)slot * G + tid) * xv.nq_cap + q;
+        long long spins = 0;
+        while (ld_acquire_sys(f) != gen) {
+            __nanosleep(64);
+            if (++spins > (1ll << 24)) { atomicExch(status, 1); break; }      // ~1 s: a peer died or never searched
+        }
+    }
+    __syncthreads();
+
+    // ---- 4. merge the G lists (positions order ties like the global id does: shards hold ascending blocks) ----
+    const float* Dp = xv.vals[xv.rank] + (size_t)slot * G * (size_t)xv.cap;
+    const long long* Ip = xv.ids[xv.rank] + (size_t)slot * G * (size_t)xv.cap;
+    auto fetch2 = [&](long long i) -> u64 {
+        const int part = (int)(i / k), j = (int)(i - (long long)part * k);
+        const size_t o = (size_t)part * (size_t)xv.cap + (size_t)q * k + j;
+        if (__ldcg(Ip + o) < 0) return 0ull;
+        const float v = __ldcg(Dp + o);
+        const float s = sanitize(largest ? v : -v);
+        return ((u64)f2ord(s) << 32) | (u64)(~(uint32_t)(part * k + j));
+    };
+    const int n2 = block_topk_stream(fetch2, (long long)G * k, k, buf, sortn, s_n, tid, MERGE_THREADS, 1);
+    for (int j = tid; j < k; j += MERGE_THREADS) {
+        if (j < n2) {
+            const uint32_t pos = ~(uint32_t)buf[j];
+            const int part = (int)(pos / k), jj = (int)(pos - (uint32_t)part * k);
+            const size_t o = (size_t)part * (size_t)xv.cap + (size_t)q * k + jj;
+            D[(size_t)q * k + j] = __ldcg(Dp + o);
+            I[(size_t)q * k + j] = __ldcg(Ip + o);
+        } else {
+            D[(size_t)q * k + j] = largest ? -3.402823466e+38f : 3.402823466e+38f;
+            I[(size_t)q * k + j] = -1;
+        }
+    }
+}
+
+}  // namespace prs

@@ -2,9 +2,11 @@
 
 One process per GPU (torchrun).  Rank g holds the contiguous row block
 [g*ceil(N/G), min(N, (g+1)*ceil(N/G))) in its own FlatIndex; queries are replicated.  A search is
-  local fused scan + top-k (csrc kernels)  ->  ncclAllGather of the [nq, k] (score, global id)
-  lists over NVLink  ->  on-device G-way merge (prs_merge_topk_device),
-so only 12*nq*k bytes per rank cross NVLink.  Ties are broken on GLOBAL ids, so the sharded
+the local fused scan + top-k, then ONE kernel (csrc/xchg.cuh) that merges the local per-CTA lists,
+stores the local top-k straight into every peer's exchange buffer over NVLink (CUDA IPC mapped peer
+memory), waits for the peers' lists and merges the G lists -- no collective launch, 12*nq*k bytes per
+rank pair.  `exchange="nccl"` keeps the plain variant (ncclAllGather of the [nq, k] lists +
+prs_merge_topk_device), which is also what searches larger than the exchange buffer use.  Ties are broken on GLOBAL ids, so the sharded
 result is bit-identical to the unsharded one.  With the `gloo` backend (CPU tests) the gather
 goes through host tensors; the merge is still the device kernel when a GPU is present.
 """
@@ -43,7 +45,8 @@ def merge_topk(D_parts, I_parts, largest: bool, tie_high_id: bool = False):
 class ShardedFlatIndex:
     """FlatIndex whose rows are split across the ranks of a torch.distributed process group."""
 
-    def __init__(self, d: int, metric: int = METRIC_L2, storage="fp16", group=None, device: int | None = None):
+    def __init__(self, d: int, metric: int = METRIC_L2, storage="fp16", group=None, device: int | None = None,
+                 exchange: str = "p2p", nq_cap: int = 1024, k_cap: int = 128):
         import torch.distributed as dist
         self.dist = dist
         self.group = group
@@ -54,6 +57,42 @@ class ShardedFlatIndex:
         self.d = d
         self.offset = 0
         self.ntotal_global = 0
+        self.exchange = exchange
+        self._x = ctypes.c_void_p()
+        self._cap = (int(nq_cap), int(nq_cap) * int(k_cap))
+        if self.world > 1 and exchange == "p2p":
+            self._open_exchange(nq_cap, k_cap)
+
+    def _open_exchange(self, nq_cap: int, k_cap: int) -> None:
+        """Create this rank's exchange buffer and map every peer's over CUDA IPC (NVLink peer memory)."""
+        import torch
+        L = _lib.lib()
+        dev = self.local.device
+        check(L.prs_xchg_create(dev, self.world, self.rank, int(nq_cap), int(k_cap), ctypes.byref(self._x)))
+        hb = int(L.prs_xchg_handle_bytes())
+        mine = (ctypes.c_ubyte * hb)()
+        check(L.prs_xchg_get_handle(self._x, mine))
+        on_gpu = self.dist.get_backend(self.group) == "nccl"
+        tdev = torch.device("cuda", dev) if on_gpu else torch.device("cpu")
+        t = torch.tensor(list(mine), dtype=torch.uint8, device=tdev)
+        allh = torch.empty(self.world * hb, dtype=torch.uint8, device=tdev)
+        self.dist.all_gather_into_tensor(allh, t, group=self.group)
+        raw = bytes(allh.cpu().tolist())
+        check(L.prs_xchg_open_peers(self._x, raw))
+        self.dist.barrier(group=self.group)
+
+    def check_exchange(self) -> None:
+        """Raises if any fused search timed out waiting for a peer (synchronises the device)."""
+        if self._x.value:
+            check(_lib.lib().prs_xchg_status(self._x))
+
+    def __del__(self):
+        try:
+            if getattr(self, "_x", None) is not None and self._x.value:
+                _lib.lib().prs_xchg_free(self._x)
+                self._x = ctypes.c_void_p()
+        except Exception:
+            pass
 
     def add_local(self, x, global_offset: int, n_total_global: int) -> None:
         """Add this rank's row block; `global_offset` is the global id of its first row."""
@@ -69,6 +108,17 @@ class ShardedFlatIndex:
     def search(self, q, k: int):
         """q: CUDA tensor [nq, d] replicated on every rank -> (D, I) CUDA tensors on every rank."""
         import torch
+        if self.world > 1 and self._x.value and int(q.shape[0]) <= self._cap[0] and int(q.shape[0]) * int(k) <= self._cap[1]:
+            from .flat import _torch_dtype_code
+            q = q.contiguous()
+            nq = int(q.shape[0])
+            D = torch.empty((nq, k), dtype=torch.float32, device=q.device)
+            I = torch.empty((nq, k), dtype=torch.int64, device=q.device)
+            st = torch.cuda.current_stream(q.device).cuda_stream
+            check(_lib.lib().prs_index_search_sharded_device(self.local._h, self._x, ctypes.c_void_p(q.data_ptr()), _torch_dtype_code(q),
+                                                             nq, int(k), ctypes.c_void_p(D.data_ptr()), ctypes.c_void_p(I.data_ptr()),
+                                                             ctypes.c_void_p(st)))
+            return D, I
         D, I = self.local.search(q, k)
         if self.world == 1:
             return D, I
