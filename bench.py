@@ -298,6 +298,7 @@ def run_b200(a):
     sampler.on = False
     launches = L.prs_launch_count() - launches0
     scan_ms, scan_launches = idx.scan_time()
+    prep_ms, merge_ms = idx.phase_times()
     idx.set_timing(False)
     last_path = idx.last_path
 
@@ -364,6 +365,8 @@ def run_b200(a):
         "e2e": {"value": qps_e2e, "unit": "queries/s", "h2d_bytes_per_step": a.batch * a.d * 4,
                 "d2h_bytes_per_step": a.batch * a.k * 12, "ms_per_step": e2e_ms / a.steps,
                 "api": "prs_index_search_host (pinned host q, D, I)" if world == 1 else "ShardedFlatIndex.search with pinned H2D/D2H"},
+        "step_breakdown_ms": {"prep_kernel": prep_ms / a.steps, "scan_kernel": scan_ms / a.steps, "merge_kernel": merge_ms / a.steps,
+                              "rest (launch gaps, event records)": dev_ms / a.steps - (prep_ms + scan_ms + merge_ms) / a.steps},
         "gpu_launches": launches,
         "l2_flush_between_steps": bool(flush),
     }

@@ -102,6 +102,9 @@ int prs_index_last_path(const prs_index* idx);
  * launches since the previous call, and resets both. */
 int prs_index_set_timing(prs_index* idx, int enable);
 int prs_index_scan_time(prs_index* idx, double* total_ms, int64_t* launches);
+/* same instrumentation for the two small kernels around the scan: summed device time of the
+ * query-preparation kernel and of the merge (or merge+exchange) kernel since the last call */
+int prs_index_phase_times(prs_index* idx, double* prep_ms, double* merge_ms);
 
 /* copy rows [i0, i0+n) back as float32 (index.reconstruct_n) */
 int prs_index_reconstruct_host(prs_index* idx, int64_t i0, int64_t n, float* out);

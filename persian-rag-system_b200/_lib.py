@@ -39,6 +39,7 @@ SIGNATURES = {
     "prs_index_last_path": (c_int, [c_void_p]),
     "prs_index_set_timing": (c_int, [c_void_p, c_int]),
     "prs_index_scan_time": (c_int, [c_void_p, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(c_i64)]),
+    "prs_index_phase_times": (c_int, [c_void_p, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]),
     "prs_index_reconstruct_host": (c_int, [c_void_p, c_i64, c_i64, c_void_p]),
     "prs_index_write": (c_int, [c_void_p, c_char_p]),
     "prs_index_read": (c_int, [c_char_p, c_int, c_int, ctypes.POINTER(c_void_p)]),

@@ -130,7 +130,8 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_parts_kernel(
     int largest, int tie_high, float* __restrict__ D, long long* __restrict__ I) {
     extern __shared__ __align__(16) unsigned char msm[];
     u64* buf = reinterpret_cast<u64*>(msm);
-    int* s_n = reinterpret_cast<int*>(msm + (size_t)sortn * 8);
+    u64* heads = buf + sortn;
+    int* s_n = reinterpret_cast<int*>(heads + MERGE_THREADS);
     const long long q = blockIdx.x;
     const int tid = threadIdx.x;
     // position p = part * k + j.  Within a part equal scores are already ordered by the tie
@@ -144,7 +145,7 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_parts_kernel(
         const uint32_t lo = tie_high ? (uint32_t)(part * k + (k - 1 - j)) : ~(uint32_t)(part * k + j);
         return ((u64)f2ord(s) << 32) | lo;
     };
-    const int n = block_topk_stream(fetch, (long long)nparts * k, k, buf, sortn, s_n, tid, MERGE_THREADS, 1);
+    const int n = block_topk_lists(fetch, nparts, k, buf, sortn, heads, s_n, tid);
     for (int j = tid; j < k; j += MERGE_THREADS) {
         if (j < n) {
             const uint32_t lo = (uint32_t)buf[j];
@@ -181,7 +182,7 @@ struct prs_index {
     bool ws_used = false;
     DevBuf lists, cand, cand_cnt, qf32, qnorm, qlow, hD, hI, hQ, stage;
     UmmaState umma;
-    ScanTimer timer;
+    ScanTimer timer, timer_prep, timer_merge;
 };
 static thread_local struct prs_xchg* t_xchg = nullptr;   // set by the calling thread for the duration of a sharded search
 
@@ -286,15 +287,21 @@ static int launch_simt(int storage, bool l2, int QB, int R, const SimtParams& p,
     }
 }
 
+static inline int merge_sortn(long long total, int k) {
+    const long long one_shot = total <= MERGE_ONESHOT ? total : 0;
+    return next_pow2((int)std::max<long long>(k + MERGE_THREADS, one_shot));
+}
+
 static int launch_merge(prs_index* idx, int parts, long long nq, int k, int out_mode, const float* qnorm,
                         float* D, int64_t* I, cudaStream_t st) {
-    const int sortn = next_pow2(k + MERGE_THREADS);
-    const size_t smem = (size_t)sortn * 8 + 16;
+    const int sortn = merge_sortn((long long)parts * k, k);
+    const size_t smem = (size_t)sortn * 8 + MERGE_THREADS * 8 + 16;
+    struct T { ScanTimer& t; cudaStream_t s; T(ScanTimer& t_, cudaStream_t s_) : t(t_), s(s_) { t.begin(s); } ~T() { t.end(s); } } tm(idx->timer_merge, st);
     if (t_xchg) {
         prs_xchg* x = t_xchg;
         ++x->gen;
         PRS_CUDA(cudaFuncSetAttribute(merge_xchg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        merge_xchg_kernel<<<(unsigned)nq, MERGE_THREADS, smem, st>>>((const u64*)idx->cand.p, (const int*)idx->cand_cnt.p, parts,
+        merge_xchg_kernel<<<(unsigned)nq, MERGE_THREADS, smem, st>>>((const u64*)idx->cand.p, parts,
                                                                     (int)nq, k, sortn, out_mode, qnorm, idx->id_offset,
                                                                     idx->metric == PRS_METRIC_IP ? 1 : 0, x->view, x->gen, D,
                                                                     (long long*)I, x->status);
@@ -302,7 +309,7 @@ static int launch_merge(prs_index* idx, int parts, long long nq, int k, int out_
         return 0;
     }
     PRS_CUDA(cudaFuncSetAttribute(merge_cand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    merge_cand_kernel<<<(unsigned)nq, MERGE_THREADS, smem, st>>>((const u64*)idx->cand.p, (const int*)idx->cand_cnt.p, parts,
+    merge_cand_kernel<<<(unsigned)nq, MERGE_THREADS, smem, st>>>((const u64*)idx->cand.p, parts,
                                                                 (int)nq, k, sortn, out_mode, qnorm, idx->id_offset, D,
                                                                 (long long*)I);
     PRS_LAUNCH_CHECK();
@@ -400,7 +407,7 @@ static int search_device_impl(prs_index* idx, const void* q, int qdtype, long lo
         if ((rc = idx->qnorm.ensure((size_t)nq * 4))) return rc;
         int parts = 0;
         if ((rc = search_umma(idx->umma, idx->x, idx->xnorm, idx->n, idx->d, idx->pitch, idx->storage, idx->metric, idx->sm_count,
-                              q, qdtype, nq, k, (float*)idx->qnorm.p, idx->cand, idx->cand_cnt, &parts, st, &idx->timer))) return rc;
+                              q, qdtype, nq, k, (float*)idx->qnorm.p, idx->cand, idx->cand_cnt, &parts, st, &idx->timer, &idx->timer_prep))) return rc;
         return launch_merge(idx, parts, nq, k, idx->metric == PRS_METRIC_L2 ? 2 : 0, (const float*)idx->qnorm.p, D, I, st);
     }
     const float* qf = (const float*)q;
@@ -524,8 +531,17 @@ int prs_index_set_path(prs_index* idx, int path) {
 int prs_index_set_timing(prs_index* idx, int enable) {
     if (!idx) { set_error("null index"); return PRS_EINVAL; }
     std::lock_guard<std::mutex> lock(idx->mu);
-    idx->timer.enabled = enable != 0;
+    idx->timer.enabled = idx->timer_prep.enabled = idx->timer_merge.enabled = enable != 0;
     return 0;
+}
+int prs_index_phase_times(prs_index* idx, double* prep_ms, double* merge_ms) {
+    if (!idx || !prep_ms || !merge_ms) { set_error("phase_times: bad arguments"); return PRS_EINVAL; }
+    DeviceGuard g(idx->device);
+    std::lock_guard<std::mutex> lock(idx->mu);
+    long long n = 0;
+    int rc = idx->timer_prep.collect(prep_ms, &n);
+    if (rc) return rc;
+    return idx->timer_merge.collect(merge_ms, &n);
 }
 int prs_index_scan_time(prs_index* idx, double* total_ms, int64_t* launches) {
     if (!idx || !total_ms || !launches) { set_error("scan_time: bad arguments"); return PRS_EINVAL; }
@@ -601,8 +617,8 @@ int prs_merge_topk_device(const float* Dp, const int64_t* Ip, int nparts, int64_
     if (nq == 0) return 0;
     if (!Dp || !Ip || !D || !I) { set_error("merge: null pointer"); return PRS_EINVAL; }
     DeviceGuard g(device);
-    const int sortn = next_pow2(k + MERGE_THREADS);
-    const size_t smem = (size_t)sortn * 8 + 16;
+    const int sortn = merge_sortn((long long)nparts * k, k);
+    const size_t smem = (size_t)sortn * 8 + MERGE_THREADS * 8 + 16;
     PRS_CUDA(cudaFuncSetAttribute(merge_parts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     merge_parts_kernel<<<(unsigned)nq, MERGE_THREADS, smem, (cudaStream_t)stream>>>(Dp, (const long long*)Ip, nparts, nq, k, sortn,
                                                                                    largest, tie_high_id, D, (long long*)I);

@@ -299,7 +299,7 @@ __global__ void __launch_bounds__(SIMT_THREADS, 1) flat_scan_simt_kernel(const S
         };
         const int n = block_topk_stream(fetch, (long long)SIMT_NW * cap, p.k, buf, p.sortn, s_n, tid, SIMT_THREADS, 1);
         const size_t o = ((size_t)blockIdx.x * p.nq_total + p.q0 + qq);
-        for (int j = tid; j < n; j += SIMT_THREADS) p.cand[o * p.k + j] = buf[j];
+        for (int j = tid; j < p.k; j += SIMT_THREADS) p.cand[o * p.k + j] = j < n ? buf[j] : 0ull;   // all k slots, 0 = empty
         if (tid == 0) p.cand_cnt[o] = n;
         __syncthreads();
     }

@@ -384,7 +384,7 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) flat_scan_umma_kernel(const U
             int n = 0;
 #pragma unroll
             for (int j = 0; j < UMMA_MAX_K; ++j) {
-                if (j < p.k && top[j]) { p.cand[o * p.k + n] = top[j]; ++n; }
+                if (j < p.k) { p.cand[o * p.k + j] = top[j]; n += top[j] != 0ull; }   // all k slots, 0 = empty (sorted: empties last)
             }
             p.cand_cnt[o] = n;
         }
@@ -399,34 +399,43 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) flat_scan_umma_kernel(const U
 // order, zero padded; ||q~||^2 of the ROUNDED query (what the expanded L2 form needs); and the
 // bootstrap array of the scan kernel zeroed.  One warp per slot row.
 template <typename TQ>
-__global__ void prep_queries_kernel(const TQ* __restrict__ q, long long nq, int d, int pitch, long long nq_pad,
-                                    int is_bf16, uint16_t* __restrict__ out, float* __restrict__ qnorm,
-                                    uint32_t* __restrict__ boot, long long boot_words) {
-    const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    for (long long i = gtid; i < boot_words; i += (long long)gridDim.x * blockDim.x) boot[i] = 0u;
-    const long long r = gtid >> 5;                 // slot row: pass * 128 + TMEM lane
-    const int lane = threadIdx.x & 31;
+__global__ void __launch_bounds__(128) prep_queries_kernel(const TQ* __restrict__ q, long long nq, int d, int pitch, long long nq_pad,
+                                                           int is_bf16, uint16_t* __restrict__ out, float* __restrict__ qnorm,
+                                                           uint32_t* __restrict__ boot, long long boot_words) {
+    // one CTA per slot row (pass * 128 + TMEM lane); <= 6 independent elements per thread, so the
+    // kernel is one memory round trip long
+    __shared__ float s_part[4];
+    const int tid = threadIdx.x;
+    for (long long i = (long long)blockIdx.x * 128 + tid; i < boot_words; i += (long long)gridDim.x * 128) boot[i] = 0u;
+    const long long r = blockIdx.x;
     if (r >= nq_pad) return;
     const int mm = (int)(r & 127);
     const long long qsrc = (r & ~127ll) + (((mm & 31) << 2) | (mm >> 5));    // query held by that lane
+    constexpr int PER = 6;                                                   // pitch <= 768
+    float v[PER];
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+        const int c = tid + i * 128;
+        v[i] = (qsrc < nq && c < d) ? (float)q[qsrc * d + c] : 0.f;
+    }
     float acc = 0.f;
-    for (int c = lane; c < pitch; c += 32) {
-        float v = 0.f;
-        if (qsrc < nq && c < d) {
-            const TQ t = q[qsrc * d + c];
-            if constexpr (sizeof(TQ) == 4) v = (float)t;
-            else v = (float)t;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+        const int c = tid + i * 128;
+        if (c < pitch) {
+            uint16_t o;
+            float back;
+            if (is_bf16) { __nv_bfloat16 h = __float2bfloat16_rn(v[i]); o = *reinterpret_cast<uint16_t*>(&h); back = __bfloat162float(h); }
+            else { __half h = __float2half_rn(v[i]); o = *reinterpret_cast<uint16_t*>(&h); back = __half2float(h); }
+            out[r * pitch + c] = o;
+            acc = fmaf(back, back, acc);
         }
-        uint16_t o;
-        float back;
-        if (is_bf16) { __nv_bfloat16 h = __float2bfloat16_rn(v); o = *reinterpret_cast<uint16_t*>(&h); back = __bfloat162float(h); }
-        else { __half h = __float2half_rn(v); o = *reinterpret_cast<uint16_t*>(&h); back = __half2float(h); }
-        out[r * pitch + c] = o;
-        acc = fmaf(back, back, acc);
     }
 #pragma unroll
     for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane == 0 && qsrc < nq) qnorm[qsrc] = acc;
+    if ((tid & 31) == 0) s_part[tid >> 5] = acc;
+    __syncthreads();
+    if (tid == 0 && qsrc < nq) qnorm[qsrc] = (s_part[0] + s_part[1]) + (s_part[2] + s_part[3]);
 }
 
 // ---------------- host side ----------------
@@ -444,7 +453,7 @@ static inline bool umma_eligible(int storage, int d, int pitch, long long nq, in
 // q: [nq, d] device, dtype qdtype.  qnorm: [nq] device out.  cand/cand_cnt: per-CTA lists out.
 static inline int search_umma(UmmaState& st, const void* x, const float* xnorm, long long n, int d, int pitch, int storage,
                               int metric, int sm_count, const void* q, int qdtype, long long nq, int k, float* qnorm,
-                              DevBuf& cand, DevBuf& cand_cnt, int* parts_out, cudaStream_t stream, ScanTimer* timer = nullptr) {
+                              DevBuf& cand, DevBuf& cand_cnt, int* parts_out, cudaStream_t stream, ScanTimer* timer = nullptr, ScanTimer* timer_prep = nullptr) {
     if (n > 0x7FFFFFFFll - BLK_ROWS) { set_error("tcgen05 path: more than 2^31 rows per shard"); return PRS_EUNSUP; }
     int rc;
     const long long nq_pad = (nq + UMMA_M - 1) / UMMA_M * UMMA_M;
@@ -455,16 +464,18 @@ static inline int search_umma(UmmaState& st, const void* x, const float* xnorm, 
     if ((rc = st.qlow.ensure((size_t)nq_pad * pitch * 2))) return rc;
     if ((rc = st.boot.ensure((size_t)boot_words * passes * 4))) return rc;
     {
-        const unsigned blocks = (unsigned)((nq_pad * 32 + 255) / 256);
+        const unsigned blocks = (unsigned)nq_pad;
         const int bf = storage == PRS_BF16;
         uint16_t* out = (uint16_t*)st.qlow.p;
         uint32_t* boot = (uint32_t*)st.boot.p;
+        if (timer_prep) timer_prep->begin(stream);
         switch (qdtype) {
-            case PRS_F32: prep_queries_kernel<float><<<blocks, 256, 0, stream>>>((const float*)q, nq, d, pitch, nq_pad, bf, out, qnorm, boot, boot_words * passes); break;
-            case PRS_F16: prep_queries_kernel<__half><<<blocks, 256, 0, stream>>>((const __half*)q, nq, d, pitch, nq_pad, bf, out, qnorm, boot, boot_words * passes); break;
-            case PRS_BF16: prep_queries_kernel<__nv_bfloat16><<<blocks, 256, 0, stream>>>((const __nv_bfloat16*)q, nq, d, pitch, nq_pad, bf, out, qnorm, boot, boot_words * passes); break;
+            case PRS_F32: prep_queries_kernel<float><<<blocks, 128, 0, stream>>>((const float*)q, nq, d, pitch, nq_pad, bf, out, qnorm, boot, boot_words * passes); break;
+            case PRS_F16: prep_queries_kernel<__half><<<blocks, 128, 0, stream>>>((const __half*)q, nq, d, pitch, nq_pad, bf, out, qnorm, boot, boot_words * passes); break;
+            case PRS_BF16: prep_queries_kernel<__nv_bfloat16><<<blocks, 128, 0, stream>>>((const __nv_bfloat16*)q, nq, d, pitch, nq_pad, bf, out, qnorm, boot, boot_words * passes); break;
             default: set_error("search: unsupported query dtype %d", qdtype); return PRS_EINVAL;
         }
+        if (timer_prep) timer_prep->end(stream);
         PRS_LAUNCH_CHECK();
     }
     if ((rc = cand.ensure((size_t)grid * nq * k * 8))) return rc;

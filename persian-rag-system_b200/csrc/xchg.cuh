@@ -33,36 +33,51 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ uint32_t ld_relaxed_sys(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
 // out_mode as in merge_cand_kernel.  largest: 1 for IP, 0 for L2 (order of the exchanged values).
 __global__ void __launch_bounds__(MERGE_THREADS) merge_xchg_kernel(
-    const u64* __restrict__ cand, const int* __restrict__ cand_cnt, int parts, int nq, int k, int sortn,
+    const u64* __restrict__ cand, int parts, int nq, int k, int sortn,
     int out_mode, const float* __restrict__ qnorm, long long id_offset, int largest,
     const XchgView xv, uint32_t gen, float* __restrict__ D, long long* __restrict__ I, int* __restrict__ status) {
     extern __shared__ __align__(16) unsigned char msm[];
     u64* buf = reinterpret_cast<u64*>(msm);
-    int* s_n = reinterpret_cast<int*>(msm + (size_t)sortn * 8);
+    u64* heads = buf + sortn;
+    int* s_n = reinterpret_cast<int*>(heads + MERGE_THREADS);
     const int q = blockIdx.x, tid = threadIdx.x;
     const int G = xv.G, slot = (int)(gen & 1u);
 
     // ---- 1. local merge over this rank's CTAs ----
     auto fetch = [&](long long i) -> u64 {
-        const int part = (int)(i / k), j = (int)(i - (long long)part * k);
-        const size_t o = (size_t)part * nq + q;
-        return (j < cand_cnt[o]) ? cand[o * k + j] : 0ull;
+        const int part = (int)((unsigned)i / (unsigned)k), j = (int)i - part * k;
+        return __ldcg(cand + ((size_t)part * nq + q) * k + j);
     };
-    const int n = block_topk_stream(fetch, (long long)parts * k, k, buf, sortn, s_n, tid, MERGE_THREADS, 1);
+    const int n = block_topk_lists(fetch, parts, k, buf, sortn, heads, s_n, tid);
+    // keep the local list in registers: buf is reused by the second merge
+    u64 mine[(PRS_MAX_K + MERGE_THREADS - 1) / MERGE_THREADS];
+#pragma unroll
+    for (int r = 0; r < (PRS_MAX_K + MERGE_THREADS - 1) / MERGE_THREADS; ++r) {
+        const int j = tid + r * MERGE_THREADS;
+        mine[r] = (j < n) ? buf[j] : 0ull;
+    }
 
     // ---- 2. push the local list into every rank's buffer (slot, my rank, query q) ----
     const size_t ebase = ((size_t)slot * G + xv.rank) * (size_t)xv.cap + (size_t)q * k;
-    for (int j = tid; j < k; j += MERGE_THREADS) {
+#pragma unroll
+    for (int r = 0; r < (PRS_MAX_K + MERGE_THREADS - 1) / MERGE_THREADS; ++r) {
+        const int j = tid + r * MERGE_THREADS;
+        if (j >= k) break;
         float dv;
         long long iv;
         if (j < n) {
-            const u64 key = buf[j];
+            const u64 key = mine[r];
             const float s = key_score(key);
             dv = out_mode == 0 ? s : (out_mode == 1 ? -s : fmaxf(0.f, qnorm[q] - s));
             iv = (long long)key_id<PRS_TIE_LOW_ID>(key) + id_offset;
@@ -75,20 +90,19 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_xchg_kernel(
             xv.ids[p][ebase + j] = iv;
         }
     }
-    __threadfence_system();
+    // bar.sync orders the CTA's stores before the flag writers; st.release.sys is cumulative, so the
+    // peer that acquires the flag sees the whole list (no per-thread system fence needed)
     __syncthreads();
-    if (tid < G) {
-        __threadfence_system();
-        st_release_sys(xv.flags[tid] + ((size_t)slot * G + xv.rank) * xv.nq_cap + q, gen);
-    }
+    if (tid < G) st_release_sys(xv.flags[tid] + ((size_t)slot * G + xv.rank) * xv.nq_cap + q, gen);
     // ---- 3. wait for the other ranks' lists of this query (they arrive in MY memory) ----
     if (tid < G) {
         const uint32_t* f = xv.flags[xv.rank] + ((size_t)slot * G + tid) * xv.nq_cap + q;
         long long spins = 0;
-        while (ld_acquire_sys(f) != gen) {
-            __nanosleep(64);
+        while (ld_relaxed_sys(f) != gen) {
+            __nanosleep(32);
             if (++spins > (1ll << 24)) { atomicExch(status, 1); break; }      // ~1 s: a peer died or never searched
         }
+        (void)ld_acquire_sys(f);                                              // order the list reads after the flag
     }
     __syncthreads();
 
@@ -103,7 +117,8 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_xchg_kernel(
         const float s = sanitize(largest ? v : -v);
         return ((u64)f2ord(s) << 32) | (u64)(~(uint32_t)(part * k + j));
     };
-    const int n2 = block_topk_stream(fetch2, (long long)G * k, k, buf, sortn, s_n, tid, MERGE_THREADS, 1);
+    __syncthreads();
+    const int n2 = block_topk_lists(fetch2, G, k, buf, sortn, heads, s_n, tid);
     for (int j = tid; j < k; j += MERGE_THREADS) {
         if (j < n2) {
             const uint32_t pos = ~(uint32_t)buf[j];

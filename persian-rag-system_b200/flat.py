@@ -102,6 +102,12 @@ class FlatIndex:
         check(self._L.prs_index_scan_time(self._h, ctypes.byref(ms), ctypes.byref(n)))
         return float(ms.value), int(n.value)
 
+    def phase_times(self):
+        """(prep kernel ms, merge kernel ms) summed since the previous call (timing must be enabled)."""
+        a, b = ctypes.c_double(0.0), ctypes.c_double(0.0)
+        check(self._L.prs_index_phase_times(self._h, ctypes.byref(a), ctypes.byref(b)))
+        return float(a.value), float(b.value)
+
     def set_id_offset(self, offset: int) -> None:
         check(self._L.prs_index_set_id_offset(self._h, int(offset)))
 
