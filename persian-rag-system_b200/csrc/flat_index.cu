@@ -433,11 +433,14 @@ const char* prs_last_error(void) { return t_error.c_str(); }
 int64_t prs_launch_count(void) { return (int64_t)g_launches.load(); }
 
 int prs_device_arch(int device) {
+    static std::atomic<int> cache[64];                       // cudaGetDeviceProperties costs milliseconds: ask once per device
+    if (device >= 0 && device < 64 && cache[device].load() > 0) return cache[device].load();
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); set_error("no CUDA device available"); return PRS_ECUDA; }
     if (device < 0 || device >= ndev) { set_error("device %d out of range (have %d)", device, ndev); return PRS_EINVAL; }
     cudaDeviceProp prop;
     PRS_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (device < 64) cache[device].store(prop.major * 10 + prop.minor);
     return prop.major * 10 + prop.minor;
 }
 
