@@ -44,7 +44,8 @@ struct UmmaParams {
     int nq_total, q0;
     u64* cand;              // [grid][nq_total][k]
     int* cand_cnt;          // [grid][nq_total]
-    uint32_t* boot;         // [grid][128] ord(best score of the CTA's first tile) + 1 counter; zeroed per launch
+    uint32_t* boot;         // per query block: [parts][128] ord(best score of the first tile) + 1 counter; zeroed per search
+    long long boot_stride;  // words between the bootstrap arrays of consecutive query blocks
 };
 
 // ---------------- PTX wrappers (tcgen05 / TMA) ----------------
@@ -70,6 +71,24 @@ __device__ __forceinline__ void umma_ts_f16(uint32_t d_tmem, uint32_t a_tmem, ui
         ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(0), "r"(0), "r"(0), "r"(0)
         : "memory");
 }
+// ---- thread-block cluster helpers (large batches: one corpus stage feeds CL query blocks) ----
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// bulk copy global -> the same shared-memory offset of every CTA in `mask`; each destination's
+// mbarrier (same offset) receives the complete_tx for these bytes
+__device__ __forceinline__ void bulk_g2s_multicast(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar, uint16_t mask) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
+                 ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+// MMA completion arrives on the barrier at the same offset in every CTA of `mask`
+__device__ __forceinline__ void umma_commit_multicast(uint64_t* bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -119,9 +138,19 @@ __device__ __noinline__ float umma_topk_insert(u64* list, int k, float s, uint32
     return last ? key_score(last) : -INFINITY;
 }
 
-template <int TILE_N>
+// CL = thread-block cluster size.  CL == 1: one CTA per SM streams its own tiles (bandwidth-bound
+// batches, nq <= 128).  CL = 2 / 4 (nq > 128): the CTAs of a cluster hold DIFFERENT 128-query blocks
+// in tensor memory and share every corpus stage -- each CTA fetches 1/CL of the stage and multicasts
+// it into all CL shared memories (cp.async.bulk ... .multicast::cluster), and a stage is recycled
+// when the MMAs of all CL CTAs have retired (tcgen05.commit ... .multicast::cluster onto every CTA's
+// `empty` barrier).  One pass over HBM then serves CL*128 queries.
+template <int TILE_N, int CL>
 __global__ void __launch_bounds__(UMMA_THREADS, 1) flat_scan_umma_kernel(const UmmaParams p) {
     static_assert(TILE_N == BLK_ROWS, "one MMA tile == one T64 row block");
+    const int crank = CL > 1 ? (int)cluster_ctarank() : 0;           // which query block of the pass this CTA serves
+    const int part = (int)blockIdx.x / CL;                            // cluster index = candidate-list slot
+    const int nparts = (int)gridDim.x / CL;
+    constexpr uint16_t CMASK = (uint16_t)((1u << CL) - 1u);
     extern __shared__ unsigned char umma_smem_raw[];
     const uint32_t STAGE_BYTES = (uint32_t)p.kbs * KBLOCK_BYTES;
     constexpr uint32_t D_OFF = UMMA_TMEM_COLS - 2 * TILE_N;     // accumulator columns at the top
@@ -143,13 +172,14 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) flat_scan_umma_kernel(const U
     const long long n_tiles = (p.n_rows + TILE_N - 1) / TILE_N;
 
     if (tid == 0) {
-        for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], CL); }
         for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 4); }
         mbar_fence_init();
     }
     if (warp == 0) tmem_alloc(tmem_ptr, UMMA_TMEM_COLS);
     tc_fence_before();
     __syncthreads();
+    if (CL > 1) cluster_sync_all();          // every CTA's barriers exist before a peer multicasts onto them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
 
@@ -161,12 +191,15 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) flat_scan_umma_kernel(const U
             int s = 0;
             uint32_t ph = 0;
             const size_t blk_bytes = (size_t)BLK_ROWS * p.pitch * 2;
-            for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+            const uint32_t slice = STAGE_BYTES / CL;
+            for (long long t = part; t < n_tiles; t += nparts) {
                 const unsigned char* src = p.x + (size_t)t * blk_bytes;
                 for (int ks = 0; ks < kstages; ++ks) {
                     mbar_wait(&empty[s], ph ^ 1u);
                     mbar_arrive_expect_tx(&full[s], STAGE_BYTES);
-                    bulk_g2s(ring + (size_t)s * STAGE_BYTES, src + (size_t)ks * STAGE_BYTES, STAGE_BYTES, &full[s]);
+                    if (CL == 1) bulk_g2s(ring + (size_t)s * STAGE_BYTES, src + (size_t)ks * STAGE_BYTES, STAGE_BYTES, &full[s]);
+                    else bulk_g2s_multicast(ring + (size_t)s * STAGE_BYTES + (size_t)crank * slice,
+                                            src + (size_t)ks * STAGE_BYTES + (size_t)crank * slice, slice, &full[s], CMASK);
                     if (++s == p.stages) { s = 0; ph ^= 1u; }
                 }
             }
@@ -176,12 +209,13 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) flat_scan_umma_kernel(const U
         // instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 [4,6)=1,
         // a/b_format [7,10)/[10,13) (0 F16, 1 BF16), K-major A and B, N>>3 at [17,23), M>>4 at [24,29)
         const uint32_t fmt = p.is_bf16 ? 1u : 0u;
-        const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(TILE_N >> 3) << 17) | ((uint32_t)(UMMA_M >> 4) << 24);
+        const uint32_t n_mma = (p.dbg & 64) ? 32u : (uint32_t)TILE_N;      // dbg 64: half-width MMAs (timing experiment)
+        const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((n_mma >> 3) << 17) | ((uint32_t)(UMMA_M >> 4) << 24);
         int s = 0, it = 0;
         uint32_t ph = 0;
         named_bar_sync(2, 160);                               // queries are in TMEM
         tc_fence_after();
-        for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+        for (long long t = part; t < n_tiles; t += nparts, ++it) {
             const int b = it & 1;
             const uint32_t aph = (uint32_t)(it >> 1) & 1u;
             mbar_wait(&tmem_empty[b], aph ^ 1u);
@@ -190,7 +224,7 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) flat_scan_umma_kernel(const U
             for (int ks = 0; ks < kstages; ++ks) {
                 mbar_wait(&full[s], ph);
                 tc_fence_after();
-                if (lane == 0 && (p.dbg & 4)) {
+                if (lane == 0 && (p.dbg & 4) && CL == 1) {
                     mbar_arrive(&empty[s]);
                     if (ks == kstages - 1) mbar_arrive(&tmem_full[b]);
                 } else if (lane == 0) {
@@ -199,12 +233,14 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) flat_scan_umma_kernel(const U
                         const int kb = ks * p.kbs + kbi;
 #pragma unroll
                         for (int k4 = 0; k4 < 4; ++k4) {
+                            if ((p.dbg & 32) && (k4 & 1)) continue;            // dbg 32: half the MMAs (timing experiment)
                             const uint64_t bdesc = umma_desc_sw128(sb + (uint32_t)kbi * KBLOCK_BYTES + (uint32_t)k4 * 32u);
                             const uint32_t a_tmem = tmem_base + (uint32_t)(kb * 32 + k4 * 8);
                             umma_ts_f16(d_tmem, a_tmem, bdesc, idesc, (kb | k4) != 0 ? 1u : 0u);
                         }
                     }
-                    umma_commit(&empty[s]);                    // frees the smem stage when these MMAs retire
+                    if (CL == 1) umma_commit(&empty[s]);       // frees the smem stage when these MMAs retire
+                    else umma_commit_multicast(&empty[s], CMASK);   // ... in every CTA of the cluster
                     if (ks == kstages - 1) umma_commit(&tmem_full[b]);
                 }
                 __syncwarp();
@@ -218,12 +254,13 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) flat_scan_umma_kernel(const U
         const int qd = warp & 3;
         const int m = qd * 32 + lane;
         const int qi = (lane << 2) | qd;
-        const bool qvalid = qi < p.nq;
+        const int my_nq = p.nq - crank * UMMA_M;                          // valid queries of this CTA's block
+        const bool qvalid = qi < my_nq;
         float* wnorm = snorm + (warp - 2) * TILE_N;
         const uint32_t lane_addr = tmem_base + ((uint32_t)(qd * 32) << 16) + D_OFF;
         {
             // stage this thread's query row into TMEM: lane m, columns [0, pitch/2)
-            const uint4* qrow = reinterpret_cast<const uint4*>(p.qlow + (size_t)m * p.pitch);
+            const uint4* qrow = reinterpret_cast<const uint4*>(p.qlow + ((size_t)crank * UMMA_M + m) * p.pitch);
             const uint32_t a_addr = tmem_base + ((uint32_t)(qd * 32) << 16);
             for (int c0 = 0; c0 < (p.pitch >> 1); c0 += 32) {
                 uint32_t v[32];
@@ -238,7 +275,8 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) flat_scan_umma_kernel(const U
             tc_fence_before();
             named_bar_sync(2, 160);
         }
-        const int G = (int)gridDim.x;
+        const int G = nparts;
+        uint32_t* const boot = p.boot + (size_t)crank * p.boot_stride;    // one bootstrap array per query block
         float thr = -INFINITY;          // admission threshold = max(bootstrap bound, this CTA's k-th best)
         bool boot_done = false;
         // thread-private top-k of this CTA for this query: 16 sorted keys in registers (key 0 = empty)
@@ -252,7 +290,7 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) flat_scan_umma_kernel(const U
         // pruning with it is exact, and it replaces the ~k*ln(rows per CTA / k) warm-up insertions
         // each CTA would otherwise need to find the threshold on its own.
         auto refresh_boot = [&]() {
-            const int published = (int)__ldcg(reinterpret_cast<const unsigned int*>(p.boot + (size_t)G * UMMA_M));
+            const int published = (int)__ldcg(reinterpret_cast<const unsigned int*>(boot + (size_t)G * UMMA_M));
             // all loads are independent and issued back to back (an L2 round trip under a saturated
             // HBM pipe is ~1 us: 148 dependent ones would cost more than the whole bootstrap saves)
             constexpr int NGRP = 40, FOLD = 4;              // covers up to 160 CTAs
@@ -263,7 +301,7 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) flat_scan_umma_kernel(const U
 #pragma unroll
                 for (int f = 0; f < FOLD; ++f) {
                     const int c = g * FOLD + f;
-                    a[f] = (c < G) ? __ldcg(p.boot + (size_t)c * UMMA_M + m) : 0u;
+                    a[f] = (c < G) ? __ldcg(boot + (size_t)c * UMMA_M + m) : 0u;
                 }
                 gm[g] = max(max(a[0], a[1]), max(a[2], a[3]));
             }
@@ -288,7 +326,7 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) flat_scan_umma_kernel(const U
         };
 
         int it = 0;
-        for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+        for (long long t = part; t < n_tiles; t += nparts, ++it) {
             const int b = it & 1;
             const uint32_t aph = (uint32_t)(it >> 1) & 1u;
             const long long row0 = t * TILE_N;
@@ -322,14 +360,14 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) flat_scan_umma_kernel(const U
                 float mx = -INFINITY;
 #pragma unroll
                 for (int j = 0; j < TILE_N; ++j) mx = (j < nvalid) ? fmaxf(mx, __uint_as_float(v[j])) : mx;
-                p.boot[(size_t)blockIdx.x * UMMA_M + m] = f2ord(mx);
+                boot[(size_t)part * UMMA_M + m] = f2ord(mx);
                 __threadfence();
                 __syncwarp();
-                if (lane == 0) atomicAdd(reinterpret_cast<unsigned int*>(p.boot + (size_t)G * UMMA_M), 1u);
+                if (lane == 0) atomicAdd(reinterpret_cast<unsigned int*>(boot + (size_t)G * UMMA_M), 1u);
                 // bounded wait for the other CTAs (they start together and do the same work); a late
                 // CTA only weakens the bound, and the refresh is repeated while it is incomplete
                 for (int spin = 0; spin < 24; ++spin) {
-                    if ((int)__ldcg(reinterpret_cast<const unsigned int*>(p.boot + (size_t)G * UMMA_M)) >= 4 * G) break;
+                    if ((int)__ldcg(reinterpret_cast<const unsigned int*>(boot + (size_t)G * UMMA_M)) >= 4 * G) break;
                     __nanosleep(64);
                 }
                 __threadfence();
@@ -380,7 +418,7 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) flat_scan_umma_kernel(const U
             }
         }
         if (qvalid) {
-            const size_t o = (size_t)blockIdx.x * p.nq_total + p.q0 + qi;
+            const size_t o = (size_t)part * p.nq_total + p.q0 + crank * UMMA_M + qi;
             int n = 0;
 #pragma unroll
             for (int j = 0; j < UMMA_MAX_K; ++j) {
@@ -391,6 +429,7 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) flat_scan_umma_kernel(const U
     }
     tc_fence_before();
     __syncthreads();
+    if (CL > 1) cluster_sync_all();          // no CTA leaves while a peer's commits can still arrive on its barriers
     tc_fence_after();
     if (warp == 0) tmem_dealloc(tmem_base, UMMA_TMEM_COLS);
 }
@@ -450,19 +489,86 @@ static inline bool umma_eligible(int storage, int d, int pitch, long long nq, in
     return (storage == PRS_F16 || storage == PRS_BF16) && pitch <= 768 && k <= UMMA_MAX_K && nq >= 1;
 }
 
-// q: [nq, d] device, dtype qdtype.  qnorm: [nq] device out.  cand/cand_cnt: per-CTA lists out.
+template <int CL>
+static inline int umma_launch(const UmmaParams& p, int n_clusters, size_t smem, cudaStream_t stream) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(n_clusters * CL), 1, 1);
+    cfg.blockDim = dim3(UMMA_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = CL > 1 ? 1 : 0;
+    PRS_CUDA(cudaLaunchKernelEx(&cfg, flat_scan_umma_kernel<BLK_ROWS, CL>, p));
+    return 0;
+}
+
+// how many clusters of CL CTAs (1 CTA per SM at this shared-memory size) the device runs at once
+template <int CL>
+static inline int umma_max_clusters(size_t smem, int sm_count) {
+    static int cached = -1;
+    static size_t cached_smem = 0;
+    if (cached > 0 && cached_smem == smem) return cached;
+    if (cudaFuncSetAttribute(flat_scan_umma_kernel<BLK_ROWS, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return 0; }
+    int n = sm_count / CL;
+    if (CL > 1) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(sm_count / CL * CL), 1, 1);
+        cfg.blockDim = dim3(UMMA_THREADS, 1, 1);
+        cfg.dynamicSmemBytes = smem;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        int q = 0;
+        if (cudaOccupancyMaxActiveClusters(&q, flat_scan_umma_kernel<BLK_ROWS, CL>, &cfg) != cudaSuccess) { cudaGetLastError(); return 0; }
+        n = q;
+    }
+    cached = n; cached_smem = smem;
+    return n;
+}
+
+// q: [nq, d] device, dtype qdtype.  qnorm: [nq] device out.  cand/cand_cnt: per-part lists out.
 static inline int search_umma(UmmaState& st, const void* x, const float* xnorm, long long n, int d, int pitch, int storage,
                               int metric, int sm_count, const void* q, int qdtype, long long nq, int k, float* qnorm,
                               DevBuf& cand, DevBuf& cand_cnt, int* parts_out, cudaStream_t stream, ScanTimer* timer = nullptr, ScanTimer* timer_prep = nullptr) {
     if (n > 0x7FFFFFFFll - BLK_ROWS) { set_error("tcgen05 path: more than 2^31 rows per shard"); return PRS_EUNSUP; }
     int rc;
-    const long long nq_pad = (nq + UMMA_M - 1) / UMMA_M * UMMA_M;
+    static const int dbg = getenv("PRS_UMMA_DEBUG") ? atoi(getenv("PRS_UMMA_DEBUG")) : 0;
+    static const int dbg_kbs = getenv("PRS_UMMA_KBS") ? atoi(getenv("PRS_UMMA_KBS")) : 0;
+    static const int dbg_cl = getenv("PRS_UMMA_CLUSTER") ? atoi(getenv("PRS_UMMA_CLUSTER")) : 0;
+    const int kblocks = pitch >> 6;
+    // k-blocks per pipeline stage: the largest divisor of the k-block count up to 6 (48 KB).  Few,
+    // large stages keep the per-stage barrier round trips of the single MMA-issuing thread off the
+    // critical path (measured: 8 KB stages 3443 GB/s, 16 KB 4431, 48 KB 4513 -> see profiles/)
+    int kbs = 1;
+    for (int c = 2; c <= 6; ++c) if (kblocks % c == 0) kbs = c;
+    if (dbg_kbs > 0 && kblocks % dbg_kbs == 0) kbs = dbg_kbs;
+    const size_t stage_bytes = (size_t)kbs * KBLOCK_BYTES;
+    const size_t fixed = 4 * (size_t)BLK_ROWS * 4 + (2 * UMMA_MAX_STAGES + 4) * 8 + 16;
+    int stages = (int)((226 * 1024 - 1024 - fixed) / stage_bytes);
+    if (stages > UMMA_MAX_STAGES) stages = UMMA_MAX_STAGES;
+    const size_t smem = 1024 + (size_t)stages * stage_bytes + fixed;
     const long long n_tiles = (n + BLK_ROWS - 1) / BLK_ROWS;
-    const int grid = (int)std::min<long long>(sm_count, n_tiles);
-    const long long boot_words = (long long)grid * UMMA_M + 32;
-    const long long passes = nq_pad / UMMA_M;
+
+    // cluster size: query blocks that share one pass over the corpus
+    int CL = nq > 2 * UMMA_M ? 4 : (nq > UMMA_M ? 2 : 1);
+    if (dbg_cl == 1 || dbg_cl == 2 || dbg_cl == 4) CL = dbg_cl;
+    int max_clusters = 0;
+    for (;;) {
+        max_clusters = CL == 4 ? umma_max_clusters<4>(smem, sm_count) : (CL == 2 ? umma_max_clusters<2>(smem, sm_count) : umma_max_clusters<1>(smem, sm_count));
+        if (max_clusters > 0 || CL == 1) break;
+        CL >>= 1;                                   // this device cannot co-schedule such clusters
+    }
+    if (max_clusters <= 0) { set_error("tcgen05 path: kernel does not fit this device"); return PRS_ECUDA; }
+    const int n_clusters = (int)std::min<long long>(max_clusters, n_tiles);
+    const long long qblock = (long long)UMMA_M * CL;
+    const long long nq_pad = (nq + qblock - 1) / qblock * qblock;
+    const long long boot_words = (long long)n_clusters * UMMA_M + 32;
+    const long long nblocks = nq_pad / UMMA_M;
     if ((rc = st.qlow.ensure((size_t)nq_pad * pitch * 2))) return rc;
-    if ((rc = st.boot.ensure((size_t)boot_words * passes * 4))) return rc;
+    if ((rc = st.boot.ensure((size_t)boot_words * nblocks * 4))) return rc;
     {
         const unsigned blocks = (unsigned)nq_pad;
         const int bf = storage == PRS_BF16;
@@ -470,47 +576,34 @@ static inline int search_umma(UmmaState& st, const void* x, const float* xnorm, 
         uint32_t* boot = (uint32_t*)st.boot.p;
         if (timer_prep) timer_prep->begin(stream);
         switch (qdtype) {
-            case PRS_F32: prep_queries_kernel<float><<<blocks, 128, 0, stream>>>((const float*)q, nq, d, pitch, nq_pad, bf, out, qnorm, boot, boot_words * passes); break;
-            case PRS_F16: prep_queries_kernel<__half><<<blocks, 128, 0, stream>>>((const __half*)q, nq, d, pitch, nq_pad, bf, out, qnorm, boot, boot_words * passes); break;
-            case PRS_BF16: prep_queries_kernel<__nv_bfloat16><<<blocks, 128, 0, stream>>>((const __nv_bfloat16*)q, nq, d, pitch, nq_pad, bf, out, qnorm, boot, boot_words * passes); break;
+            case PRS_F32: prep_queries_kernel<float><<<blocks, 128, 0, stream>>>((const float*)q, nq, d, pitch, nq_pad, bf, out, qnorm, boot, boot_words * nblocks); break;
+            case PRS_F16: prep_queries_kernel<__half><<<blocks, 128, 0, stream>>>((const __half*)q, nq, d, pitch, nq_pad, bf, out, qnorm, boot, boot_words * nblocks); break;
+            case PRS_BF16: prep_queries_kernel<__nv_bfloat16><<<blocks, 128, 0, stream>>>((const __nv_bfloat16*)q, nq, d, pitch, nq_pad, bf, out, qnorm, boot, boot_words * nblocks); break;
             default: set_error("search: unsupported query dtype %d", qdtype); return PRS_EINVAL;
         }
         if (timer_prep) timer_prep->end(stream);
         PRS_LAUNCH_CHECK();
     }
-    if ((rc = cand.ensure((size_t)grid * nq * k * 8))) return rc;
-    if ((rc = cand_cnt.ensure((size_t)grid * nq * 4))) return rc;
-    const int kblocks = pitch >> 6;
-    // k-blocks per pipeline stage: the largest divisor of the k-block count up to 6 (48 KB).  Few,
-    // large stages keep the per-stage barrier round trips of the single MMA-issuing thread off the
-    // critical path (measured: 8 KB stages 3443 GB/s, 16 KB 4431, 48 KB 4513 -> see profiles/)
-    int kbs = 1;
-    for (int c = 2; c <= 6; ++c) if (kblocks % c == 0) kbs = c;
-    static const int dbg = getenv("PRS_UMMA_DEBUG") ? atoi(getenv("PRS_UMMA_DEBUG")) : 0;
-    static const int dbg_kbs = getenv("PRS_UMMA_KBS") ? atoi(getenv("PRS_UMMA_KBS")) : 0;
-    if (dbg_kbs > 0 && kblocks % dbg_kbs == 0) kbs = dbg_kbs;
-    const size_t stage_bytes = (size_t)kbs * KBLOCK_BYTES;
-    const size_t fixed = 4 * (size_t)BLK_ROWS * 4 + (2 * UMMA_MAX_STAGES + 4) * 8 + 16;
-    int stages = (int)((226 * 1024 - 1024 - fixed) / stage_bytes);
-    if (stages > UMMA_MAX_STAGES) stages = UMMA_MAX_STAGES;
-    const size_t smem = 1024 + (size_t)stages * stage_bytes + fixed;
-    PRS_CUDA(cudaFuncSetAttribute(flat_scan_umma_kernel<BLK_ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    for (long long q0 = 0; q0 < nq; q0 += UMMA_M) {
+    if ((rc = cand.ensure((size_t)n_clusters * nq * k * 8))) return rc;
+    if ((rc = cand_cnt.ensure((size_t)n_clusters * nq * 4))) return rc;
+    for (long long q0 = 0; q0 < nq; q0 += qblock) {
         UmmaParams p;
         p.x = (const unsigned char*)x;
         p.qlow = (const uint16_t*)st.qlow.p + (size_t)q0 * pitch;
         p.xnorm = xnorm; p.n_rows = n; p.pitch = pitch;
-        p.nq = (int)std::min<long long>(UMMA_M, nq - q0);
+        p.nq = (int)std::min<long long>(qblock, nq - q0);
         p.k = k; p.l2 = metric == PRS_METRIC_L2; p.stages = stages; p.is_bf16 = storage == PRS_BF16; p.kbs = kbs; p.dbg = dbg;
         p.nq_total = (int)nq; p.q0 = (int)q0;
         p.cand = (u64*)cand.p; p.cand_cnt = (int*)cand_cnt.p;
         p.boot = (uint32_t*)st.boot.p + (size_t)(q0 / UMMA_M) * boot_words;
+        p.boot_stride = boot_words;
         if (timer) timer->begin(stream);
-        flat_scan_umma_kernel<BLK_ROWS><<<grid, UMMA_THREADS, smem, stream>>>(p);
+        rc = CL == 4 ? umma_launch<4>(p, n_clusters, smem, stream) : (CL == 2 ? umma_launch<2>(p, n_clusters, smem, stream) : umma_launch<1>(p, n_clusters, smem, stream));
+        if (rc) return rc;
         if (timer) timer->end(stream);
         PRS_LAUNCH_CHECK();
     }
-    *parts_out = grid;
+    *parts_out = n_clusters;
     return 0;
 }
 

@@ -38,5 +38,10 @@ if __name__ == "__main__":
     tot += run(5000, 512, 100, 16, O.METRIC_L2, "bf16")
     tot += run(200000, 768, 64, 10, O.METRIC_IP, "fp16")
     tot += run(200000, 768, 300, 10, O.METRIC_L2, "bf16")
+    tot += run(30000, 384, 129, 10, O.METRIC_IP, "fp16")       # cluster of 2, second block nearly empty
+    tot += run(30000, 512, 256, 16, O.METRIC_L2, "fp16")       # cluster of 2, full
+    tot += run(30000, 768, 257, 10, O.METRIC_IP, "bf16")       # cluster of 4, blocks 3 and 4 (almost) empty
+    tot += run(100000, 768, 1024, 10, O.METRIC_IP, "fp16")     # cluster of 4, two passes
+    tot += run(100, 64, 600, 5, O.METRIC_L2, "fp16")           # fewer tiles than clusters
     print("TOTAL BAD", tot)
     sys.exit(1 if tot else 0)
