@@ -40,6 +40,7 @@ struct UmmaParams {
     const float* xnorm;     // [n_rows] squared norms of the stored rows
     long long n_rows;
     int pitch, nq, k, l2, stages, is_bf16, kbs;   // kbs: k-blocks per pipeline stage
+    int nbuf;               // accumulator buffers in TMEM: 2 when pitch <= 512, else 1
     int dbg;                // experiments only (PRS_UMMA_DEBUG): 1 no bootstrap+no inserts, 2 epilogue releases without reading, 4 no MMA
     int nq_total, q0;
     u64* cand;              // [grid][nq_total][k]
@@ -140,20 +141,31 @@ __device__ __noinline__ float umma_topk_insert(u64* list, int k, float s, uint32
 
 // CL = thread-block cluster size.  CL == 1: one CTA per SM streams its own tiles (bandwidth-bound
 // batches, nq <= 128).  CL = 2 / 4 (nq > 128): the CTAs of a cluster hold DIFFERENT 128-query blocks
-// in tensor memory and share every corpus stage -- each CTA fetches 1/CL of the stage and multicasts
-// it into all CL shared memories (cp.async.bulk ... .multicast::cluster), and a stage is recycled
-// when the MMAs of all CL CTAs have retired (tcgen05.commit ... .multicast::cluster onto every CTA's
-// `empty` barrier).  One pass over HBM then serves CL*128 queries.
-template <int TILE_N, int CL>
+// in tensor memory and share every corpus stage -- the stage's bulk copies are dealt round-robin to
+// the CTAs and each one is multicast into all CL shared memories (cp.async.bulk ...
+// .multicast::cluster); a stage is recycled when the MMAs of all CL CTAs have retired
+// (tcgen05.commit ... .multicast::cluster onto every CTA's `empty` barrier).  One pass over HBM then
+// serves CL*128 queries.
+//
+// NB = T64 row blocks per MMA tile (tile = 64*NB corpus rows).  Measured on B200: a tcgen05.mma
+// costs the issuing thread ~54 cycles whatever its width, so with N = 64 (32 cycles of tensor work)
+// a tile costs ~1.7k + 54 * 4 * (pitch/64) cycles -- above the HBM time of a 64-row tile once
+// pitch <= 512.  NB = 2 (N = 128) halves the MMA count per row and is used whenever the query block
+// leaves room in tensor memory for two 128-column accumulator buffers (pitch <= 512: d = 384 went
+// from 74 % to 86 % of the HBM roofline); pitch 768 keeps NB = 1 with double buffering (a single
+// 128-column buffer serialises MMA and epilogue: 93.7 % vs 95.3 %).
+template <int CL, int NB>
 __global__ void __launch_bounds__(UMMA_THREADS, 1) flat_scan_umma_kernel(const UmmaParams p) {
-    static_assert(TILE_N == BLK_ROWS, "one MMA tile == one T64 row block");
+    constexpr int TILE_N = NB * BLK_ROWS;
+    constexpr int UMMA_KB_STAGE_BYTES = NB * KBLOCK_BYTES;   // one k-block of a tile: NB adjacent 8 KB block pieces
     const int crank = CL > 1 ? (int)cluster_ctarank() : 0;           // which query block of the pass this CTA serves
     const int part = (int)blockIdx.x / CL;                            // cluster index = candidate-list slot
     const int nparts = (int)gridDim.x / CL;
     constexpr uint16_t CMASK = (uint16_t)((1u << CL) - 1u);
     extern __shared__ unsigned char umma_smem_raw[];
-    const uint32_t STAGE_BYTES = (uint32_t)p.kbs * KBLOCK_BYTES;
-    constexpr uint32_t D_OFF = UMMA_TMEM_COLS - 2 * TILE_N;     // accumulator columns at the top
+    const uint32_t STAGE_BYTES = (uint32_t)p.kbs * UMMA_KB_STAGE_BYTES;
+    const int nbuf = p.nbuf;                                           // accumulator buffers (1 or 2)
+    const uint32_t D_OFF = UMMA_TMEM_COLS - (uint32_t)nbuf * TILE_N;   // accumulator columns at the top
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     // 1024-byte aligned carve-up (SWIZZLE_128B atoms are 1024 bytes)
@@ -169,7 +181,8 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) flat_scan_umma_kernel(const U
 
     const int kblocks = p.pitch >> 6;
     const int kstages = kblocks / p.kbs;           // pipeline stages per tile
-    const long long n_tiles = (p.n_rows + TILE_N - 1) / TILE_N;
+    const long long n_blocks = (p.n_rows + BLK_ROWS - 1) / BLK_ROWS;
+    const long long n_tiles = (n_blocks + NB - 1) / NB;
 
     if (tid == 0) {
         for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], CL); }
@@ -191,15 +204,23 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) flat_scan_umma_kernel(const U
             int s = 0;
             uint32_t ph = 0;
             const size_t blk_bytes = (size_t)BLK_ROWS * p.pitch * 2;
-            const uint32_t slice = STAGE_BYTES / CL;
             for (long long t = part; t < n_tiles; t += nparts) {
-                const unsigned char* src = p.x + (size_t)t * blk_bytes;
+                const int nblk = (int)((n_blocks - NB * t < NB) ? (n_blocks - NB * t) : NB);   // the last tile may be short
+                const unsigned char* src = p.x + (size_t)(NB * t) * blk_bytes;
                 for (int ks = 0; ks < kstages; ++ks) {
                     mbar_wait(&empty[s], ph ^ 1u);
-                    mbar_arrive_expect_tx(&full[s], STAGE_BYTES);
-                    if (CL == 1) bulk_g2s(ring + (size_t)s * STAGE_BYTES, src + (size_t)ks * STAGE_BYTES, STAGE_BYTES, &full[s]);
-                    else bulk_g2s_multicast(ring + (size_t)s * STAGE_BYTES + (size_t)crank * slice,
-                                            src + (size_t)ks * STAGE_BYTES + (size_t)crank * slice, slice, &full[s], CMASK);
+                    mbar_arrive_expect_tx(&full[s], (uint32_t)(p.kbs * nblk) * KBLOCK_BYTES);
+                    unsigned char* dst = ring + (size_t)s * STAGE_BYTES;
+                    int c = 0;
+                    for (int kbi = 0; kbi < p.kbs; ++kbi) {
+                        for (int bl = 0; bl < nblk; ++bl, ++c) {
+                            // k-block (ks*kbs + kbi) of row block NB*t + bl: 8 KB contiguous in HBM (T64 layout)
+                            const unsigned char* g = src + (size_t)bl * blk_bytes + (size_t)(ks * p.kbs + kbi) * KBLOCK_BYTES;
+                            unsigned char* d = dst + (size_t)kbi * UMMA_KB_STAGE_BYTES + (size_t)bl * KBLOCK_BYTES;
+                            if (CL == 1) bulk_g2s(d, g, KBLOCK_BYTES, &full[s]);
+                            else if ((c % CL) == crank) bulk_g2s_multicast(d, g, KBLOCK_BYTES, &full[s], CMASK);
+                        }
+                    }
                     if (++s == p.stages) { s = 0; ph ^= 1u; }
                 }
             }
@@ -209,32 +230,27 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) flat_scan_umma_kernel(const U
         // instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 [4,6)=1,
         // a/b_format [7,10)/[10,13) (0 F16, 1 BF16), K-major A and B, N>>3 at [17,23), M>>4 at [24,29)
         const uint32_t fmt = p.is_bf16 ? 1u : 0u;
-        const uint32_t n_mma = (p.dbg & 64) ? 32u : (uint32_t)TILE_N;      // dbg 64: half-width MMAs (timing experiment)
-        const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((n_mma >> 3) << 17) | ((uint32_t)(UMMA_M >> 4) << 24);
+        const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(TILE_N >> 3) << 17) | ((uint32_t)(UMMA_M >> 4) << 24);
         int s = 0, it = 0;
         uint32_t ph = 0;
         named_bar_sync(2, 160);                               // queries are in TMEM
         tc_fence_after();
         for (long long t = part; t < n_tiles; t += nparts, ++it) {
-            const int b = it & 1;
-            const uint32_t aph = (uint32_t)(it >> 1) & 1u;
+            const int b = nbuf == 2 ? (it & 1) : 0;
+            const uint32_t aph = (uint32_t)(nbuf == 2 ? (it >> 1) : it) & 1u;
             mbar_wait(&tmem_empty[b], aph ^ 1u);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + D_OFF + (uint32_t)(b * TILE_N);
             for (int ks = 0; ks < kstages; ++ks) {
                 mbar_wait(&full[s], ph);
                 tc_fence_after();
-                if (lane == 0 && (p.dbg & 4) && CL == 1) {
-                    mbar_arrive(&empty[s]);
-                    if (ks == kstages - 1) mbar_arrive(&tmem_full[b]);
-                } else if (lane == 0) {
+                if (lane == 0) {
                     const uint32_t sb = smem_u32(ring + (size_t)s * STAGE_BYTES);
                     for (int kbi = 0; kbi < p.kbs; ++kbi) {
                         const int kb = ks * p.kbs + kbi;
 #pragma unroll
                         for (int k4 = 0; k4 < 4; ++k4) {
-                            if ((p.dbg & 32) && (k4 & 1)) continue;            // dbg 32: half the MMAs (timing experiment)
-                            const uint64_t bdesc = umma_desc_sw128(sb + (uint32_t)kbi * KBLOCK_BYTES + (uint32_t)k4 * 32u);
+                            const uint64_t bdesc = umma_desc_sw128(sb + (uint32_t)kbi * UMMA_KB_STAGE_BYTES + (uint32_t)k4 * 32u);
                             const uint32_t a_tmem = tmem_base + (uint32_t)(kb * 32 + k4 * 8);
                             umma_ts_f16(d_tmem, a_tmem, bdesc, idesc, (kb | k4) != 0 ? 1u : 0u);
                         }
@@ -325,10 +341,64 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) flat_scan_umma_kernel(const U
             boot_done = published >= 4 * G;
         };
 
+        // one 64-column half of the tile: TMEM -> registers
+        auto load_half = [&](uint32_t (&v)[BLK_ROWS], int b, int h) {
+            tmem_ld32(lane_addr + (uint32_t)(b * TILE_N + h * BLK_ROWS), *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+            tmem_ld32(lane_addr + (uint32_t)(b * TILE_N + h * BLK_ROWS + 32), *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
+            tmem_ld_wait();
+            if (p.l2) {
+#pragma unroll
+                for (int j = 0; j < BLK_ROWS; ++j) v[j] = __float_as_uint(fmaf(2.f, __uint_as_float(v[j]), -wnorm[h * BLK_ROWS + j]));
+            }
+        };
+        // fast path: one compare per score into a bit mask (no branches, small code)
+        auto survivors = [&](const uint32_t (&v)[BLK_ROWS], int nv, uint32_t (&hm)[2]) {
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                hm[hh] = 0u;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) hm[hh] |= (__uint_as_float(v[hh * 32 + j]) >= thr ? 1u : 0u) << j;
+                const int left = nv - hh * 32;
+                if (left < 32) hm[hh] &= (left <= 0) ? 0u : ((1u << left) - 1u);
+                if (!qvalid) hm[hh] = 0u;
+            }
+        };
+        // rare path: a score reached the threshold.  One copy of the code for all columns.
+        auto insert_hits = [&](const uint32_t (&v)[BLK_ROWS], const uint32_t (&hm)[2], long long rbase) {
+#pragma unroll 1
+            for (int hh = 0; hh < 2; ++hh) {
+                uint32_t mask = hm[hh];
+#pragma unroll 1
+                while (mask) {
+                    const int j = __ffs(mask) - 1 + hh * 32;
+                    mask &= mask - 1;
+                    uint32_t bits = 0u;
+#pragma unroll
+                    for (int jj = 0; jj < BLK_ROWS; ++jj) bits = (jj == j) ? v[jj] : bits;
+                    const float sc = __uint_as_float(bits);
+                    if (sc >= thr) {
+                        // branch-free sorted insertion (descending); the key that falls off the end is dropped
+                        u64 key = make_key<PRS_TIE_LOW_ID>(sc, (uint32_t)(rbase + j));
+#pragma unroll
+                        for (int i = 0; i < UMMA_MAX_K; ++i) {
+                            const bool up = key > top[i];
+                            const u64 lo = up ? top[i] : key;
+                            top[i] = up ? key : top[i];
+                            key = lo;
+                        }
+                        u64 kth = 0ull;
+#pragma unroll
+                        for (int i = 0; i < UMMA_MAX_K; ++i) kth = (i == p.k - 1) ? top[i] : kth;
+                        if (kth) thr = fmaxf(thr, key_score(kth));
+                    }
+                }
+            }
+        };
+
         int it = 0;
         for (long long t = part; t < n_tiles; t += nparts, ++it) {
-            const int b = it & 1;
-            const uint32_t aph = (uint32_t)(it >> 1) & 1u;
+            const int b = nbuf == 2 ? (it & 1) : 0;
+            const uint32_t aph = (uint32_t)(nbuf == 2 ? (it >> 1) : it) & 1u;
             const long long row0 = t * TILE_N;
             const int nvalid = (int)((p.n_rows - row0 < TILE_N) ? (p.n_rows - row0) : TILE_N);
             if (p.l2) {
@@ -342,24 +412,25 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) flat_scan_umma_kernel(const U
             }
             mbar_wait(&tmem_full[b], aph);
             tc_fence_after();
-            // the whole tile row of this query -> registers, then hand the TMEM buffer straight back
-            uint32_t v[TILE_N];
-            tmem_ld32(lane_addr + (uint32_t)(b * TILE_N), *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
-            tmem_ld32(lane_addr + (uint32_t)(b * TILE_N + 32), *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
-            tmem_ld_wait();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[b]);
-            if (p.dbg & 2) continue;
-            if (p.l2) {
-#pragma unroll
-                for (int j = 0; j < TILE_N; ++j) v[j] = __float_as_uint(fmaf(2.f, __uint_as_float(v[j]), -wnorm[j]));
+            uint32_t v[BLK_ROWS];
+            uint32_t hm[2];
+            if (p.dbg & 2) {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tmem_empty[b]);
+                continue;
             }
             if (p.dbg & 1) { thr = INFINITY; boot_done = true; }
             else if (it == 0) {
+                // bootstrap pass over the first tile (both halves): best score per query, then the bound
                 float mx = -INFINITY;
+#pragma unroll 1
+                for (int h = 0; h < NB; ++h) {
+                    load_half(v, b, h);
+                    const int nv = nvalid - h * BLK_ROWS;
 #pragma unroll
-                for (int j = 0; j < TILE_N; ++j) mx = (j < nvalid) ? fmaxf(mx, __uint_as_float(v[j])) : mx;
+                    for (int j = 0; j < BLK_ROWS; ++j) mx = (j < nv) ? fmaxf(mx, __uint_as_float(v[j])) : mx;
+                }
                 boot[(size_t)part * UMMA_M + m] = f2ord(mx);
                 __threadfence();
                 __syncwarp();
@@ -376,45 +447,18 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) flat_scan_umma_kernel(const U
             } else if (!boot_done && (it & (it + 1)) == 0) {
                 refresh_boot();          // it = 1, 3, 7, 15, ...
             }
-            // fast path: one compare per score, collected in a bit mask (no branches, small code)
-            uint32_t hm[TILE_N / 32];
-#pragma unroll
-            for (int h = 0; h < TILE_N / 32; ++h) {
-                hm[h] = 0u;
-#pragma unroll
-                for (int j = 0; j < 32; ++j) hm[h] |= (__uint_as_float(v[h * 32 + j]) >= thr ? 1u : 0u) << j;
-                const int left = nvalid - h * 32;
-                if (left < 32) hm[h] &= (left <= 0) ? 0u : ((1u << left) - 1u);
-                if (!qvalid) hm[h] = 0u;
-            }
-            // rare path: a score reached the threshold.  One copy of the code for all 64 columns.
+            // 64 columns at a time: registers, mask, the rare insertions.  After the LAST load the
+            // accumulator buffer goes straight back to the MMA warp.
 #pragma unroll 1
-            for (int h = 0; h < TILE_N / 32; ++h) {
-                uint32_t mask = hm[h];
-#pragma unroll 1
-                while (mask) {
-                    const int j = __ffs(mask) - 1 + h * 32;
-                    mask &= mask - 1;
-                    uint32_t bits = 0u;
-#pragma unroll
-                    for (int jj = 0; jj < TILE_N; ++jj) bits = (jj == j) ? v[jj] : bits;
-                    const float sc = __uint_as_float(bits);
-                    if (sc >= thr) {
-                        // branch-free sorted insertion (descending); the key that falls off the end is dropped
-                        u64 key = make_key<PRS_TIE_LOW_ID>(sc, (uint32_t)(row0 + j));
-#pragma unroll
-                        for (int i = 0; i < UMMA_MAX_K; ++i) {
-                            const bool up = key > top[i];
-                            const u64 lo = up ? top[i] : key;
-                            top[i] = up ? key : top[i];
-                            key = lo;
-                        }
-                        u64 kth = 0ull;
-#pragma unroll
-                        for (int i = 0; i < UMMA_MAX_K; ++i) kth = (i == p.k - 1) ? top[i] : kth;
-                        if (kth) thr = fmaxf(thr, key_score(kth));
-                    }
+            for (int h = 0; h < NB; ++h) {
+                load_half(v, b, h);
+                if (h == NB - 1) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tmem_empty[b]);
                 }
+                survivors(v, nvalid - h * BLK_ROWS, hm);
+                if (hm[0] | hm[1]) insert_hits(v, hm, row0 + h * BLK_ROWS);
             }
         }
         if (qvalid) {
@@ -489,7 +533,7 @@ static inline bool umma_eligible(int storage, int d, int pitch, long long nq, in
     return (storage == PRS_F16 || storage == PRS_BF16) && pitch <= 768 && k <= UMMA_MAX_K && nq >= 1;
 }
 
-template <int CL>
+template <int CL, int NB>
 static inline int umma_launch(const UmmaParams& p, int n_clusters, size_t smem, cudaStream_t stream) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(n_clusters * CL), 1, 1);
@@ -500,17 +544,17 @@ static inline int umma_launch(const UmmaParams& p, int n_clusters, size_t smem, 
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = CL > 1 ? 1 : 0;
-    PRS_CUDA(cudaLaunchKernelEx(&cfg, flat_scan_umma_kernel<BLK_ROWS, CL>, p));
+    PRS_CUDA(cudaLaunchKernelEx(&cfg, flat_scan_umma_kernel<CL, NB>, p));
     return 0;
 }
 
 // how many clusters of CL CTAs (1 CTA per SM at this shared-memory size) the device runs at once
-template <int CL>
+template <int CL, int NB>
 static inline int umma_max_clusters(size_t smem, int sm_count) {
     static int cached = -1;
     static size_t cached_smem = 0;
     if (cached > 0 && cached_smem == smem) return cached;
-    if (cudaFuncSetAttribute(flat_scan_umma_kernel<BLK_ROWS, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return 0; }
+    if (cudaFuncSetAttribute(flat_scan_umma_kernel<CL, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return 0; }
     int n = sm_count / CL;
     if (CL > 1) {
         cudaLaunchConfig_t cfg = {};
@@ -522,7 +566,7 @@ static inline int umma_max_clusters(size_t smem, int sm_count) {
         attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr; cfg.numAttrs = 1;
         int q = 0;
-        if (cudaOccupancyMaxActiveClusters(&q, flat_scan_umma_kernel<BLK_ROWS, CL>, &cfg) != cudaSuccess) { cudaGetLastError(); return 0; }
+        if (cudaOccupancyMaxActiveClusters(&q, flat_scan_umma_kernel<CL, NB>, &cfg) != cudaSuccess) { cudaGetLastError(); return 0; }
         n = q;
     }
     cached = n; cached_smem = smem;
@@ -542,22 +586,26 @@ static inline int search_umma(UmmaState& st, const void* x, const float* xnorm, 
     // k-blocks per pipeline stage: the largest divisor of the k-block count up to 6 (48 KB).  Few,
     // large stages keep the per-stage barrier round trips of the single MMA-issuing thread off the
     // critical path (measured: 8 KB stages 3443 GB/s, 16 KB 4431, 48 KB 4513 -> see profiles/)
+    static const int dbg_nb = getenv("PRS_UMMA_NB") ? atoi(getenv("PRS_UMMA_NB")) : 0;
+    int NB = pitch <= 512 ? 2 : 1;                  // row blocks per MMA tile (two accumulator buffers must fit TMEM)
+    if (dbg_nb == 1) NB = 1;
     int kbs = 1;
-    for (int c = 2; c <= 6; ++c) if (kblocks % c == 0) kbs = c;
+    for (int c = 2; c <= 6 / NB; ++c) if (kblocks % c == 0) kbs = c;      // stages of up to 48 KB
     if (dbg_kbs > 0 && kblocks % dbg_kbs == 0) kbs = dbg_kbs;
-    const size_t stage_bytes = (size_t)kbs * KBLOCK_BYTES;
-    const size_t fixed = 4 * (size_t)BLK_ROWS * 4 + (2 * UMMA_MAX_STAGES + 4) * 8 + 16;
+    const size_t stage_bytes = (size_t)kbs * NB * KBLOCK_BYTES;
+    const size_t fixed = 4 * (size_t)NB * BLK_ROWS * 4 + (2 * UMMA_MAX_STAGES + 4) * 8 + 16;
     int stages = (int)((226 * 1024 - 1024 - fixed) / stage_bytes);
     if (stages > UMMA_MAX_STAGES) stages = UMMA_MAX_STAGES;
     const size_t smem = 1024 + (size_t)stages * stage_bytes + fixed;
-    const long long n_tiles = (n + BLK_ROWS - 1) / BLK_ROWS;
+    const long long n_tiles = (n + NB * BLK_ROWS - 1) / (NB * BLK_ROWS);
 
     // cluster size: query blocks that share one pass over the corpus
     int CL = nq > 2 * UMMA_M ? 4 : (nq > UMMA_M ? 2 : 1);
     if (dbg_cl == 1 || dbg_cl == 2 || dbg_cl == 4) CL = dbg_cl;
     int max_clusters = 0;
     for (;;) {
-        max_clusters = CL == 4 ? umma_max_clusters<4>(smem, sm_count) : (CL == 2 ? umma_max_clusters<2>(smem, sm_count) : umma_max_clusters<1>(smem, sm_count));
+        if (NB == 2) max_clusters = CL == 4 ? umma_max_clusters<4, 2>(smem, sm_count) : (CL == 2 ? umma_max_clusters<2, 2>(smem, sm_count) : umma_max_clusters<1, 2>(smem, sm_count));
+        else max_clusters = CL == 4 ? umma_max_clusters<4, 1>(smem, sm_count) : (CL == 2 ? umma_max_clusters<2, 1>(smem, sm_count) : umma_max_clusters<1, 1>(smem, sm_count));
         if (max_clusters > 0 || CL == 1) break;
         CL >>= 1;                                   // this device cannot co-schedule such clusters
     }
@@ -593,12 +641,14 @@ static inline int search_umma(UmmaState& st, const void* x, const float* xnorm, 
         p.xnorm = xnorm; p.n_rows = n; p.pitch = pitch;
         p.nq = (int)std::min<long long>(qblock, nq - q0);
         p.k = k; p.l2 = metric == PRS_METRIC_L2; p.stages = stages; p.is_bf16 = storage == PRS_BF16; p.kbs = kbs; p.dbg = dbg;
+        p.nbuf = 2;
         p.nq_total = (int)nq; p.q0 = (int)q0;
         p.cand = (u64*)cand.p; p.cand_cnt = (int*)cand_cnt.p;
         p.boot = (uint32_t*)st.boot.p + (size_t)(q0 / UMMA_M) * boot_words;
         p.boot_stride = boot_words;
         if (timer) timer->begin(stream);
-        rc = CL == 4 ? umma_launch<4>(p, n_clusters, smem, stream) : (CL == 2 ? umma_launch<2>(p, n_clusters, smem, stream) : umma_launch<1>(p, n_clusters, smem, stream));
+        if (NB == 2) rc = CL == 4 ? umma_launch<4, 2>(p, n_clusters, smem, stream) : (CL == 2 ? umma_launch<2, 2>(p, n_clusters, smem, stream) : umma_launch<1, 2>(p, n_clusters, smem, stream));
+        else rc = CL == 4 ? umma_launch<4, 1>(p, n_clusters, smem, stream) : (CL == 2 ? umma_launch<2, 1>(p, n_clusters, smem, stream) : umma_launch<1, 1>(p, n_clusters, smem, stream));
         if (rc) return rc;
         if (timer) timer->end(stream);
         PRS_LAUNCH_CHECK();
