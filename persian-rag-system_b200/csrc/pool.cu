@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(POOL_THREADS) pool_norm_cluster_kernel(const T
     const long long* mb = mask + (size_t)b * T_len;
     float acc[POOL_CPL] = {0.f, 0.f, 0.f, 0.f};
     float cnt = 0.f;
-    constexpr int NW = POOL_THREADS / 32, UNR = sizeof(T) == 2 ? 16 : 8;    // bytes in flight per lane: 128
+    constexpr int NW = POOL_THREADS / 32, UNR = 8;     // rows in flight per lane (16 was measured slower for 16-bit: registers)
     for (int t0 = warp; t0 < T_len; t0 += NW * UNR) {
         float m[UNR];
         float x[UNR][POOL_CPL];
