@@ -5,7 +5,7 @@ Workload (BASELINE.json configs[1]): multilingual-e5-base shape, d = 768, 1 M sy
 chunks, cosine == inner product, k = 10, fp16 storage / fp32 accumulate.  One STEP = one batch of
 `--batch` queries (default 64, the top of the north-star's bandwidth-bound range) searched against
 the whole corpus: scan + fused top-k + merge.  The corpus (1.536 GB) is 12x the 126 MB L2, so every
-step streams it from HBM ("inputs larger than L2"); when a shard is smaller than 4x L2 (N > 2 GPUs)
+step streams it from HBM ("inputs larger than L2"); when a shard is smaller than 2x L2 (N = 8)
 the L2 is flushed between steps and steps are timed one by one.
 
   python bench.py [--gpus N --steps K --warmup W]          this engine (libprs.so), one rank per GPU
@@ -54,6 +54,8 @@ def parse():
     ap.add_argument("--metric", default="ip", choices=["ip", "l2"])
     ap.add_argument("--path", default="auto", choices=["auto", "cuda-core", "tcgen05"])
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"], help="N>1: fused peer-memory exchange, or ncclAllGather + merge")
+    ap.add_argument("--capacity-rows", type=int, default=50_000_000,
+                    help="rows per GPU of the secondary weak-scaling measurement (configs[4] share: 400M x 384 over 8 GPUs); 0 = skip")
     ap.add_argument("--no-sweep", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sweep-out", default="")
@@ -253,8 +255,16 @@ def run_b200(a):
 
     pitch = (a.d + 63) // 64 * 64
     shard_bytes = n_local * pitch * es
-    flush = shard_bytes < 4 * L2_BYTES
+    # a shard streamed cyclically through the 126 MB L2 keeps nothing between steps once it is > 2x L2;
+    # smaller shards (N = 8: 192 MB) get an explicit flush between steps: WRITE a 256 MB buffer, then
+    # read a second one so that the dirty lines are written back before the timed step, not during it
+    flush = shard_bytes < 2 * L2_BYTES
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if flush else None
+    flush_rd = torch.zeros(64 << 20, dtype=torch.float32, device=dev) if flush else None
+
+    def l2_flush(i):
+        flush_buf.fill_(i & 0xFF)
+        flush_rd.sum()
 
     def barrier():
         if world > 1:
@@ -287,7 +297,7 @@ def run_b200(a):
     else:
         evs = []
         for s in range(a.steps):
-            flush_buf.fill_(s & 0xFF)
+            l2_flush(s)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             step_device(a.warmup + s)
@@ -317,13 +327,21 @@ def run_b200(a):
         step_e2e(w)
     barrier()
     sampler.on = True
-    t0 = time.perf_counter()
-    for s in range(a.steps):
-        if flush:
-            flush_buf.fill_(s & 0xFF)
-        step_e2e(a.warmup + s)
-    barrier()
-    e2e_ms = (time.perf_counter() - t0) * 1e3
+    if not flush:
+        t0 = time.perf_counter()
+        for s in range(a.steps):
+            step_e2e(a.warmup + s)
+        barrier()
+        e2e_ms = (time.perf_counter() - t0) * 1e3
+    else:                                   # steps timed one by one, the L2 flush between them is not part of a step
+        e2e_ms = 0.0
+        for s in range(a.steps):
+            l2_flush(s)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            step_e2e(a.warmup + s)          # synchronous: returns with the results on the host
+            e2e_ms += (time.perf_counter() - t0) * 1e3
+        barrier()
     sampler.on = False
     if rank == 0:
         sampler.stop()
@@ -424,12 +442,78 @@ def run_b200(a):
         except AssertionError as e:
             out["parity"] = {"error": str(e)[:300]}
 
+    # ---- secondary: capacity (weak) scaling -- every GPU holds the per-GPU share of configs[4]
+    # (400M x 384 fp16 over 8 GPUs = 50M rows = 38.4 GB per GPU); the global corpus grows with N and the
+    # time per batch should stay flat.  Not the headline (the headline keeps the 1M x 768 corpus).
     if world > 1:
         sh.check_exchange()
+    if a.capacity_rows > 0:
+        try:
+            del sh, idx, Qd
+            torch.cuda.empty_cache()
+            out["capacity_scaling"] = measure_capacity(a, world, rank, local, dev, peak)
+        except Exception as e:                                    # never lose the headline line
+            out["capacity_scaling"] = {"error": repr(e)[:300]}
     if rank == 0:
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+
+
+def measure_capacity(a, world, rank, local, dev, peak):
+    import torch
+    import torch.distributed as dist
+    import persian_rag_system_b200 as P
+    from persian_rag_system_b200.sharded import ShardedFlatIndex
+    d, rows, B, k = 384, a.capacity_rows, 64, 10
+    sh = ShardedFlatIndex(d, P.METRIC_INNER_PRODUCT, "fp16", device=local, exchange=a.exchange, nq_cap=64, k_cap=16)
+    idx = sh.local
+    idx.reserve(rows)
+    gen = torch.Generator(device=dev).manual_seed(99 + rank)
+    slab = (512 << 20) // (d * 4)
+    done = 0
+    while done < rows:
+        c = min(slab, rows - done)
+        xb = torch.randn(c, d, generator=gen, device=dev)
+        xb /= xb.norm(dim=1, keepdim=True)
+        idx.add(xb.half())
+        done += c
+    del xb
+    sh.offset, sh.ntotal_global = rank * rows, rows * world
+    idx.set_id_offset(rank * rows)
+    gq = torch.Generator(device=dev).manual_seed(77)
+    q = torch.randn(B, d, generator=gq, device=dev)
+    q /= q.norm(dim=1, keepdim=True)
+    for _ in range(3):
+        D, I = sh.search(q, k)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    iters = 20
+    idx.set_timing(True); idx.scan_time()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        D, I = sh.search(q, k)
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = e0.elapsed_time(e1) / iters
+    scan_ms, n = idx.scan_time()
+    idx.set_timing(False)
+    t = torch.tensor([ms, scan_ms / max(n, 1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        sh.check_exchange()
+    ms, scan = (float(v) for v in t.tolist())
+    shard_bytes = rows * d * 2
+    # sanity: the best hit of query 0 must be a valid global id
+    ok = bool((I[:, 0] >= 0).all().item() and (I[:, 0] < rows * world).all().item())
+    return {"workload": f"configs[4] share: {rows} x {d} fp16 rows per GPU, global corpus {rows * world} rows, batch {B}, k={k}",
+            "scaling": "weak (corpus grows with N)", "ms_per_batch": ms, "qps": B / (ms * 1e-3), "scan_ms": scan,
+            "scan_gbs_per_gpu": shard_bytes / (scan * 1e-3) / 1e9, "frac_hbm": shard_bytes / (scan * 1e-3) / 1e9 / peak,
+            "aggregate_scan_gbs": world * shard_bytes / (scan * 1e-3) / 1e9, "ids_valid": ok}
 
 
 def main():

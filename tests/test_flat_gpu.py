@@ -190,6 +190,37 @@ def test_16bit_storage_vs_oracle(P, storage, path, metric, n, d, nq, k):
     assert flips <= nq * k * 0.05
 
 
+@pytest.mark.parametrize("n,d,nq,k,metric,storage", [
+    (30000, 384, 129, 10, O.METRIC_IP, "fp16"),      # cluster of 2, second query block nearly empty; two row blocks per tile
+    (30000, 512, 256, 16, O.METRIC_L2, "fp16"),      # cluster of 2, both blocks full
+    (30000, 768, 257, 10, O.METRIC_IP, "bf16"),      # cluster of 4, blocks 3 and 4 (almost) empty; one row block per tile
+    (60000, 768, 700, 10, O.METRIC_L2, "fp16"),      # cluster of 4, two passes
+    (100, 64, 600, 5, O.METRIC_L2, "fp16"),          # fewer tiles than clusters
+    (65, 384, 3, 16, O.METRIC_IP, "fp16"),           # a tile whose second row block holds one row
+    (8256, 384, 1, 10, O.METRIC_L2, "bf16"),         # odd number of row blocks (129): the last tile is half empty
+])
+def test_tcgen05_clusters_and_tile_shapes_vs_oracle(P, n, d, nq, k, metric, storage):
+    """nq > 128 runs thread-block clusters (TMA multicast of the corpus stages, one 128-query block
+    per CTA); pitch <= 512 uses two T64 row blocks per MMA tile.  Every shape must match the oracle."""
+    rng = np.random.default_rng(n + d + nq)
+    x = rng.standard_normal((n, d)).astype(np.float32)
+    x /= np.linalg.norm(x, axis=1, keepdims=True)
+    q = rng.standard_normal((nq, d)).astype(np.float32)
+    q /= np.linalg.norm(q, axis=1, keepdims=True)
+    idx = P.FlatIndex(d, metric, storage)
+    idx.add(x)
+    D, I = idx.search(q, k)
+    assert idx.last_path == "tcgen05"
+    xs, qs = _round_to(x, storage), _round_to(q, storage)
+    S = O.flat_scores_f64(xs, qs, metric)
+    for r in range(nq):
+        O.check_topk_against_scores(I[r], D[r], S[r], k, metric == O.METRIC_IP, rtol=RTOL_16, atol=2e-5, what=f"q{r}")
+    # the same queries one by one (no cluster, different CTA->query mapping) give the same lists
+    for r in (0, nq // 2, nq - 1):
+        D1, I1 = idx.search(q[r:r + 1], k)
+        assert np.array_equal(I1[0], I[r]) and np.array_equal(D1[0], D[r])
+
+
 @pytest.mark.parametrize("storage", ["fp16", "bf16"])
 @pytest.mark.parametrize("d", [40, 128, 384])
 def test_16bit_t64_layout_incremental_add_and_reconstruct(P, storage, d):
