@@ -113,15 +113,6 @@ __global__ void fill_empty_kernel(float* D, long long* I, long long n, float dv)
     if (i < n) { D[i] = dv; I[i] = -1; }
 }
 
-__global__ void qnorm_kernel(const float* __restrict__ q, int d, int stride, float* __restrict__ out) {
-    const int row = blockIdx.x, lane = threadIdx.x;
-    float acc = 0.f;
-    for (int c = lane; c < d; c += 32) { const float v = q[(size_t)row * stride + c]; acc = fmaf(v, v, acc); }
-#pragma unroll
-    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane == 0) out[row] = acc;
-}
-
 // ------------------------------------------------------------------------------------------
 // row-sharded merge: [nparts, nq, k] (score, id) lists -> [nq, k]
 // ------------------------------------------------------------------------------------------
@@ -145,7 +136,7 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_parts_kernel(
         const uint32_t lo = tie_high ? (uint32_t)(part * k + (k - 1 - j)) : ~(uint32_t)(part * k + j);
         return ((u64)f2ord(s) << 32) | lo;
     };
-    const int n = block_topk_lists(fetch, nparts, k, buf, sortn, heads, s_n, tid);
+    const int n = block_topk_lists(fetch, nparts, k, k, buf, sortn, heads, s_n, tid);
     for (int j = tid; j < k; j += MERGE_THREADS) {
         if (j < n) {
             const uint32_t lo = (uint32_t)buf[j];
@@ -397,10 +388,24 @@ static int search_device_impl(prs_index* idx, const void* q, int qdtype, long lo
     }
     int rc;
     int path = idx->path_force;
-    if (path == 0) path = umma_eligible(idx->storage, idx->d, idx->pitch, nq, k) ? 2 : 1;
+    const bool wide = umma_wide_eligible(idx->storage, idx->pitch, nq, k, idx->n);
+    if (path == 0) path = (umma_eligible(idx->storage, idx->d, idx->pitch, nq, k) || wide) ? 2 : 1;
+    if (path == 2 && wide) {
+        // 16 < k <= 1024: sample -> threshold -> collect -> select (flat_umma.cuh), then the usual merge of ONE part
+        if ((rc = idx->qnorm.ensure((size_t)nq * 4))) return rc;
+        bool overflowed = false;
+        if ((rc = search_umma_wide(idx->umma, idx->x, idx->xnorm, idx->n, idx->d, idx->pitch, idx->storage, idx->metric, idx->sm_count,
+                                   q, qdtype, nq, k, (float*)idx->qnorm.p, idx->cand, idx->cand_cnt, &overflowed, st, &idx->timer, &idx->timer_prep))) return rc;
+        if (!overflowed) {
+            idx->last_path = 2;
+            return launch_merge(idx, 1, nq, k, idx->metric == PRS_METRIC_L2 ? 2 : 0, (const float*)idx->qnorm.p, D, I, st);
+        }
+        if (idx->path_force == 2) { set_error("tcgen05 wide-k path: candidate buffer overflow (too many rows tie with the threshold)"); return PRS_EUNSUP; }
+        path = 1;                                   // pathological input: exact CUDA-core scan instead
+    }
     if (path == 2) {
         if (!umma_eligible(idx->storage, idx->d, idx->pitch, nq, k)) {
-            set_error("tcgen05 path needs fp16/bf16 storage, d <= 768 and k <= %d (storage=%d, d=%d, k=%d)", UMMA_MAX_K, idx->storage, idx->d, k);
+            set_error("tcgen05 path needs fp16/bf16 storage, d <= 768 and k <= %d, or k <= %d on >= 32k rows (storage=%d, d=%d, k=%d)", UMMA_MAX_K, UMMA_WIDE_MAX_K, idx->storage, idx->d, k);
             return PRS_EUNSUP;
         }
         idx->last_path = 2;

@@ -23,8 +23,12 @@
 // Warp roles (192 threads): warp 0 = TMA producer + TMEM allocator, warp 1 = MMA issuer,
 // warps 2..5 = epilogue (TMEM lane quarter = warp % 4).
 #pragma once
+#include <algorithm>
+#include <vector>
+
 #include "common.cuh"
 #include "host_common.h"
+#include "topk_merge.cuh"
 
 namespace prs {
 
@@ -45,6 +49,14 @@ struct UmmaParams {
     int nq_total, q0;
     u64* cand;              // [grid][nq_total][k]
     int* cand_cnt;          // [grid][nq_total]
+    int tile_step;          // 1 = every tile; S > 1 = every S-th tile (threshold sampling pass of the wide-k path)
+    int mode;               // 0: per-part sorted top-k lists (k <= 16), pruned by the cross-CTA bootstrap bound;
+                            // 1: collect every score >= tau[q];  2: like 0 but every part keeps its own full top-k (no bootstrap)
+    const float* tau;       // mode 1: [nq_total] admission threshold per query (a lower bound of its k-th best)
+    u64* coll;              // mode 1: [parts][nq_total][coll_cap] unsorted keys
+    int* coll_cnt;          // mode 1: [parts][nq_total]
+    int coll_cap;
+    int* overflow;          // mode 1: set to 1 when a (part, query) buffer was too small
     uint32_t* boot;         // per query block: [parts][128] ord(best score of the first tile) + 1 counter; zeroed per search
     long long boot_stride;  // words between the bootstrap arrays of consecutive query blocks
 };
@@ -121,24 +133,6 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
     return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
 
-// thread-private sorted (descending) list of k keys, stride UMMA_M between entries.
-// Returns the new admission threshold.  (Superseded by the register-resident list in the kernel.)
-__device__ __noinline__ float umma_topk_insert(u64* list, int k, float s, uint32_t id, float thr) {
-    const u64 key = make_key<PRS_TIE_LOW_ID>(s, id);
-    u64 last = list[(k - 1) * UMMA_M];
-    if (key <= last) return thr;   // thr >= own k-th already
-    int pos = k - 1;
-    while (pos > 0) {
-        const u64 up = list[(pos - 1) * UMMA_M];
-        if (up >= key) break;
-        list[pos * UMMA_M] = up;
-        --pos;
-    }
-    list[pos * UMMA_M] = key;
-    last = list[(k - 1) * UMMA_M];
-    return last ? key_score(last) : -INFINITY;
-}
-
 // CL = thread-block cluster size.  CL == 1: one CTA per SM streams its own tiles (bandwidth-bound
 // batches, nq <= 128).  CL = 2 / 4 (nq > 128): the CTAs of a cluster hold DIFFERENT 128-query blocks
 // in tensor memory and share every corpus stage -- the stage's bulk copies are dealt round-robin to
@@ -182,7 +176,8 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) flat_scan_umma_kernel(const U
     const int kblocks = p.pitch >> 6;
     const int kstages = kblocks / p.kbs;           // pipeline stages per tile
     const long long n_blocks = (p.n_rows + BLK_ROWS - 1) / BLK_ROWS;
-    const long long n_tiles = (n_blocks + NB - 1) / NB;
+    const long long n_tiles_all = (n_blocks + NB - 1) / NB;
+    const long long n_tiles = (n_tiles_all + p.tile_step - 1) / p.tile_step;   // tiles this launch visits: t * tile_step
 
     if (tid == 0) {
         for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], CL); }
@@ -204,7 +199,8 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) flat_scan_umma_kernel(const U
             int s = 0;
             uint32_t ph = 0;
             const size_t blk_bytes = (size_t)BLK_ROWS * p.pitch * 2;
-            for (long long t = part; t < n_tiles; t += nparts) {
+            for (long long ti = part; ti < n_tiles; ti += nparts) {
+                const long long t = ti * p.tile_step;
                 const int nblk = (int)((n_blocks - NB * t < NB) ? (n_blocks - NB * t) : NB);   // the last tile may be short
                 const unsigned char* src = p.x + (size_t)(NB * t) * blk_bytes;
                 for (int ks = 0; ks < kstages; ++ks) {
@@ -235,7 +231,7 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) flat_scan_umma_kernel(const U
         uint32_t ph = 0;
         named_bar_sync(2, 160);                               // queries are in TMEM
         tc_fence_after();
-        for (long long t = part; t < n_tiles; t += nparts, ++it) {
+        for (long long ti = part; ti < n_tiles; ti += nparts, ++it) {
             const int b = nbuf == 2 ? (it & 1) : 0;
             const uint32_t aph = (uint32_t)(nbuf == 2 ? (it >> 1) : it) & 1u;
             mbar_wait(&tmem_empty[b], aph ^ 1u);
@@ -295,6 +291,14 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) flat_scan_umma_kernel(const U
         uint32_t* const boot = p.boot + (size_t)crank * p.boot_stride;    // one bootstrap array per query block
         float thr = -INFINITY;          // admission threshold = max(bootstrap bound, this CTA's k-th best)
         bool boot_done = false;
+        // mode 1 (wide k): fixed threshold tau[q]; every score that reaches it goes, unsorted, into this
+        // thread's private slice of the collection buffer (no atomics: one thread owns (part, query))
+        const bool collect = p.mode == 1;
+        const size_t qglobal = (size_t)p.q0 + (size_t)crank * UMMA_M + qi;
+        u64* const cslice = collect ? p.coll + ((size_t)part * p.nq_total + qglobal) * (size_t)p.coll_cap : nullptr;
+        int ccount = 0;
+        if (collect) { boot_done = true; thr = qvalid ? __ldg(p.tau + qglobal) : INFINITY; }
+        if (p.mode == 2) boot_done = true;
         // thread-private top-k of this CTA for this query: 16 sorted keys in registers (key 0 = empty)
         u64 top[UMMA_MAX_K];
 #pragma unroll
@@ -376,7 +380,11 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) flat_scan_umma_kernel(const U
 #pragma unroll
                     for (int jj = 0; jj < BLK_ROWS; ++jj) bits = (jj == j) ? v[jj] : bits;
                     const float sc = __uint_as_float(bits);
-                    if (sc >= thr) {
+                    if (collect) {
+                        if (ccount < p.coll_cap) cslice[ccount] = make_key<PRS_TIE_LOW_ID>(sc, (uint32_t)(rbase + j));
+                        else *p.overflow = 1;
+                        ++ccount;
+                    } else if (sc >= thr) {
                         // branch-free sorted insertion (descending); the key that falls off the end is dropped
                         u64 key = make_key<PRS_TIE_LOW_ID>(sc, (uint32_t)(rbase + j));
 #pragma unroll
@@ -396,7 +404,8 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) flat_scan_umma_kernel(const U
         };
 
         int it = 0;
-        for (long long t = part; t < n_tiles; t += nparts, ++it) {
+        for (long long ti = part; ti < n_tiles; ti += nparts, ++it) {
+            const long long t = ti * p.tile_step;
             const int b = nbuf == 2 ? (it & 1) : 0;
             const uint32_t aph = (uint32_t)(nbuf == 2 ? (it >> 1) : it) & 1u;
             const long long row0 = t * TILE_N;
@@ -421,7 +430,7 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) flat_scan_umma_kernel(const U
                 continue;
             }
             if (p.dbg & 1) { thr = INFINITY; boot_done = true; }
-            else if (it == 0) {
+            else if (it == 0 && p.mode == 0) {
                 // bootstrap pass over the first tile (both halves): best score per query, then the bound
                 float mx = -INFINITY;
 #pragma unroll 1
@@ -461,7 +470,8 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) flat_scan_umma_kernel(const U
                 if (hm[0] | hm[1]) insert_hits(v, hm, row0 + h * BLK_ROWS);
             }
         }
-        if (qvalid) {
+        if (qvalid && collect) p.coll_cnt[(size_t)part * p.nq_total + qglobal] = ccount < p.coll_cap ? ccount : p.coll_cap;
+        if (qvalid && !collect) {
             const size_t o = (size_t)part * p.nq_total + p.q0 + crank * UMMA_M + qi;
             int n = 0;
 #pragma unroll
@@ -523,9 +533,9 @@ __global__ void __launch_bounds__(128) prep_queries_kernel(const TQ* __restrict_
 
 // ---------------- host side ----------------
 struct UmmaState {
-    DevBuf qlow, boot;
+    DevBuf qlow, boot, tau, coll, coll_cnt;
     void invalidate() {}
-    void release() { qlow.release(); boot.release(); }
+    void release() { qlow.release(); boot.release(); tau.release(); coll.release(); coll_cnt.release(); }
 };
 
 static inline bool umma_eligible(int storage, int d, int pitch, long long nq, int k) {
@@ -573,87 +583,211 @@ static inline int umma_max_clusters(size_t smem, int sm_count) {
     return n;
 }
 
-// q: [nq, d] device, dtype qdtype.  qnorm: [nq] device out.  cand/cand_cnt: per-part lists out.
-static inline int search_umma(UmmaState& st, const void* x, const float* xnorm, long long n, int d, int pitch, int storage,
-                              int metric, int sm_count, const void* q, int qdtype, long long nq, int k, float* qnorm,
-                              DevBuf& cand, DevBuf& cand_cnt, int* parts_out, cudaStream_t stream, ScanTimer* timer = nullptr, ScanTimer* timer_prep = nullptr) {
-    if (n > 0x7FFFFFFFll - BLK_ROWS) { set_error("tcgen05 path: more than 2^31 rows per shard"); return PRS_EUNSUP; }
-    int rc;
+// everything about a search that depends only on shapes
+struct UmmaPlan {
+    int CL = 1, NB = 1, kbs = 1, stages = 2, n_clusters = 1, dbg = 0;
+    size_t smem = 0;
+    long long n_tiles = 0, qblock = 128, nq_pad = 128, boot_words = 0, nblocks = 1;
+};
+
+static inline int umma_plan(long long n, int pitch, long long nq, int sm_count, UmmaPlan& pl, bool no_clusters = false) {
     static const int dbg = getenv("PRS_UMMA_DEBUG") ? atoi(getenv("PRS_UMMA_DEBUG")) : 0;
     static const int dbg_kbs = getenv("PRS_UMMA_KBS") ? atoi(getenv("PRS_UMMA_KBS")) : 0;
     static const int dbg_cl = getenv("PRS_UMMA_CLUSTER") ? atoi(getenv("PRS_UMMA_CLUSTER")) : 0;
-    const int kblocks = pitch >> 6;
-    // k-blocks per pipeline stage: the largest divisor of the k-block count up to 6 (48 KB).  Few,
-    // large stages keep the per-stage barrier round trips of the single MMA-issuing thread off the
-    // critical path (measured: 8 KB stages 3443 GB/s, 16 KB 4431, 48 KB 4513 -> see profiles/)
     static const int dbg_nb = getenv("PRS_UMMA_NB") ? atoi(getenv("PRS_UMMA_NB")) : 0;
-    int NB = pitch <= 512 ? 2 : 1;                  // row blocks per MMA tile (two accumulator buffers must fit TMEM)
-    if (dbg_nb == 1) NB = 1;
-    int kbs = 1;
-    for (int c = 2; c <= 6 / NB; ++c) if (kblocks % c == 0) kbs = c;      // stages of up to 48 KB
-    if (dbg_kbs > 0 && kblocks % dbg_kbs == 0) kbs = dbg_kbs;
-    const size_t stage_bytes = (size_t)kbs * NB * KBLOCK_BYTES;
-    const size_t fixed = 4 * (size_t)NB * BLK_ROWS * 4 + (2 * UMMA_MAX_STAGES + 4) * 8 + 16;
-    int stages = (int)((226 * 1024 - 1024 - fixed) / stage_bytes);
-    if (stages > UMMA_MAX_STAGES) stages = UMMA_MAX_STAGES;
-    const size_t smem = 1024 + (size_t)stages * stage_bytes + fixed;
-    const long long n_tiles = (n + NB * BLK_ROWS - 1) / (NB * BLK_ROWS);
-
+    if (n > 0x7FFFFFFFll - 2 * BLK_ROWS) { set_error("tcgen05 path: more than 2^31 rows per shard"); return PRS_EUNSUP; }
+    pl.dbg = dbg;
+    const int kblocks = pitch >> 6;
+    pl.NB = pitch <= 512 ? 2 : 1;                   // row blocks per MMA tile (two accumulator buffers must fit TMEM)
+    if (dbg_nb == 1) pl.NB = 1;
+    // k-blocks per pipeline stage: stages of up to 48 KB.  Few, large stages keep the per-stage
+    // barrier round trips of the single MMA-issuing thread off the critical path (measured: 8 KB
+    // stages 3443 GB/s, 16 KB 4431, 48 KB 4513 -> see profiles/)
+    pl.kbs = 1;
+    for (int c = 2; c <= 6 / pl.NB; ++c) if (kblocks % c == 0) pl.kbs = c;
+    if (dbg_kbs > 0 && kblocks % dbg_kbs == 0) pl.kbs = dbg_kbs;
+    const size_t stage_bytes = (size_t)pl.kbs * pl.NB * KBLOCK_BYTES;
+    const size_t fixed = 4 * (size_t)pl.NB * BLK_ROWS * 4 + (2 * UMMA_MAX_STAGES + 4) * 8 + 16;
+    pl.stages = (int)((226 * 1024 - 1024 - fixed) / stage_bytes);
+    if (pl.stages > UMMA_MAX_STAGES) pl.stages = UMMA_MAX_STAGES;
+    pl.smem = 1024 + (size_t)pl.stages * stage_bytes + fixed;
+    pl.n_tiles = (n + pl.NB * BLK_ROWS - 1) / (pl.NB * BLK_ROWS);
     // cluster size: query blocks that share one pass over the corpus
-    int CL = nq > 2 * UMMA_M ? 4 : (nq > UMMA_M ? 2 : 1);
-    if (dbg_cl == 1 || dbg_cl == 2 || dbg_cl == 4) CL = dbg_cl;
+    pl.CL = nq > 2 * UMMA_M ? 4 : (nq > UMMA_M ? 2 : 1);
+    if (dbg_cl == 1 || dbg_cl == 2 || dbg_cl == 4) pl.CL = dbg_cl;
+    if (no_clusters) pl.CL = 1;
     int max_clusters = 0;
     for (;;) {
-        if (NB == 2) max_clusters = CL == 4 ? umma_max_clusters<4, 2>(smem, sm_count) : (CL == 2 ? umma_max_clusters<2, 2>(smem, sm_count) : umma_max_clusters<1, 2>(smem, sm_count));
-        else max_clusters = CL == 4 ? umma_max_clusters<4, 1>(smem, sm_count) : (CL == 2 ? umma_max_clusters<2, 1>(smem, sm_count) : umma_max_clusters<1, 1>(smem, sm_count));
-        if (max_clusters > 0 || CL == 1) break;
-        CL >>= 1;                                   // this device cannot co-schedule such clusters
+        const int CL = pl.CL;
+        if (pl.NB == 2) max_clusters = CL == 4 ? umma_max_clusters<4, 2>(pl.smem, sm_count) : (CL == 2 ? umma_max_clusters<2, 2>(pl.smem, sm_count) : umma_max_clusters<1, 2>(pl.smem, sm_count));
+        else max_clusters = CL == 4 ? umma_max_clusters<4, 1>(pl.smem, sm_count) : (CL == 2 ? umma_max_clusters<2, 1>(pl.smem, sm_count) : umma_max_clusters<1, 1>(pl.smem, sm_count));
+        if (max_clusters > 0 || pl.CL == 1) break;
+        pl.CL >>= 1;                                // this device cannot co-schedule such clusters
     }
     if (max_clusters <= 0) { set_error("tcgen05 path: kernel does not fit this device"); return PRS_ECUDA; }
-    const int n_clusters = (int)std::min<long long>(max_clusters, n_tiles);
-    const long long qblock = (long long)UMMA_M * CL;
-    const long long nq_pad = (nq + qblock - 1) / qblock * qblock;
-    const long long boot_words = (long long)n_clusters * UMMA_M + 32;
-    const long long nblocks = nq_pad / UMMA_M;
-    if ((rc = st.qlow.ensure((size_t)nq_pad * pitch * 2))) return rc;
-    if ((rc = st.boot.ensure((size_t)boot_words * nblocks * 4))) return rc;
-    {
-        const unsigned blocks = (unsigned)nq_pad;
-        const int bf = storage == PRS_BF16;
-        uint16_t* out = (uint16_t*)st.qlow.p;
-        uint32_t* boot = (uint32_t*)st.boot.p;
-        if (timer_prep) timer_prep->begin(stream);
-        switch (qdtype) {
-            case PRS_F32: prep_queries_kernel<float><<<blocks, 128, 0, stream>>>((const float*)q, nq, d, pitch, nq_pad, bf, out, qnorm, boot, boot_words * nblocks); break;
-            case PRS_F16: prep_queries_kernel<__half><<<blocks, 128, 0, stream>>>((const __half*)q, nq, d, pitch, nq_pad, bf, out, qnorm, boot, boot_words * nblocks); break;
-            case PRS_BF16: prep_queries_kernel<__nv_bfloat16><<<blocks, 128, 0, stream>>>((const __nv_bfloat16*)q, nq, d, pitch, nq_pad, bf, out, qnorm, boot, boot_words * nblocks); break;
-            default: set_error("search: unsupported query dtype %d", qdtype); return PRS_EINVAL;
-        }
-        if (timer_prep) timer_prep->end(stream);
-        PRS_LAUNCH_CHECK();
+    pl.n_clusters = (int)std::min<long long>(max_clusters, pl.n_tiles);
+    pl.qblock = (long long)UMMA_M * pl.CL;
+    pl.nq_pad = (nq + pl.qblock - 1) / pl.qblock * pl.qblock;
+    pl.boot_words = (long long)pl.n_clusters * UMMA_M + 32;
+    pl.nblocks = pl.nq_pad / UMMA_M;
+    return 0;
+}
+
+// queries -> 16-bit slot rows + ||q~||^2; bootstrap arrays zeroed (one launch)
+static inline int umma_prep(UmmaState& st, const UmmaPlan& pl, const void* q, int qdtype, long long nq, int d, int pitch, int storage,
+                            float* qnorm, cudaStream_t stream, ScanTimer* timer_prep) {
+    int rc;
+    if ((rc = st.qlow.ensure((size_t)pl.nq_pad * pitch * 2))) return rc;
+    if ((rc = st.boot.ensure((size_t)pl.boot_words * pl.nblocks * 4))) return rc;
+    const unsigned blocks = (unsigned)pl.nq_pad;
+    const int bf = storage == PRS_BF16;
+    uint16_t* out = (uint16_t*)st.qlow.p;
+    uint32_t* boot = (uint32_t*)st.boot.p;
+    const long long bw = pl.boot_words * pl.nblocks;
+    if (timer_prep) timer_prep->begin(stream);
+    switch (qdtype) {
+        case PRS_F32: prep_queries_kernel<float><<<blocks, 128, 0, stream>>>((const float*)q, nq, d, pitch, pl.nq_pad, bf, out, qnorm, boot, bw); break;
+        case PRS_F16: prep_queries_kernel<__half><<<blocks, 128, 0, stream>>>((const __half*)q, nq, d, pitch, pl.nq_pad, bf, out, qnorm, boot, bw); break;
+        case PRS_BF16: prep_queries_kernel<__nv_bfloat16><<<blocks, 128, 0, stream>>>((const __nv_bfloat16*)q, nq, d, pitch, pl.nq_pad, bf, out, qnorm, boot, bw); break;
+        default: set_error("search: unsupported query dtype %d", qdtype); return PRS_EINVAL;
     }
-    if ((rc = cand.ensure((size_t)n_clusters * nq * k * 8))) return rc;
-    if ((rc = cand_cnt.ensure((size_t)n_clusters * nq * 4))) return rc;
-    for (long long q0 = 0; q0 < nq; q0 += qblock) {
+    if (timer_prep) timer_prep->end(stream);
+    PRS_LAUNCH_CHECK();
+    return 0;
+}
+
+// all passes of one scan over the corpus (mode 0: sorted top-k lists of k <= 16; mode 1: collect >= tau)
+static inline int umma_scan(UmmaState& st, const UmmaPlan& pl, const void* x, const float* xnorm, long long n, int pitch, int storage,
+                            int metric, long long nq, int k, int tile_step, int mode, u64* cand, int* cand_cnt, const float* tau,
+                            u64* coll, int* coll_cnt, int coll_cap, int* overflow, cudaStream_t stream, ScanTimer* timer) {
+    for (long long q0 = 0; q0 < nq; q0 += pl.qblock) {
         UmmaParams p;
         p.x = (const unsigned char*)x;
         p.qlow = (const uint16_t*)st.qlow.p + (size_t)q0 * pitch;
         p.xnorm = xnorm; p.n_rows = n; p.pitch = pitch;
-        p.nq = (int)std::min<long long>(qblock, nq - q0);
-        p.k = k; p.l2 = metric == PRS_METRIC_L2; p.stages = stages; p.is_bf16 = storage == PRS_BF16; p.kbs = kbs; p.dbg = dbg;
+        p.nq = (int)std::min<long long>(pl.qblock, nq - q0);
+        p.k = k; p.l2 = metric == PRS_METRIC_L2; p.stages = pl.stages; p.is_bf16 = storage == PRS_BF16; p.kbs = pl.kbs; p.dbg = pl.dbg;
         p.nbuf = 2;
         p.nq_total = (int)nq; p.q0 = (int)q0;
-        p.cand = (u64*)cand.p; p.cand_cnt = (int*)cand_cnt.p;
-        p.boot = (uint32_t*)st.boot.p + (size_t)(q0 / UMMA_M) * boot_words;
-        p.boot_stride = boot_words;
+        p.cand = cand; p.cand_cnt = cand_cnt;
+        p.tile_step = tile_step; p.mode = mode; p.tau = tau; p.coll = coll; p.coll_cnt = coll_cnt; p.coll_cap = coll_cap; p.overflow = overflow;
+        p.boot = (uint32_t*)st.boot.p + (size_t)(q0 / UMMA_M) * pl.boot_words;
+        p.boot_stride = pl.boot_words;
         if (timer) timer->begin(stream);
-        if (NB == 2) rc = CL == 4 ? umma_launch<4, 2>(p, n_clusters, smem, stream) : (CL == 2 ? umma_launch<2, 2>(p, n_clusters, smem, stream) : umma_launch<1, 2>(p, n_clusters, smem, stream));
-        else rc = CL == 4 ? umma_launch<4, 1>(p, n_clusters, smem, stream) : (CL == 2 ? umma_launch<2, 1>(p, n_clusters, smem, stream) : umma_launch<1, 1>(p, n_clusters, smem, stream));
+        int rc;
+        const int CL = pl.CL, nc = pl.n_clusters;
+        if (pl.NB == 2) rc = CL == 4 ? umma_launch<4, 2>(p, nc, pl.smem, stream) : (CL == 2 ? umma_launch<2, 2>(p, nc, pl.smem, stream) : umma_launch<1, 2>(p, nc, pl.smem, stream));
+        else rc = CL == 4 ? umma_launch<4, 1>(p, nc, pl.smem, stream) : (CL == 2 ? umma_launch<2, 1>(p, nc, pl.smem, stream) : umma_launch<1, 1>(p, nc, pl.smem, stream));
         if (rc) return rc;
         if (timer) timer->end(stream);
         PRS_LAUNCH_CHECK();
     }
-    *parts_out = n_clusters;
+    return 0;
+}
+
+// k <= 16.  q: [nq, d] device, dtype qdtype.  qnorm: [nq] device out.  cand: per-part lists out.
+static inline int search_umma(UmmaState& st, const void* x, const float* xnorm, long long n, int d, int pitch, int storage,
+                              int metric, int sm_count, const void* q, int qdtype, long long nq, int k, float* qnorm,
+                              DevBuf& cand, DevBuf& cand_cnt, int* parts_out, cudaStream_t stream, ScanTimer* timer = nullptr, ScanTimer* timer_prep = nullptr) {
+    UmmaPlan pl;
+    int rc;
+    if ((rc = umma_plan(n, pitch, nq, sm_count, pl))) return rc;
+    if ((rc = umma_prep(st, pl, q, qdtype, nq, d, pitch, storage, qnorm, stream, timer_prep))) return rc;
+    if ((rc = cand.ensure((size_t)pl.n_clusters * nq * k * 8))) return rc;
+    if ((rc = cand_cnt.ensure((size_t)pl.n_clusters * nq * 4))) return rc;
+    if ((rc = umma_scan(st, pl, x, xnorm, n, pitch, storage, metric, nq, k, 1, 0, (u64*)cand.p, (int*)cand_cnt.p, nullptr, nullptr, nullptr, 0,
+                        nullptr, stream, timer))) return rc;
+    *parts_out = pl.n_clusters;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Wide k (16 < k <= 1024): sample -> threshold -> collect -> select.
+//   1. the scan kernel visits every S-th tile and leaves, per part, that part's own top-L list of the
+//      sample (L = 4 / 8 / 16; no cross-CTA bootstrap here -- its bound is only valid for k <= L);
+//   2. tau[q] = k-th largest key of their union (k distinct rows: a lower bound of the true k-th best);
+//   3. the full scan runs in collect mode: every score >= tau[q] is appended, unsorted, to the
+//      (part, query) slice of a collection buffer -- about k * S candidates per query in total;
+//   4. one CTA per query selects the k best of its slices into a single sorted list (then the
+//      ordinary merge / merge+exchange kernel finishes it).
+// Cost: (1 + 1/S) scans.  If a slice overflows (pathological duplicates) *overflowed is set and the
+// caller falls back to the CUDA-core scan.  Synchronises `stream` to read that flag.
+// ---------------------------------------------------------------------------------------------------
+constexpr int UMMA_WIDE_MAX_K = PRS_MAX_K;
+static inline bool umma_wide_eligible(int storage, int pitch, long long nq, int k, long long n) {
+    return (storage == PRS_F16 || storage == PRS_BF16) && pitch <= 768 && k > UMMA_MAX_K && k <= UMMA_WIDE_MAX_K && nq >= 1 &&
+           n >= 32ll * k && n >= 16384;
+}
+
+static inline int search_umma_wide(UmmaState& st, const void* x, const float* xnorm, long long n, int d, int pitch, int storage,
+                                   int metric, int sm_count, const void* q, int qdtype, long long nq, int k, float* qnorm,
+                                   DevBuf& cand, DevBuf& cand_cnt, bool* overflowed, cudaStream_t stream,
+                                   ScanTimer* timer = nullptr, ScanTimer* timer_prep = nullptr) {
+    UmmaPlan pl;
+    int rc;
+    *overflowed = false;
+    // one CTA per part (no clusters): the threshold needs many independent per-part lists
+    if ((rc = umma_plan(n, pitch, nq, sm_count, pl, true))) return rc;
+    const int parts = pl.n_clusters;
+    // sampling step: every part keeps >= 2 sampled tiles and the sample holds >= 32 k rows
+    long long S = pl.n_tiles / (2ll * parts);
+    const long long rows_per_tile = (long long)pl.NB * BLK_ROWS;
+    S = std::min<long long>(S, (pl.n_tiles * rows_per_tile) / (32ll * k));
+    S = std::max<long long>(1, std::min<long long>(16, S));
+    const long long sampled = (pl.n_tiles + S - 1) / S;
+    const double ratio = (double)pl.n_tiles / (double)sampled;
+    const double expect = (double)k * ratio / parts;                 // survivors per (part, query)
+    int cap = next_pow2((int)std::min<double>(1 << 20, std::max<double>(64.0, 6.0 * expect + 32.0)));
+    const size_t coll_bytes = (size_t)parts * nq * cap * 8;
+    if (coll_bytes > (4ull << 30)) { *overflowed = true; return 0; }  // would not fit: let the caller use the CUDA-core scan
+    int L = 4;                                                        // per-part list length of the sampling pass
+    while (L < UMMA_MAX_K && (long long)parts * L < 3ll * k) L <<= 1;  // parts * L >= ~3k candidates for the threshold
+    if ((long long)parts * L < 2ll * k) { *overflowed = true; return 0; }   // too few parts for a useful bound
+    if ((rc = umma_prep(st, pl, q, qdtype, nq, d, pitch, storage, qnorm, stream, timer_prep))) return rc;
+    if ((rc = cand.ensure(std::max<size_t>((size_t)parts * nq * L * 8, (size_t)nq * k * 8)))) return rc;
+    if ((rc = cand_cnt.ensure((size_t)parts * nq * 4))) return rc;
+    if ((rc = st.tau.ensure((size_t)nq * 4 + 16))) return rc;
+    if ((rc = st.coll.ensure(coll_bytes))) return rc;
+    if ((rc = st.coll_cnt.ensure((size_t)parts * nq * 4))) return rc;
+    int* overflow = (int*)((unsigned char*)st.tau.p + (size_t)nq * 4 + 8 - (((size_t)nq * 4) & 7));
+    PRS_CUDA(cudaMemsetAsync(overflow, 0, 4, stream));
+    // 1. sampling pass (top-16 lists)
+    if ((rc = umma_scan(st, pl, x, xnorm, n, pitch, storage, metric, nq, L, (int)S, 2, (u64*)cand.p, (int*)cand_cnt.p, nullptr, nullptr, nullptr, 0,
+                        nullptr, stream, nullptr))) return rc;
+    // 2. thresholds
+    {
+        const int sortn = next_pow2((int)std::max<long long>(k + MERGE_THREADS, std::min<long long>((long long)parts * L, MERGE_ONESHOT)));
+        const size_t smem = (size_t)sortn * 8 + MERGE_THREADS * 8 + 16;
+        PRS_CUDA(cudaFuncSetAttribute(tau_from_lists_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        tau_from_lists_kernel<<<(unsigned)nq, MERGE_THREADS, smem, stream>>>((const u64*)cand.p, parts, (int)nq, L, k, sortn, (float*)st.tau.p);
+        PRS_LAUNCH_CHECK();
+    }
+    // 3. collecting pass (the dominant kernel: timed)
+    if ((rc = umma_scan(st, pl, x, xnorm, n, pitch, storage, metric, nq, k, 1, 1, nullptr, nullptr, (const float*)st.tau.p, (u64*)st.coll.p,
+                        (int*)st.coll_cnt.p, cap, overflow, stream, timer))) return rc;
+    // 4. select into one sorted list per query: cand[1][nq][k]
+    {
+        const int sortn = next_pow2(k + MERGE_THREADS);
+        const size_t smem = (size_t)sortn * 8 + (size_t)(parts + 2) * 4 + 16;
+        PRS_CUDA(cudaFuncSetAttribute(select_collected_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        select_collected_kernel<<<(unsigned)nq, MERGE_THREADS, smem, stream>>>((const u64*)st.coll.p, (const int*)st.coll_cnt.p, parts, (int)nq, cap, k,
+                                                                             sortn, (u64*)cand.p);
+        PRS_LAUNCH_CHECK();
+    }
+    int h_over = 0;
+    PRS_CUDA(cudaMemcpyAsync(&h_over, overflow, 4, cudaMemcpyDeviceToHost, stream));
+    PRS_CUDA(cudaStreamSynchronize(stream));
+    if (getenv("PRS_WIDE_DEBUG")) {
+        std::vector<float> ht((size_t)nq);
+        std::vector<int> hc((size_t)parts * nq);
+        cudaMemcpy(ht.data(), st.tau.p, (size_t)nq * 4, cudaMemcpyDeviceToHost);
+        cudaMemcpy(hc.data(), st.coll_cnt.p, (size_t)parts * nq * 4, cudaMemcpyDeviceToHost);
+        long long tot0 = 0; int mx = 0;
+        for (int p2 = 0; p2 < parts; ++p2) { tot0 += hc[(size_t)p2 * nq]; mx = std::max(mx, hc[(size_t)p2 * nq]); }
+        fprintf(stderr, "[wide] n=%lld k=%d parts=%d S=%lld cap=%d tau[0]=%g tau[last]=%g q0: total=%lld max=%d overflow=%d\n",
+                n, k, parts, S, cap, ht[0], ht[(size_t)nq - 1], tot0, mx, h_over);
+    }
+    *overflowed = h_over != 0;
     return 0;
 }
 

@@ -11,7 +11,7 @@ namespace prs {
 constexpr int MERGE_THREADS = 256;
 constexpr int MERGE_ONESHOT = 4096;     // inputs up to this many keys are sorted in shared memory in one shot
 
-// CTA-level top-k over `parts` lists of k keys each (list p = keys [p*k, (p+1)*k), sorted
+// CTA-level top-k over `parts` lists of L keys each (list p = keys [p*L, (p+1)*L), sorted
 // descending, 0 = empty).  buf: sortn keys of shared memory (power of two, >= k + MERGE_THREADS);
 // heads: MERGE_THREADS keys of shared memory; s_n: two ints.
 // Inputs that fit (parts*k <= sortn) are done in one memory round trip:
@@ -24,8 +24,8 @@ constexpr int MERGE_ONESHOT = 4096;     // inputs up to this many keys are sorte
 // Larger inputs stream through block_topk_stream.  On return buf[0..k) holds the result
 // (descending, 0 = empty); returns the number of valid entries.
 template <class Fetch>
-__device__ __forceinline__ int block_topk_lists(Fetch fetch, int parts, int k, u64* buf, int sortn, u64* heads, int* s_n, int tid) {
-    const long long total = (long long)parts * k;
+__device__ __forceinline__ int block_topk_lists(Fetch fetch, int parts, int L, int k, u64* buf, int sortn, u64* heads, int* s_n, int tid) {
+    const long long total = (long long)parts * L;
     if (total > sortn) return block_topk_stream(fetch, total, k, buf, sortn, s_n, tid, MERGE_THREADS, 1);
     constexpr int NREG = MERGE_ONESHOT / MERGE_THREADS;        // 16
     u64 v[NREG];
@@ -35,7 +35,7 @@ __device__ __forceinline__ int block_topk_lists(Fetch fetch, int parts, int k, u
         v[i] = idx < (int)total ? fetch((long long)idx) : 0ull;
     }
     const int nheads = parts < MERGE_THREADS ? parts : MERGE_THREADS;
-    const u64 myhead = tid < nheads ? fetch((long long)tid * k) : 0ull;
+    const u64 myhead = tid < nheads ? fetch((long long)tid * L) : 0ull;
     heads[tid] = myhead;
     if (tid == 0) { s_n[0] = 0; s_n[1] = 0; }
     __syncthreads();
@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_cand_kernel(
         const int part = (int)((unsigned)i / (unsigned)k), j = (int)i - part * k;
         return __ldcg(cand + ((size_t)part * nq + q) * k + j);
     };
-    const int n = block_topk_lists(fetch, parts, k, buf, sortn, heads, s_n, tid);
+    const int n = block_topk_lists(fetch, parts, k, k, buf, sortn, heads, s_n, tid);
     for (int j = tid; j < k; j += MERGE_THREADS) {
         float dv;
         long long iv;
@@ -94,5 +94,51 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_cand_kernel(
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Wide-k path (16 < k <= 1024 on the tcgen05 scan).
+// tau: the sampling pass left, per part, a sorted top-L list of each query over a SAMPLE of the
+// rows; the k-th largest key of their union belongs to k distinct rows, so its score is a lower
+// bound of the query's true k-th best -- the admission threshold of the collecting pass.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(MERGE_THREADS) tau_from_lists_kernel(const u64* __restrict__ cand, int parts, int nq, int L, int k,
+                                                                       int sortn, float* __restrict__ tau) {
+    extern __shared__ __align__(16) unsigned char msm[];
+    u64* buf = reinterpret_cast<u64*>(msm);
+    u64* heads = buf + sortn;
+    int* s_n = reinterpret_cast<int*>(heads + MERGE_THREADS);
+    const int q = blockIdx.x, tid = threadIdx.x;
+    auto fetch = [&](long long i) -> u64 {
+        const int part = (int)((unsigned)i / (unsigned)L), j = (int)i - part * L;
+        return __ldcg(cand + ((size_t)part * nq + q) * L + j);
+    };
+    const int n = block_topk_lists(fetch, parts, L, k, buf, sortn, heads, s_n, tid);
+    if (tid == 0) tau[q] = (n >= k) ? key_score(buf[k - 1]) : -INFINITY;
+}
+
+// select: the collecting pass left, per (part, query), an unsorted slice of keys >= tau[q]; one CTA
+// per query streams all slices through the block top-k and writes ONE sorted list of k keys
+// (0 = empty), which the ordinary merge / merge+exchange kernel then finishes as a single part.
+__global__ void __launch_bounds__(MERGE_THREADS) select_collected_kernel(const u64* __restrict__ coll, const int* __restrict__ coll_cnt,
+                                                                         int parts, int nq, int cap, int k, int sortn,
+                                                                         u64* __restrict__ out) {
+    extern __shared__ __align__(16) unsigned char msm[];
+    u64* buf = reinterpret_cast<u64*>(msm);
+    int* offs = reinterpret_cast<int*>(buf + sortn);             // [parts + 1]
+    int* s_n = offs + parts + 1;
+    const int q = blockIdx.x, tid = threadIdx.x;
+    for (int p = tid; p < parts; p += MERGE_THREADS) offs[p + 1] = __ldcg(coll_cnt + (size_t)p * nq + q);
+    if (tid == 0) offs[0] = 0;
+    __syncthreads();
+    if (tid == 0) for (int p = 0; p < parts; ++p) offs[p + 1] += offs[p];
+    __syncthreads();
+    const long long total = offs[parts];
+    auto fetch = [&](long long i) -> u64 {
+        int lo = 0, hi = parts;                                  // last part with offs[part] <= i
+        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (offs[mid] <= (int)i) lo = mid; else hi = mid; }
+        return __ldcg(coll + ((size_t)lo * nq + q) * (size_t)cap + ((int)i - offs[lo]));
+    };
+    const int n = block_topk_stream(fetch, total, k, buf, sortn, s_n, tid, MERGE_THREADS, 1);
+    for (int j = tid; j < k; j += MERGE_THREADS) out[(size_t)q * k + j] = (j < n) ? buf[j] : 0ull;
+}
 
 }  // namespace prs

@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_xchg_kernel(
         const int part = (int)((unsigned)i / (unsigned)k), j = (int)i - part * k;
         return __ldcg(cand + ((size_t)part * nq + q) * k + j);
     };
-    const int n = block_topk_lists(fetch, parts, k, buf, sortn, heads, s_n, tid);
+    const int n = block_topk_lists(fetch, parts, k, k, buf, sortn, heads, s_n, tid);
     // keep the local list in registers: buf is reused by the second merge
     u64 mine[(PRS_MAX_K + MERGE_THREADS - 1) / MERGE_THREADS];
 #pragma unroll
@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_xchg_kernel(
         return ((u64)f2ord(s) << 32) | (u64)(~(uint32_t)(part * k + j));
     };
     __syncthreads();
-    const int n2 = block_topk_lists(fetch2, G, k, buf, sortn, heads, s_n, tid);
+    const int n2 = block_topk_lists(fetch2, G, k, k, buf, sortn, heads, s_n, tid);
     for (int j = tid; j < k; j += MERGE_THREADS) {
         if (j < n2) {
             const uint32_t pos = ~(uint32_t)buf[j];

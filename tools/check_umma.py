@@ -43,5 +43,11 @@ if __name__ == "__main__":
     tot += run(30000, 768, 257, 10, O.METRIC_IP, "bf16")       # cluster of 4, blocks 3 and 4 (almost) empty
     tot += run(100000, 768, 1024, 10, O.METRIC_IP, "fp16")     # cluster of 4, two passes
     tot += run(100, 64, 600, 5, O.METRIC_L2, "fp16")           # fewer tiles than clusters
+    # wide k (16 < k <= 1024): sample -> threshold -> collect -> select
+    tot += run(200000, 768, 64, 100, O.METRIC_IP, "fp16")
+    tot += run(200000, 384, 1, 17, O.METRIC_L2, "fp16")
+    tot += run(100000, 512, 300, 100, O.METRIC_L2, "bf16")
+    tot += run(70000, 384, 5, 1024, O.METRIC_IP, "fp16")
+    tot += run(40000, 768, 130, 33, O.METRIC_L2, "fp16")
     print("TOTAL BAD", tot)
     sys.exit(1 if tot else 0)
