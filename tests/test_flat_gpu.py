@@ -221,6 +221,46 @@ def test_tcgen05_clusters_and_tile_shapes_vs_oracle(P, n, d, nq, k, metric, stor
         assert np.array_equal(I1[0], I[r]) and np.array_equal(D1[0], D[r])
 
 
+@pytest.mark.parametrize("n,d,nq,k,metric,storage", [
+    (200000, 768, 64, 100, O.METRIC_IP, "fp16"),
+    (200000, 384, 1, 17, O.METRIC_L2, "fp16"),
+    (100000, 512, 300, 100, O.METRIC_L2, "bf16"),     # several 128-query passes
+    (70000, 384, 5, 1024, O.METRIC_IP, "fp16"),       # k at the API maximum
+    (40000, 768, 130, 33, O.METRIC_L2, "fp16"),
+])
+def test_tcgen05_wide_k_vs_oracle(P, n, d, nq, k, metric, storage):
+    """16 < k <= 1024 on 16-bit corpora: sampled per-part lists -> threshold -> collecting scan -> select."""
+    rng = np.random.default_rng(n + d + nq + k)
+    x = rng.standard_normal((n, d)).astype(np.float32)
+    x /= np.linalg.norm(x, axis=1, keepdims=True)
+    q = rng.standard_normal((nq, d)).astype(np.float32)
+    q /= np.linalg.norm(q, axis=1, keepdims=True)
+    idx = P.FlatIndex(d, metric, storage)
+    idx.add(x)
+    D, I = idx.search(q, k)
+    assert idx.last_path == "tcgen05"
+    xs, qs = _round_to(x, storage), _round_to(q, storage)
+    S = O.flat_scores_f64(xs, qs, metric)
+    for r in range(0, nq, max(1, nq // 24)):
+        O.check_topk_against_scores(I[r], D[r], S[r], k, metric == O.METRIC_IP, rtol=RTOL_16, atol=2e-5, what=f"wide q{r}")
+
+
+def test_tcgen05_wide_k_pathological_duplicates_fall_back_exactly(P):
+    """Thousands of identical rows tie with the threshold: the collection buffers overflow and the
+    search must fall back to the exact CUDA-core scan (ties then ordered by ascending row id)."""
+    rng = np.random.default_rng(3)
+    base = rng.standard_normal((40000, 128)).astype(np.float32)
+    base /= np.linalg.norm(base, axis=1, keepdims=True)
+    x = base.copy()
+    x[5000:25000] = x[0]                               # 20 000 copies of row 0
+    idx = P.FlatIndex(128, P.METRIC_IP, "fp16")
+    idx.add(x)
+    D, I = idx.search(x[:1], 100)
+    assert idx.last_path == "cuda-core"
+    want = [0] + list(range(5000, 5099))
+    assert I[0].tolist() == want and np.allclose(D[0], D[0, 0])
+
+
 @pytest.mark.parametrize("storage", ["fp16", "bf16"])
 @pytest.mark.parametrize("d", [40, 128, 384])
 def test_16bit_t64_layout_incremental_add_and_reconstruct(P, storage, d):
@@ -273,6 +313,8 @@ def test_auto_path_selection(P):
     f32.add(x)
     f32.search(rng.standard_normal((64, 256)).astype(np.float32), 10)
     assert f32.last_path == "cuda-core"           # fp32 storage is the exact-parity CUDA-core scan
+    idx.search(rng.standard_normal((4, 256)).astype(np.float32), 100)
+    assert idx.last_path == "cuda-core"           # wide k needs >= 16384 rows for its sampled threshold
     idx.search(rng.standard_normal((64, 256)).astype(np.float32), 100)
     assert idx.last_path == "cuda-core"           # k beyond the in-smem lists
 
