@@ -168,11 +168,21 @@ struct prs_index {
     long long id_offset = 0;
     int path_force = 0, last_path = 0;
     std::mutex mu, host_mu;
-    cudaEvent_t ws_event = nullptr;
-    cudaStream_t ws_stream = nullptr;
-    bool ws_used = false;
-    DevBuf lists, cand, cand_cnt, qf32, qnorm, qlow, hD, hI, hQ, stage;
-    UmmaState umma;
+    // Search workspaces.  Two slots used round-robin so that two searches can be IN FLIGHT on two
+    // streams (the merge / exchange kernel of one overlaps the scan of the next); a slot is reused
+    // only after the search that last used it has finished (event wait when the stream differs).
+    struct Workspace {
+        DevBuf lists, cand, cand_cnt, qf32, qnorm;
+        UmmaState umma;
+        cudaEvent_t event = nullptr;
+        cudaStream_t stream = nullptr;
+        bool used = false;
+    };
+    static constexpr int NSLOT = 2;
+    Workspace slot[NSLOT];
+    Workspace* cur = &slot[0];          // workspace of the search being issued (set under mu)
+    unsigned next_slot = 0;
+    DevBuf hD, hI, hQ, stage;
     ScanTimer timer, timer_prep, timer_merge;
 };
 static thread_local struct prs_xchg* t_xchg = nullptr;   // set by the calling thread for the duration of a sharded search
@@ -224,7 +234,6 @@ static int index_grow(prs_index* idx, long long n_total) {
     if (idx->x) cudaFree(idx->x);
     if (idx->xnorm) cudaFree(idx->xnorm);
     idx->x = nx; idx->xnorm = nn; idx->cap_rows = n_total;
-    idx->umma.invalidate();
     return 0;
 }
 
@@ -263,7 +272,6 @@ static int add_device_impl(prs_index* idx, const void* x, int dtype, long long n
     }
     if (rc) return rc;
     idx->n += n;
-    idx->umma.invalidate();
     return 0;
 }
 
@@ -292,7 +300,7 @@ static int launch_merge(prs_index* idx, int parts, long long nq, int k, int out_
         prs_xchg* x = t_xchg;
         ++x->gen;
         PRS_CUDA(cudaFuncSetAttribute(merge_xchg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        merge_xchg_kernel<<<(unsigned)nq, MERGE_THREADS, smem, st>>>((const u64*)idx->cand.p, parts,
+        merge_xchg_kernel<<<(unsigned)nq, MERGE_THREADS, smem, st>>>((const u64*)idx->cur->cand.p, parts,
                                                                     (int)nq, k, sortn, out_mode, qnorm, idx->id_offset,
                                                                     idx->metric == PRS_METRIC_IP ? 1 : 0, x->view, x->gen, D,
                                                                     (long long*)I, x->status);
@@ -300,7 +308,7 @@ static int launch_merge(prs_index* idx, int parts, long long nq, int k, int out_
         return 0;
     }
     PRS_CUDA(cudaFuncSetAttribute(merge_cand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    merge_cand_kernel<<<(unsigned)nq, MERGE_THREADS, smem, st>>>((const u64*)idx->cand.p, parts,
+    merge_cand_kernel<<<(unsigned)nq, MERGE_THREADS, smem, st>>>((const u64*)idx->cur->cand.p, parts,
                                                                 (int)nq, k, sortn, out_mode, qnorm, idx->id_offset, D,
                                                                 (long long*)I);
     PRS_LAUNCH_CHECK();
@@ -335,9 +343,9 @@ static int search_simt(prs_index* idx, const float* qf, int q_stride, long long 
         const long long n_tiles = (idx->n + tile_rows - 1) / tile_rows;
         grid = (int)std::min<long long>(idx->sm_count, n_tiles);
     }
-    if ((rc = idx->lists.ensure((size_t)grid * SIMT_NW * qb_max * cap * 8))) return rc;
-    if ((rc = idx->cand.ensure((size_t)grid * nq * k * 8))) return rc;
-    if ((rc = idx->cand_cnt.ensure((size_t)grid * nq * 4))) return rc;
+    if ((rc = idx->cur->lists.ensure((size_t)grid * SIMT_NW * qb_max * cap * 8))) return rc;
+    if ((rc = idx->cur->cand.ensure((size_t)grid * nq * k * 8))) return rc;
+    if ((rc = idx->cur->cand_cnt.ensure((size_t)grid * nq * 4))) return rc;
     while (done < nq) {
         const long long left = nq - done;
         const int QB = left >= 8 ? 8 : (left >= 4 ? 4 : (left >= 2 ? 2 : 1));
@@ -356,7 +364,7 @@ static int search_simt(prs_index* idx, const float* qf, int q_stride, long long 
             return PRS_EUNSUP;
         }
         p.stages = stages;
-        p.lists = (u64*)idx->lists.p; p.cand = (u64*)idx->cand.p; p.cand_cnt = (int*)idx->cand_cnt.p;
+        p.lists = (u64*)idx->cur->lists.p; p.cand = (u64*)idx->cur->cand.p; p.cand_cnt = (int*)idx->cur->cand_cnt.p;
         p.nq_total = (int)nq; p.q0 = (int)done; p.sortn = sortn;
         const size_t smem = 512 + qbytes + (size_t)stages * tile_bytes;
         idx->timer.begin(st);
@@ -376,9 +384,11 @@ static int search_device_impl(prs_index* idx, const void* q, int qdtype, long lo
     std::lock_guard<std::mutex> lock(idx->mu);
     // the scan workspace is shared by all searches on this index: order a search issued on a new
     // stream after the previous one (same-stream searches are ordered already)
-    if (!idx->ws_event) PRS_CUDA(cudaEventCreateWithFlags(&idx->ws_event, cudaEventDisableTiming));
-    if (idx->ws_used && idx->ws_stream != st) PRS_CUDA(cudaStreamWaitEvent(st, idx->ws_event, 0));
-    struct Rec { prs_index* i; cudaStream_t s; ~Rec() { cudaEventRecord(i->ws_event, s); i->ws_stream = s; i->ws_used = true; } } rec{idx, st};
+    prs_index::Workspace* ws = &idx->slot[idx->next_slot++ % prs_index::NSLOT];
+    idx->cur = ws;
+    if (!ws->event) PRS_CUDA(cudaEventCreateWithFlags(&ws->event, cudaEventDisableTiming));
+    if (ws->used && ws->stream != st) PRS_CUDA(cudaStreamWaitEvent(st, ws->event, 0));
+    struct Rec { prs_index::Workspace* w; cudaStream_t s; ~Rec() { cudaEventRecord(w->event, s); w->stream = s; w->used = true; } } rec{ws, st};
     if (idx->n == 0) {
         const long long tot = nq * k;
         fill_empty_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(D, (long long*)I, tot,
@@ -392,13 +402,13 @@ static int search_device_impl(prs_index* idx, const void* q, int qdtype, long lo
     if (path == 0) path = (umma_eligible(idx->storage, idx->d, idx->pitch, nq, k) || wide) ? 2 : 1;
     if (path == 2 && wide) {
         // 16 < k <= 1024: sample -> threshold -> collect -> select (flat_umma.cuh), then the usual merge of ONE part
-        if ((rc = idx->qnorm.ensure((size_t)nq * 4))) return rc;
+        if ((rc = idx->cur->qnorm.ensure((size_t)nq * 4))) return rc;
         bool overflowed = false;
-        if ((rc = search_umma_wide(idx->umma, idx->x, idx->xnorm, idx->n, idx->d, idx->pitch, idx->storage, idx->metric, idx->sm_count,
-                                   q, qdtype, nq, k, (float*)idx->qnorm.p, idx->cand, idx->cand_cnt, &overflowed, st, &idx->timer, &idx->timer_prep))) return rc;
+        if ((rc = search_umma_wide(idx->cur->umma, idx->x, idx->xnorm, idx->n, idx->d, idx->pitch, idx->storage, idx->metric, idx->sm_count,
+                                   q, qdtype, nq, k, (float*)idx->cur->qnorm.p, idx->cur->cand, idx->cur->cand_cnt, &overflowed, st, &idx->timer, &idx->timer_prep))) return rc;
         if (!overflowed) {
             idx->last_path = 2;
-            return launch_merge(idx, 1, nq, k, idx->metric == PRS_METRIC_L2 ? 2 : 0, (const float*)idx->qnorm.p, D, I, st);
+            return launch_merge(idx, 1, nq, k, idx->metric == PRS_METRIC_L2 ? 2 : 0, (const float*)idx->cur->qnorm.p, D, I, st);
         }
         if (idx->path_force == 2) { set_error("tcgen05 wide-k path: candidate buffer overflow (too many rows tie with the threshold)"); return PRS_EUNSUP; }
         path = 1;                                   // pathological input: exact CUDA-core scan instead
@@ -409,21 +419,21 @@ static int search_device_impl(prs_index* idx, const void* q, int qdtype, long lo
             return PRS_EUNSUP;
         }
         idx->last_path = 2;
-        if ((rc = idx->qnorm.ensure((size_t)nq * 4))) return rc;
+        if ((rc = idx->cur->qnorm.ensure((size_t)nq * 4))) return rc;
         int parts = 0;
-        if ((rc = search_umma(idx->umma, idx->x, idx->xnorm, idx->n, idx->d, idx->pitch, idx->storage, idx->metric, idx->sm_count,
-                              q, qdtype, nq, k, (float*)idx->qnorm.p, idx->cand, idx->cand_cnt, &parts, st, &idx->timer, &idx->timer_prep))) return rc;
-        return launch_merge(idx, parts, nq, k, idx->metric == PRS_METRIC_L2 ? 2 : 0, (const float*)idx->qnorm.p, D, I, st);
+        if ((rc = search_umma(idx->cur->umma, idx->x, idx->xnorm, idx->n, idx->d, idx->pitch, idx->storage, idx->metric, idx->sm_count,
+                              q, qdtype, nq, k, (float*)idx->cur->qnorm.p, idx->cur->cand, idx->cur->cand_cnt, &parts, st, &idx->timer, &idx->timer_prep))) return rc;
+        return launch_merge(idx, parts, nq, k, idx->metric == PRS_METRIC_L2 ? 2 : 0, (const float*)idx->cur->qnorm.p, D, I, st);
     }
     const float* qf = (const float*)q;
     if (qdtype != PRS_F32) {
         const long long tot = nq * idx->d;
-        if ((rc = idx->qf32.ensure((size_t)tot * 4))) return rc;
-        if (qdtype == PRS_F16) to_f32_kernel<__half><<<(unsigned)((tot + 255) / 256), 256, 0, st>>>((const __half*)q, tot, (float*)idx->qf32.p);
-        else if (qdtype == PRS_BF16) to_f32_kernel<__nv_bfloat16><<<(unsigned)((tot + 255) / 256), 256, 0, st>>>((const __nv_bfloat16*)q, tot, (float*)idx->qf32.p);
+        if ((rc = idx->cur->qf32.ensure((size_t)tot * 4))) return rc;
+        if (qdtype == PRS_F16) to_f32_kernel<__half><<<(unsigned)((tot + 255) / 256), 256, 0, st>>>((const __half*)q, tot, (float*)idx->cur->qf32.p);
+        else if (qdtype == PRS_BF16) to_f32_kernel<__nv_bfloat16><<<(unsigned)((tot + 255) / 256), 256, 0, st>>>((const __nv_bfloat16*)q, tot, (float*)idx->cur->qf32.p);
         else { set_error("search: unsupported query dtype %d", qdtype); return PRS_EINVAL; }
         PRS_LAUNCH_CHECK();
-        qf = (const float*)idx->qf32.p;
+        qf = (const float*)idx->cur->qf32.p;
     }
     idx->last_path = 1;
     return search_simt(idx, qf, idx->d, nq, k, D, I, st);
@@ -473,10 +483,12 @@ void prs_index_free(prs_index* idx) {
     DeviceGuard g(idx->device);
     if (idx->x) cudaFree(idx->x);
     if (idx->xnorm) cudaFree(idx->xnorm);
-    idx->lists.release(); idx->cand.release(); idx->cand_cnt.release(); idx->qf32.release(); idx->qnorm.release();
-    idx->qlow.release(); idx->hD.release(); idx->hI.release(); idx->hQ.release(); idx->stage.release();
-    idx->umma.release();
-    if (idx->ws_event) cudaEventDestroy(idx->ws_event);
+    for (auto& w : idx->slot) {
+        w.lists.release(); w.cand.release(); w.cand_cnt.release(); w.qf32.release(); w.qnorm.release();
+        w.umma.release();
+        if (w.event) cudaEventDestroy(w.event);
+    }
+    idx->hD.release(); idx->hI.release(); idx->hQ.release(); idx->stage.release();
     delete idx;
 }
 

@@ -46,7 +46,7 @@ class ShardedFlatIndex:
     """FlatIndex whose rows are split across the ranks of a torch.distributed process group."""
 
     def __init__(self, d: int, metric: int = METRIC_L2, storage="fp16", group=None, device: int | None = None,
-                 exchange: str = "p2p", nq_cap: int = 1024, k_cap: int = 128):
+                 exchange: str = "p2p", nq_cap: int = 1024, k_cap: int = 128, lanes: int = 2):
         import torch.distributed as dist
         self.dist = dist
         self.group = group
@@ -58,39 +58,47 @@ class ShardedFlatIndex:
         self.offset = 0
         self.ntotal_global = 0
         self.exchange = exchange
-        self._x = ctypes.c_void_p()
+        # `lanes` independent exchange contexts, used round-robin: consecutive searches issued on
+        # different CUDA streams can then be in flight together (each context has its own slots and
+        # generation counter; every rank must issue the same sequence of searches)
+        self._xs = []
+        self._calls = 0
         self._cap = (int(nq_cap), int(nq_cap) * int(k_cap))
         if self.world > 1 and exchange == "p2p":
-            self._open_exchange(nq_cap, k_cap)
+            for _ in range(max(1, int(lanes))):
+                self._xs.append(self._open_exchange(nq_cap, k_cap))
 
-    def _open_exchange(self, nq_cap: int, k_cap: int) -> None:
-        """Create this rank's exchange buffer and map every peer's over CUDA IPC (NVLink peer memory)."""
+    def _open_exchange(self, nq_cap: int, k_cap: int):
+        """Create one exchange buffer of this rank and map every peer's over CUDA IPC (NVLink peer memory)."""
         import torch
         L = _lib.lib()
         dev = self.local.device
-        check(L.prs_xchg_create(dev, self.world, self.rank, int(nq_cap), int(k_cap), ctypes.byref(self._x)))
+        x = ctypes.c_void_p()
+        check(L.prs_xchg_create(dev, self.world, self.rank, int(nq_cap), int(k_cap), ctypes.byref(x)))
         hb = int(L.prs_xchg_handle_bytes())
         mine = (ctypes.c_ubyte * hb)()
-        check(L.prs_xchg_get_handle(self._x, mine))
+        check(L.prs_xchg_get_handle(x, mine))
         on_gpu = self.dist.get_backend(self.group) == "nccl"
         tdev = torch.device("cuda", dev) if on_gpu else torch.device("cpu")
         t = torch.tensor(list(mine), dtype=torch.uint8, device=tdev)
         allh = torch.empty(self.world * hb, dtype=torch.uint8, device=tdev)
         self.dist.all_gather_into_tensor(allh, t, group=self.group)
         raw = bytes(allh.cpu().tolist())
-        check(L.prs_xchg_open_peers(self._x, raw))
+        check(L.prs_xchg_open_peers(x, raw))
         self.dist.barrier(group=self.group)
+        return x
 
     def check_exchange(self) -> None:
         """Raises if any fused search timed out waiting for a peer (synchronises the device)."""
-        if self._x.value:
-            check(_lib.lib().prs_xchg_status(self._x))
+        for x in self._xs:
+            check(_lib.lib().prs_xchg_status(x))
 
     def __del__(self):
         try:
-            if getattr(self, "_x", None) is not None and self._x.value:
-                _lib.lib().prs_xchg_free(self._x)
-                self._x = ctypes.c_void_p()
+            for x in getattr(self, "_xs", []):
+                if x.value:
+                    _lib.lib().prs_xchg_free(x)
+            self._xs = []
         except Exception:
             pass
 
@@ -108,14 +116,16 @@ class ShardedFlatIndex:
     def search(self, q, k: int):
         """q: CUDA tensor [nq, d] replicated on every rank -> (D, I) CUDA tensors on every rank."""
         import torch
-        if self.world > 1 and self._x.value and int(q.shape[0]) <= self._cap[0] and int(q.shape[0]) * int(k) <= self._cap[1]:
+        if self.world > 1 and self._xs and int(q.shape[0]) <= self._cap[0] and int(q.shape[0]) * int(k) <= self._cap[1]:
+            x = self._xs[self._calls % len(self._xs)]
+            self._calls += 1
             from .flat import _torch_dtype_code
             q = q.contiguous()
             nq = int(q.shape[0])
             D = torch.empty((nq, k), dtype=torch.float32, device=q.device)
             I = torch.empty((nq, k), dtype=torch.int64, device=q.device)
             st = torch.cuda.current_stream(q.device).cuda_stream
-            check(_lib.lib().prs_index_search_sharded_device(self.local._h, self._x, ctypes.c_void_p(q.data_ptr()), _torch_dtype_code(q),
+            check(_lib.lib().prs_index_search_sharded_device(self.local._h, x, ctypes.c_void_p(q.data_ptr()), _torch_dtype_code(q),
                                                              nq, int(k), ctypes.c_void_p(D.data_ptr()), ctypes.c_void_p(I.data_ptr()),
                                                              ctypes.c_void_p(st)))
             return D, I
