@@ -51,7 +51,9 @@ struct UmmaParams {
     int* cand_cnt;          // [grid][nq_total]
     int tile_step;          // 1 = every tile; S > 1 = every S-th tile (threshold sampling pass of the wide-k path)
     int mode;               // 0: per-part sorted top-k lists (k <= 16), pruned by the cross-CTA bootstrap bound;
-                            // 1: collect every score >= tau[q];  2: like 0 but every part keeps its own full top-k (no bootstrap)
+                            // 1: collect every score >= tau[q];  2: best score of every visited tile -> gmax (threshold sampling)
+    float* gmax;            // mode 2: [nq_total][gmax_stride] best score per (query, sampled tile)
+    long long gmax_stride;
     const float* tau;       // mode 1: [nq_total] admission threshold per query (a lower bound of its k-th best)
     u64* coll;              // mode 1: [parts][nq_total][coll_cap] unsorted keys
     int* coll_cnt;          // mode 1: [parts][nq_total]
@@ -429,6 +431,24 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) flat_scan_umma_kernel(const U
                 if (lane == 0) mbar_arrive(&tmem_empty[b]);
                 continue;
             }
+            if (p.mode == 2) {
+                // threshold sampling: only the best score of this tile per query (branch free, no lists)
+                float mx = -INFINITY;
+#pragma unroll 1
+                for (int h = 0; h < NB; ++h) {
+                    load_half(v, b, h);
+                    if (h == NB - 1) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&tmem_empty[b]);
+                    }
+                    const int nv = nvalid - h * BLK_ROWS;
+#pragma unroll
+                    for (int j = 0; j < BLK_ROWS; ++j) mx = (j < nv) ? fmaxf(mx, __uint_as_float(v[j])) : mx;
+                }
+                if (qvalid) p.gmax[qglobal * p.gmax_stride + ti] = sanitize(mx);
+                continue;
+            }
             if (p.dbg & 1) { thr = INFINITY; boot_done = true; }
             else if (it == 0 && p.mode == 0) {
                 // bootstrap pass over the first tile (both halves): best score per query, then the bound
@@ -471,7 +491,7 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) flat_scan_umma_kernel(const U
             }
         }
         if (qvalid && collect) p.coll_cnt[(size_t)part * p.nq_total + qglobal] = ccount < p.coll_cap ? ccount : p.coll_cap;
-        if (qvalid && !collect) {
+        if (qvalid && p.mode == 0) {
             const size_t o = (size_t)part * p.nq_total + p.q0 + crank * UMMA_M + qi;
             int n = 0;
 #pragma unroll
@@ -533,9 +553,9 @@ __global__ void __launch_bounds__(128) prep_queries_kernel(const TQ* __restrict_
 
 // ---------------- host side ----------------
 struct UmmaState {
-    DevBuf qlow, boot, tau, coll, coll_cnt;
+    DevBuf qlow, boot, tau, gmax, coll, coll_cnt;
     void invalidate() {}
-    void release() { qlow.release(); boot.release(); tau.release(); coll.release(); coll_cnt.release(); }
+    void release() { qlow.release(); boot.release(); tau.release(); gmax.release(); coll.release(); coll_cnt.release(); }
 };
 
 static inline bool umma_eligible(int storage, int d, int pitch, long long nq, int k) {
@@ -659,7 +679,8 @@ static inline int umma_prep(UmmaState& st, const UmmaPlan& pl, const void* q, in
 // all passes of one scan over the corpus (mode 0: sorted top-k lists of k <= 16; mode 1: collect >= tau)
 static inline int umma_scan(UmmaState& st, const UmmaPlan& pl, const void* x, const float* xnorm, long long n, int pitch, int storage,
                             int metric, long long nq, int k, int tile_step, int mode, u64* cand, int* cand_cnt, const float* tau,
-                            u64* coll, int* coll_cnt, int coll_cap, int* overflow, cudaStream_t stream, ScanTimer* timer) {
+                            u64* coll, int* coll_cnt, int coll_cap, int* overflow, cudaStream_t stream, ScanTimer* timer,
+                            float* gmax = nullptr, long long gmax_stride = 0) {
     for (long long q0 = 0; q0 < nq; q0 += pl.qblock) {
         UmmaParams p;
         p.x = (const unsigned char*)x;
@@ -671,6 +692,7 @@ static inline int umma_scan(UmmaState& st, const UmmaPlan& pl, const void* x, co
         p.nq_total = (int)nq; p.q0 = (int)q0;
         p.cand = cand; p.cand_cnt = cand_cnt;
         p.tile_step = tile_step; p.mode = mode; p.tau = tau; p.coll = coll; p.coll_cnt = coll_cnt; p.coll_cap = coll_cap; p.overflow = overflow;
+        p.gmax = gmax; p.gmax_stride = gmax_stride;
         p.boot = (uint32_t*)st.boot.p + (size_t)(q0 / UMMA_M) * pl.boot_words;
         p.boot_stride = pl.boot_words;
         if (timer) timer->begin(stream);
@@ -703,9 +725,10 @@ static inline int search_umma(UmmaState& st, const void* x, const float* xnorm, 
 
 // ---------------------------------------------------------------------------------------------------
 // Wide k (16 < k <= 1024): sample -> threshold -> collect -> select.
-//   1. the scan kernel visits every S-th tile and leaves, per part, that part's own top-L list of the
-//      sample (L = 4 / 8 / 16; no cross-CTA bootstrap here -- its bound is only valid for k <= L);
-//   2. tau[q] = k-th largest key of their union (k distinct rows: a lower bound of the true k-th best);
+//   1. the scan kernel visits every S-th tile (S <= 16) and records only the BEST score of each visited
+//      tile per query (branch free: no lists, no insertions);
+//   2. tau[q] = k-th largest of those M tile maxima -- scores of k distinct rows, hence a lower bound of
+//      the true k-th best (with few qualifying rows per tile this is as tight as the sample's own k-th);
 //   3. the full scan runs in collect mode: every score >= tau[q] is appended, unsorted, to the
 //      (part, query) slice of a collection buffer -- about k * S candidates per query in total;
 //   4. one CTA per query selects the k best of its slices into a single sorted list (then the
@@ -716,7 +739,7 @@ static inline int search_umma(UmmaState& st, const void* x, const float* xnorm, 
 constexpr int UMMA_WIDE_MAX_K = PRS_MAX_K;
 static inline bool umma_wide_eligible(int storage, int pitch, long long nq, int k, long long n) {
     return (storage == PRS_F16 || storage == PRS_BF16) && pitch <= 768 && k > UMMA_MAX_K && k <= UMMA_WIDE_MAX_K && nq >= 1 &&
-           n >= 32ll * k && n >= 16384;
+           n >= 256ll * k && n >= 16384;                      // >= 2k tiles of 128 rows to sample a threshold from
 }
 
 static inline int search_umma_wide(UmmaState& st, const void* x, const float* xnorm, long long n, int d, int pitch, int storage,
@@ -726,40 +749,35 @@ static inline int search_umma_wide(UmmaState& st, const void* x, const float* xn
     UmmaPlan pl;
     int rc;
     *overflowed = false;
-    // one CTA per part (no clusters): the threshold needs many independent per-part lists
+    // no clusters: 148 independent parts keep the collection slices short
     if ((rc = umma_plan(n, pitch, nq, sm_count, pl, true))) return rc;
     const int parts = pl.n_clusters;
-    // sampling step: every part keeps >= 2 sampled tiles and the sample holds >= 32 k rows
-    long long S = pl.n_tiles / (2ll * parts);
-    const long long rows_per_tile = (long long)pl.NB * BLK_ROWS;
-    S = std::min<long long>(S, (pl.n_tiles * rows_per_tile) / (32ll * k));
-    S = std::max<long long>(1, std::min<long long>(16, S));
-    const long long sampled = (pl.n_tiles + S - 1) / S;
-    const double ratio = (double)pl.n_tiles / (double)sampled;
-    const double expect = (double)k * ratio / parts;                 // survivors per (part, query)
+    // sampling step S: the sample must hold M >= 2k tiles (each contributes its best score = one
+    // distinct row); at most every 16th tile so that the collecting pass sees <= ~16 k candidates per query
+    long long S = std::min<long long>(16, pl.n_tiles / (2ll * k));
+    if (S < 1) { *overflowed = true; return 0; }                     // corpus too small for a sampled bound
+    const long long M = (pl.n_tiles + S - 1) / S;                    // sampled tiles
+    const double expect = (double)k * (double)S / parts;             // survivors per (part, query)
     int cap = next_pow2((int)std::min<double>(1 << 20, std::max<double>(64.0, 6.0 * expect + 32.0)));
     const size_t coll_bytes = (size_t)parts * nq * cap * 8;
     if (coll_bytes > (4ull << 30)) { *overflowed = true; return 0; }  // would not fit: let the caller use the CUDA-core scan
-    int L = 4;                                                        // per-part list length of the sampling pass
-    while (L < UMMA_MAX_K && (long long)parts * L < 3ll * k) L <<= 1;  // parts * L >= ~3k candidates for the threshold
-    if ((long long)parts * L < 2ll * k) { *overflowed = true; return 0; }   // too few parts for a useful bound
     if ((rc = umma_prep(st, pl, q, qdtype, nq, d, pitch, storage, qnorm, stream, timer_prep))) return rc;
-    if ((rc = cand.ensure(std::max<size_t>((size_t)parts * nq * L * 8, (size_t)nq * k * 8)))) return rc;
-    if ((rc = cand_cnt.ensure((size_t)parts * nq * 4))) return rc;
+    if ((rc = cand.ensure((size_t)nq * k * 8))) return rc;
     if ((rc = st.tau.ensure((size_t)nq * 4 + 16))) return rc;
+    if ((rc = st.gmax.ensure((size_t)nq * M * 4))) return rc;
     if ((rc = st.coll.ensure(coll_bytes))) return rc;
     if ((rc = st.coll_cnt.ensure((size_t)parts * nq * 4))) return rc;
     int* overflow = (int*)((unsigned char*)st.tau.p + (size_t)nq * 4 + 8 - (((size_t)nq * 4) & 7));
     PRS_CUDA(cudaMemsetAsync(overflow, 0, 4, stream));
-    // 1. sampling pass (top-16 lists)
-    if ((rc = umma_scan(st, pl, x, xnorm, n, pitch, storage, metric, nq, L, (int)S, 2, (u64*)cand.p, (int*)cand_cnt.p, nullptr, nullptr, nullptr, 0,
-                        nullptr, stream, nullptr))) return rc;
-    // 2. thresholds
+    // 1. sampling pass: best score of every S-th tile
+    if ((rc = umma_scan(st, pl, x, xnorm, n, pitch, storage, metric, nq, k, (int)S, 2, nullptr, nullptr, nullptr, nullptr, nullptr, 0,
+                        nullptr, stream, nullptr, (float*)st.gmax.p, M))) return rc;
+    // 2. thresholds: k-th largest of the M tile maxima
     {
-        const int sortn = next_pow2((int)std::max<long long>(k + MERGE_THREADS, std::min<long long>((long long)parts * L, MERGE_ONESHOT)));
-        const size_t smem = (size_t)sortn * 8 + MERGE_THREADS * 8 + 16;
-        PRS_CUDA(cudaFuncSetAttribute(tau_from_lists_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        tau_from_lists_kernel<<<(unsigned)nq, MERGE_THREADS, smem, stream>>>((const u64*)cand.p, parts, (int)nq, L, k, sortn, (float*)st.tau.p);
+        const int sortn = next_pow2(k + MERGE_THREADS);
+        const size_t smem = (size_t)sortn * 8 + 16;
+        PRS_CUDA(cudaFuncSetAttribute(tau_from_maxima_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        tau_from_maxima_kernel<<<(unsigned)nq, MERGE_THREADS, smem, stream>>>((const float*)st.gmax.p, M, k, sortn, (float*)st.tau.p);
         PRS_LAUNCH_CHECK();
     }
     // 3. collecting pass (the dominant kernel: timed)
@@ -784,8 +802,8 @@ static inline int search_umma_wide(UmmaState& st, const void* x, const float* xn
         cudaMemcpy(hc.data(), st.coll_cnt.p, (size_t)parts * nq * 4, cudaMemcpyDeviceToHost);
         long long tot0 = 0; int mx = 0;
         for (int p2 = 0; p2 < parts; ++p2) { tot0 += hc[(size_t)p2 * nq]; mx = std::max(mx, hc[(size_t)p2 * nq]); }
-        fprintf(stderr, "[wide] n=%lld k=%d parts=%d S=%lld cap=%d tau[0]=%g tau[last]=%g q0: total=%lld max=%d overflow=%d\n",
-                n, k, parts, S, cap, ht[0], ht[(size_t)nq - 1], tot0, mx, h_over);
+        fprintf(stderr, "[wide] n=%lld k=%d parts=%d S=%lld M=%lld cap=%d tau[0]=%g tau[last]=%g q0: total=%lld max=%d overflow=%d\n",
+                n, k, parts, S, M, cap, ht[0], ht[(size_t)nq - 1], tot0, mx, h_over);
     }
     *overflowed = h_over != 0;
     return 0;

@@ -96,22 +96,19 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_cand_kernel(
 
 // ---------------------------------------------------------------------------------------------
 // Wide-k path (16 < k <= 1024 on the tcgen05 scan).
-// tau: the sampling pass left, per part, a sorted top-L list of each query over a SAMPLE of the
-// rows; the k-th largest key of their union belongs to k distinct rows, so its score is a lower
-// bound of the query's true k-th best -- the admission threshold of the collecting pass.
+// tau: the sampling pass left the best score of every sampled tile per query (gmax[q][M]); the
+// k-th largest of them belongs to k distinct rows, so it is a lower bound of the query's true
+// k-th best -- the admission threshold of the collecting pass.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(MERGE_THREADS) tau_from_lists_kernel(const u64* __restrict__ cand, int parts, int nq, int L, int k,
-                                                                       int sortn, float* __restrict__ tau) {
+__global__ void __launch_bounds__(MERGE_THREADS) tau_from_maxima_kernel(const float* __restrict__ gmax, long long M, int k, int sortn,
+                                                                        float* __restrict__ tau) {
     extern __shared__ __align__(16) unsigned char msm[];
     u64* buf = reinterpret_cast<u64*>(msm);
-    u64* heads = buf + sortn;
-    int* s_n = reinterpret_cast<int*>(heads + MERGE_THREADS);
+    int* s_n = reinterpret_cast<int*>(buf + sortn);
     const int q = blockIdx.x, tid = threadIdx.x;
-    auto fetch = [&](long long i) -> u64 {
-        const int part = (int)((unsigned)i / (unsigned)L), j = (int)i - part * L;
-        return __ldcg(cand + ((size_t)part * nq + q) * L + j);
-    };
-    const int n = block_topk_lists(fetch, parts, L, k, buf, sortn, heads, s_n, tid);
+    const float* row = gmax + (size_t)q * M;
+    auto fetch = [&](long long i) -> u64 { return ((u64)f2ord(__ldcg(row + i)) << 32) | (u64)(uint32_t)i; };
+    const int n = block_topk_stream(fetch, M, k, buf, sortn, s_n, tid, MERGE_THREADS, 1);
     if (tid == 0) tau[q] = (n >= k) ? key_score(buf[k - 1]) : -INFINITY;
 }
 

@@ -225,7 +225,7 @@ def test_tcgen05_clusters_and_tile_shapes_vs_oracle(P, n, d, nq, k, metric, stor
     (200000, 768, 64, 100, O.METRIC_IP, "fp16"),
     (200000, 384, 1, 17, O.METRIC_L2, "fp16"),
     (100000, 512, 300, 100, O.METRIC_L2, "bf16"),     # several 128-query passes
-    (70000, 384, 5, 1024, O.METRIC_IP, "fp16"),       # k at the API maximum
+    (300000, 384, 5, 1024, O.METRIC_IP, "fp16"),      # k at the API maximum
     (40000, 768, 130, 33, O.METRIC_L2, "fp16"),
 ])
 def test_tcgen05_wide_k_vs_oracle(P, n, d, nq, k, metric, storage):

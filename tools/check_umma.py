@@ -47,7 +47,7 @@ if __name__ == "__main__":
     tot += run(200000, 768, 64, 100, O.METRIC_IP, "fp16")
     tot += run(200000, 384, 1, 17, O.METRIC_L2, "fp16")
     tot += run(100000, 512, 300, 100, O.METRIC_L2, "bf16")
-    tot += run(70000, 384, 5, 1024, O.METRIC_IP, "fp16")
+    tot += run(300000, 384, 5, 1024, O.METRIC_IP, "fp16")
     tot += run(40000, 768, 130, 33, O.METRIC_L2, "fp16")
     print("TOTAL BAD", tot)
     sys.exit(1 if tot else 0)
