@@ -24,6 +24,7 @@
 // warps 2..5 = epilogue (TMEM lane quarter = warp % 4).
 #pragma once
 #include <algorithm>
+#include <type_traits>
 #include <vector>
 
 #include "common.cuh"
@@ -273,18 +274,31 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) flat_scan_umma_kernel(const U
         float* wnorm = snorm + (warp - 2) * TILE_N;
         const uint32_t lane_addr = tmem_base + ((uint32_t)(qd * 32) << 16) + D_OFF;
         {
-            // stage this thread's query row into TMEM: lane m, columns [0, pitch/2)
+            // stage this thread's query row into TMEM: lane m, columns [0, pitch/2).  The MMA warp waits
+            // for this, so the row is fetched with 24 independent 16-byte loads in flight per round
+            // (three TMEM stores per round) instead of 8; empty slots store zeros without reading.
             const uint4* qrow = reinterpret_cast<const uint4*>(p.qlow + ((size_t)crank * UMMA_M + m) * p.pitch);
             const uint32_t a_addr = tmem_base + ((uint32_t)(qd * 32) << 16);
-            for (int c0 = 0; c0 < (p.pitch >> 1); c0 += 32) {
-                uint32_t v[32];
+            const int ncol = p.pitch >> 1;                     // 32-bit TMEM columns of the A operand
+            auto stage = [&](auto NG, int c0) {                 // NG x 32 columns starting at c0
+                constexpr int G_ = decltype(NG)::value;
+                uint32_t v[G_][32];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const uint4 t4 = __ldg(&qrow[(c0 >> 2) + i]);
-                    v[4 * i] = t4.x; v[4 * i + 1] = t4.y; v[4 * i + 2] = t4.z; v[4 * i + 3] = t4.w;
+                for (int g = 0; g < G_; ++g) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        uint4 t4 = make_uint4(0u, 0u, 0u, 0u);
+                        if (qvalid) t4 = __ldg(&qrow[((c0 + g * 32) >> 2) + i]);
+                        v[g][4 * i] = t4.x; v[g][4 * i + 1] = t4.y; v[g][4 * i + 2] = t4.z; v[g][4 * i + 3] = t4.w;
+                    }
                 }
-                tmem_st32(a_addr + (uint32_t)c0, v);
-            }
+#pragma unroll
+                for (int g = 0; g < G_; ++g) tmem_st32(a_addr + (uint32_t)(c0 + g * 32), v[g]);
+            };
+            int c0 = 0;
+            for (; c0 + 96 <= ncol; c0 += 96) stage(std::integral_constant<int, 3>{}, c0);
+            if (ncol - c0 == 64) stage(std::integral_constant<int, 2>{}, c0);
+            else if (ncol - c0 == 32) stage(std::integral_constant<int, 1>{}, c0);
             tmem_st_wait();
             tc_fence_before();
             named_bar_sync(2, 160);
