@@ -139,6 +139,24 @@ def host_threads():
         return os.cpu_count() or 1
 
 
+def use_all_host_threads():
+    """The CPU legs use every host core this process may run on, whatever OMP_NUM_THREADS says
+    (torchrun exports OMP_NUM_THREADS=1 to its workers).  Returns the BLAS thread count in effect."""
+    n = host_threads()
+    try:
+        import torch
+        torch.set_num_threads(n)
+    except Exception:
+        pass
+    try:
+        from threadpoolctl import threadpool_info, threadpool_limits
+        threadpool_limits(limits=n)
+        got = [int(i.get("num_threads", 1)) for i in threadpool_info() if i.get("user_api") == "blas"]
+        return max(got) if got else n
+    except Exception:
+        return n
+
+
 # ------------------------------------------------------------------------------------------------
 # CPU leg: the oracle port (faiss IndexFlat restated: sgemm blocks + threshold/heap), all host cores
 # ------------------------------------------------------------------------------------------------
@@ -164,6 +182,7 @@ def run_reference(a):
         return
     import torch
     from oracle import oracle as O
+    cores = use_all_host_threads()
     metric_code = O.METRIC_IP if a.metric == "ip" else O.METRIC_L2
     g = torch.Generator().manual_seed(1234)
     x = torch.randn(a.rows, a.d, generator=g)
@@ -182,7 +201,6 @@ def run_reference(a):
         O.flat_search_np_threshold(x32, Q[a.warmup + s], a.k, metric_code)
     dt = time.perf_counter() - t0
     qps = a.steps * a.batch / dt
-    cores = host_threads()
     sample = f"full workload per step: {a.batch} queries x {a.rows} x {a.d} fp32 rows, k={a.k}"
     print(json.dumps({
         "impl": "reference", "metric": METRIC_NAME, "value": qps, "unit": "queries/s", "n_gpus": a.gpus,
@@ -481,11 +499,12 @@ def run_b200(a):
     # ---- CPU baseline beside it (rank 0, N = 1): oracle port on the same corpus and queries ----
     if world == 1 and rank == 0 and not a.no_cpu_baseline:
         from oracle import oracle as O
+        blas_threads = use_all_host_threads()
         x32 = idx.reconstruct_n(0, n_local)                       # the stored (rounded) rows, as fp32
         qlast = Qh[nbatches - 1].numpy()
         times, (Dc, Ic) = cpu_search_timed(x32, qlast, a.k, O.METRIC_IP if a.metric == "ip" else O.METRIC_L2, budget_s=12.0)
         cpu_qps = a.batch / float(np.median(times))
-        out["cpu_baseline"] = {"value": cpu_qps, "unit": "queries/s", "cores": host_threads(), "kind": "port",
+        out["cpu_baseline"] = {"value": cpu_qps, "unit": "queries/s", "cores": blas_threads, "kind": "port",
                                "sample": f"{len(times)} x (1 batch of {a.batch} queries over all {n_local} rows, fp32), median",
                                "ms_per_batch": float(np.median(times)) * 1e3,
                                "note": "faiss-cpu wheel absent: numpy/OpenBLAS restatement of faiss IndexFlat.search"}

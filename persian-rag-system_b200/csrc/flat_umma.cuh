@@ -251,7 +251,10 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) flat_scan_umma_kernel(const U
                         for (int k4 = 0; k4 < 4; ++k4) {
                             const uint64_t bdesc = umma_desc_sw128(sb + (uint32_t)kbi * UMMA_KB_STAGE_BYTES + (uint32_t)k4 * 32u);
                             const uint32_t a_tmem = tmem_base + (uint32_t)(kb * 32 + k4 * 8);
-                            umma_ts_f16(d_tmem, a_tmem, bdesc, idesc, (kb | k4) != 0 ? 1u : 0u);
+                            // dbg 128 (timing experiment, wrong results): odd MMAs accumulate into the OTHER buffer,
+                            // i.e. two independent accumulation chains instead of one
+                            const uint32_t d_use = ((p.dbg & 128) && (k4 & 1)) ? (tmem_base + D_OFF + (uint32_t)((b ^ 1) * TILE_N)) : d_tmem;
+                            umma_ts_f16(d_use, a_tmem, bdesc, idesc, (kb | k4) != 0 ? 1u : 0u);
                         }
                     }
                     if (CL == 1) umma_commit(&empty[s]);       // frees the smem stage when these MMAs retire
