@@ -80,9 +80,11 @@ def run_sparse(a):
     indptr, indices, values, cdf, df = gen_sparse(a.docs, a.terms, 7, dev)
     nnz = int(indices.shape[0])
     t_gen = time.time() - t0
+    print(f"[sparse] generated nnz={nnz} in {t_gen:.1f}s", file=sys.stderr, flush=True)
     t0 = time.time()
     idx = P.SparseIndex(indptr, indices, values, a.terms)
     t_build = time.time() - t0
+    print(f"[sparse] index built in {t_build:.1f}s", file=sys.stderr, flush=True)
     # queries: 1 + Poisson(6) Zipf tokens (stop-word-like heads included, the reference removes none)
     rng = np.random.default_rng(11)
     qlen = 1 + rng.poisson(6, size=a.queries)
@@ -93,12 +95,14 @@ def run_sparse(a):
     q_w = np.ones(q_terms.shape[0], np.float64)
     torch.cuda.synchronize()
     idx.search(q_indptr[:9], q_terms[: q_indptr[8]], q_w[: q_indptr[8]], a.k)             # warm-up
+    print("[sparse] warm-up search done", file=sys.stderr, flush=True)
     reps = []
     for _ in range(a.reps):
         t0 = time.perf_counter()
         S, I = idx.search(q_indptr, q_terms, q_w, a.k)
         reps.append(time.perf_counter() - t0)
     t_gpu = float(np.median(reps))
+    print(f"[sparse] gpu searches done {t_gpu*1e3:.2f} ms", file=sys.stderr, flush=True)
     postings = idx.last_postings
     peak, src = hbm_peak()
     gbs = 8.0 * postings / t_gpu / 1e9
