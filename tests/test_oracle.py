@@ -146,3 +146,20 @@ def test_tie_rules():
     O.check_topk_against_scores([3, 1, 2, 4], [1, 1, 0, 0], s, 4, True, rtol=1e-6)
     with pytest.raises(AssertionError):
         O.check_topk_against_scores([3, 0, 2, 4], [1, 0, 0, 0], s, 4, True, rtol=1e-6)
+
+
+def test_threshold_restatement_equals_blocked_numpy_restatement():
+    """bench.py's CPU baseline (sgemm blocks + threshold select, faiss's nq >= 20 organisation) must
+    return exactly what the plain blocked restatement returns, duplicates and k > n included."""
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal((30000, 48)).astype(np.float32)
+    x[2000:2100] = x[:100]                                   # exact duplicates -> ties on id
+    q = rng.standard_normal((21, 48)).astype(np.float32)
+    q[:4] = x[:4]
+    for metric in (O.METRIC_L2, O.METRIC_IP):
+        for k in (1, 10, 100):
+            Da, Ia = O.flat_search_np(x, q, k, metric)
+            Db, Ib = O.flat_search_np_threshold(x, q, k, metric, block=4096)
+            assert np.array_equal(Ia, Ib) and np.array_equal(Da, Db)
+    Da, Ia = O.flat_search_np_threshold(x[:7], q, 10, O.METRIC_L2)
+    assert (Ia[:, 7:] == -1).all() and (Ia[:, :7] >= 0).all()
