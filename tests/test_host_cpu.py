@@ -194,3 +194,17 @@ def test_shard_bounds_and_merge_rule(P):
         Ip.append(np.where(I >= 0, I + lo, -1))
     D, I = merge_topk_host_lists(np.stack(Dp), np.stack(Ip), largest=False)
     assert np.array_equal(I, Iw) and np.array_equal(D, Dw)
+
+
+def test_t64_corpus_layout_is_a_swizzled_bijection(tmp_path):
+    """The HBM layout of 16-bit corpora (csrc/common.cuh::t64_offset) checked on the host: bijective per
+    64-row block, k-block-major, chunk ^ (row & 7) swizzle -- the image tcgen05's SWIZZLE_128B descriptor expects."""
+    import shutil
+    import subprocess
+    if not shutil.which("nvcc"):
+        pytest.skip("nvcc not on PATH")
+    src = os.path.join(ROOT, "tests", "native", "t64_layout_check.cu")
+    exe = str(tmp_path / "t64_layout_check")
+    subprocess.run(["nvcc", "-std=c++17", "-O1", "-o", exe, src], check=True, capture_output=True)
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.strip() == "ok", out.stdout + out.stderr
