@@ -5,14 +5,15 @@
 // src/create_embeddings.py:97-101 (sentence-transformers Pooling(mean) then Normalize):
 //   out[b,:] = sum_t hidden[b,t,:] * mask[b,t] / max(sum_t mask[b,t], 1e-9)
 //   if normalize: out[b,:] /= max(||out[b,:]||_2, 1e-12)
-// Work split: a thread-block CLUSTER per sequence, one CTA per 128-column chunk of H (H = 768 -> 6
-// CTAs, 384 -> 3), so B = 32 sequences already fill the machine.  Inside a CTA each of the 8 warps
-// takes every 8th token and a lane owns 4 consecutive columns (8- or 16-byte loads, 8 rows in
+// Work split: a thread-block CLUSTER per sequence, one CTA per chunk of H (128 fp32 or 256 16-bit
+// columns: H = 768 fp16 -> 3 CTAs, fp32 -> 6), so B = 32 sequences already fill the machine.  Inside
+// a CTA each of the 8 warps takes every 8th token and a lane moves 16 bytes per row (8 rows in
 // flight), partial sums meet in shared memory; the squared norm is reduced ACROSS the cluster's
 // CTAs through distributed shared memory (no workspace, no second kernel, no atomics).  [T, H] is
 // streamed from HBM exactly once (bytes = B*T*H*sizeof(h) + B*T*8 + B*H*4), fp32 accumulate.  The
 // result stays on the device so it can be handed straight to prs_index_search_device.
-// Shapes the cluster path does not cover (H % 4 != 0 or H > 1024) use the one-CTA-per-sequence kernel.
+// Shapes the cluster path does not cover (H not a multiple of the lane width, or more than 8 chunks)
+// use the one-CTA-per-sequence kernel.
 #include <cooperative_groups.h>
 
 #include "common.cuh"
@@ -85,40 +86,48 @@ __global__ void __launch_bounds__(POOL_THREADS) pool_norm_kernel(const T* __rest
 }
 
 // ---- cluster kernel: grid (nchunks, B), cluster (nchunks, 1, 1), 256 threads ----
-constexpr int POOL_CHUNK = 128;       // columns per CTA
-constexpr int POOL_CPL = 4;           // columns per lane
+// every lane moves 16 bytes per row: 4 fp32 columns or 8 16-bit columns; a CTA owns 32 lanes' worth
 template <typename T> struct PoolVec;
 template <> struct PoolVec<float> {
+    static constexpr int CPL = 4;
     __device__ static __forceinline__ void ld(const float* p, float (&f)[4]) { const float4 v = __ldg(reinterpret_cast<const float4*>(p)); f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w; }
 };
 template <> struct PoolVec<__half> {
-    __device__ static __forceinline__ void ld(const __half* p, float (&f)[4]) {
-        const uint2 v = __ldg(reinterpret_cast<const uint2*>(p));
-        const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&v.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&v.y));
-        f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y;
+    static constexpr int CPL = 8;
+    __device__ static __forceinline__ void ld(const __half* p, float (&f)[8]) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { const float2 t = __half22float2(*reinterpret_cast<const __half2*>(&w[i])); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
     }
 };
 template <> struct PoolVec<__nv_bfloat16> {
-    __device__ static __forceinline__ void ld(const __nv_bfloat16* p, float (&f)[4]) {
-        const uint2 v = __ldg(reinterpret_cast<const uint2*>(p));
-        f[0] = __uint_as_float(v.x << 16); f[1] = __uint_as_float(v.x & 0xFFFF0000u);
-        f[2] = __uint_as_float(v.y << 16); f[3] = __uint_as_float(v.y & 0xFFFF0000u);
+    static constexpr int CPL = 8;
+    __device__ static __forceinline__ void ld(const __nv_bfloat16* p, float (&f)[8]) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { f[2 * i] = __uint_as_float(w[i] << 16); f[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u); }
     }
 };
 
 template <typename T>
 __global__ void __launch_bounds__(POOL_THREADS) pool_norm_cluster_kernel(const T* __restrict__ hidden, const long long* __restrict__ mask,
                                                                          int T_len, int H, int normalize, float* __restrict__ out) {
+    constexpr int POOL_CPL = PoolVec<T>::CPL;            // columns per lane
+    constexpr int POOL_CHUNK = 32 * POOL_CPL;            // columns per CTA (128 fp32 / 256 16-bit)
     __shared__ float s_acc[POOL_THREADS / 32][POOL_CHUNK];
     __shared__ float s_cnt[POOL_THREADS / 32];
     __shared__ float s_sq;                       // this CTA's share of the squared norm (read by the cluster)
     cg::cluster_group cluster = cg::this_cluster();
     const int chunk = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int col = chunk * POOL_CHUNK + lane * POOL_CPL;
-    const bool live = col < H;                   // H % 4 == 0: a lane is entirely inside or outside
+    const bool live = col < H;                   // H % CPL == 0: a lane is entirely inside or outside
     const T* hb = hidden + (size_t)b * T_len * H + col;
     const long long* mb = mask + (size_t)b * T_len;
-    float acc[POOL_CPL] = {0.f, 0.f, 0.f, 0.f};
+    float acc[POOL_CPL];
+#pragma unroll
+    for (int c = 0; c < POOL_CPL; ++c) acc[c] = 0.f;
     float cnt = 0.f;
     constexpr int NW = POOL_THREADS / 32, UNR = 8;     // rows in flight per lane (16 was measured slower for 16-bit: registers)
     for (int t0 = warp; t0 < T_len; t0 += NW * UNR) {
@@ -133,7 +142,10 @@ __global__ void __launch_bounds__(POOL_THREADS) pool_norm_cluster_kernel(const T
         for (int u = 0; u < UNR; ++u) {
             const int t = t0 + u * NW;
             if (live && t < T_len && m[u] != 0.f) PoolVec<T>::ld(hb + (size_t)t * H, x[u]);
-            else { x[u][0] = x[u][1] = x[u][2] = x[u][3] = 0.f; }
+            else {
+#pragma unroll
+                for (int c = 0; c < POOL_CPL; ++c) x[u][c] = 0.f;
+            }
         }
 #pragma unroll
         for (int u = 0; u < UNR; ++u) {
@@ -178,6 +190,7 @@ using namespace prs;
 
 template <typename T>
 static cudaError_t launch_pool_cluster(const void* hidden, const int64_t* mask, int B, int T_len, int H, int normalize, float* out, cudaStream_t st) {
+    constexpr int POOL_CHUNK = 32 * PoolVec<T>::CPL;
     const int nchunks = (H + POOL_CHUNK - 1) / POOL_CHUNK;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)nchunks, (unsigned)B, 1);
@@ -200,7 +213,8 @@ extern "C" int prs_pool_norm(const void* hidden, int dtype, const int64_t* mask,
     if (!g.ok) { set_error("pool_norm: no CUDA device %d", device); return PRS_ECUDA; }
     cudaStream_t st = (cudaStream_t)stream;
     if (B > 65535) { set_error("pool_norm: B=%d > 65535 sequences per call", B); return PRS_EINVAL; }
-    if (H % POOL_CPL == 0 && H <= 8 * POOL_CHUNK && dtype >= PRS_F32 && dtype <= PRS_BF16) {
+    const int cpl = dtype == PRS_F32 ? 4 : 8;      // 16 bytes per lane and row
+    if (H % cpl == 0 && H <= 8 * 32 * cpl && dtype >= PRS_F32 && dtype <= PRS_BF16) {
         cudaError_t e = dtype == PRS_F32 ? launch_pool_cluster<float>(hidden, mask, B, T, H, normalize, out, st)
                         : dtype == PRS_F16 ? launch_pool_cluster<__half>(hidden, mask, B, T, H, normalize, out, st)
                                            : launch_pool_cluster<__nv_bfloat16>(hidden, mask, B, T, H, normalize, out, st);
