@@ -9,6 +9,7 @@ CPU compute path in this package.
 from ._lib import (BF16, F16, F32, F64, MAX_K, METRIC_INNER_PRODUCT, METRIC_L2, PrsError, build, lib)
 METRIC_IP = METRIC_INNER_PRODUCT      # short alias (faiss spells it METRIC_INNER_PRODUCT)
 from .flat import FlatIndex, IndexFlatIP, IndexFlatL2, read_index, write_index
+from .index_build import create_model_embeddings, index_path_for, setup_faiss_index
 from .sparse import BM25Index, SparseIndex, TfidfIndex
 from .pooling import mean_pool_normalize
 from .retrieval import MultiModelRetrieval, RetrievalSystem
@@ -17,6 +18,6 @@ from .sharded import ShardedFlatIndex
 __all__ = [
     "FlatIndex", "IndexFlatL2", "IndexFlatIP", "read_index", "write_index",
     "SparseIndex", "BM25Index", "TfidfIndex", "mean_pool_normalize",
-    "RetrievalSystem", "MultiModelRetrieval", "ShardedFlatIndex",
+    "RetrievalSystem", "MultiModelRetrieval", "ShardedFlatIndex", "create_model_embeddings", "setup_faiss_index", "index_path_for",
     "METRIC_L2", "METRIC_INNER_PRODUCT", "METRIC_IP", "F32", "F16", "BF16", "F64", "MAX_K", "PrsError", "build", "lib",
 ]

@@ -208,3 +208,18 @@ def test_t64_corpus_layout_is_a_swizzled_bijection(tmp_path):
     subprocess.run(["nvcc", "-std=c++17", "-O1", "-o", exe, src], check=True, capture_output=True)
     out = subprocess.run([exe], capture_output=True, text=True)
     assert out.returncode == 0 and out.stdout.strip() == "ok", out.stdout + out.stderr
+
+
+# ------------------------------------------------------------------ index build mirror (§8 a-2), host logic
+def test_index_build_naming_skip_and_missing_file(P, tmp_path, capsys):
+    """create_model_embeddings keeps the reference's contract without touching the GPU: file naming
+    (src/create_embeddings.py:62), skip-if-exists -> True (:64-66), missing chunk file -> False (:68-70)."""
+    d = str(tmp_path / "faiss")
+    assert P.index_path_for("models/e5-base-ft", "sentence") == "results/faiss/e5-base-ft_drugs_sentence_chunks.index"
+    path = P.index_path_for("models/e5-base-ft", "word", d)
+    os.makedirs(d)
+    open(path, "wb").write(b"already here")
+    assert P.create_model_embeddings("models/e5-base-ft", "no_such_chunks.csv", "word", encoder=object(), faiss_dir=d) is True
+    assert open(path, "rb").read() == b"already here"                      # untouched
+    assert P.create_model_embeddings("models/e5-base-ft", "no_such_chunks.csv", "sentence", encoder=object(), faiss_dir=d) is False
+    assert "not found" in capsys.readouterr().out

@@ -179,3 +179,28 @@ def test_sharded_equals_unsharded(P, G, metric):
     assert np.array_equal(I.cpu().numpy(), Iw) and np.array_equal(D.cpu().numpy(), Dw)
     Dr, Ir = O.flat_search_c(x, q, k, metric, form=1)
     assert np.array_equal(Iw, Ir)
+
+
+# ------------------------------------------------------------------ index build mirror (§8 a-2)
+def test_create_model_embeddings_writes_the_faiss_file_the_reference_would(P, world, tmp_path, gold_dir, golden_indices):
+    """encode in batches of 32 -> IndexFlatL2.add -> write_index: the file must equal, byte for byte,
+    what faiss writes for the same float32 rows (oracle writer pinned on the reference's shipped files)."""
+    import pandas as pd
+    name = "drugs_sentence_chunks.index"
+    x, _ = golden_indices[name]
+    texts = [f"chunk {i}" for i in range(x.shape[0])]
+    csv = tmp_path / "chunks.csv"
+    pd.DataFrame({"id": [f"sentence_chunk_{i}" for i in range(len(texts))], "text": texts}).to_csv(csv, index=False)
+    enc = FakeEncoder({t: x[i] for i, t in enumerate(texts)}, x.shape[1])
+    out_dir = str(tmp_path / "faiss")
+    assert P.create_model_embeddings("models/distiluse-ft", str(csv), "sentence", encoder=enc, faiss_dir=out_dir) is True
+    path = P.index_path_for("models/distiluse-ft", "sentence", out_dir)
+    want = tmp_path / "want.index"
+    O.write_faiss_flat(str(want), x, O.METRIC_L2)
+    assert open(path, "rb").read() == open(want, "rb").read() == open(os.path.join(gold_dir, "indices", name), "rb").read()
+    # second call: skip-if-exists
+    assert P.create_model_embeddings("models/distiluse-ft", str(csv), "sentence", encoder=None, faiss_dir=out_dir) is True
+    # setup_faiss_index: same rows, exact L2, searchable at once; the IVF branch is replaced by the exact scan
+    idx = P.setup_faiss_index(x, index_type="ivf")
+    D, I = idx.search(x[:5], 1)
+    assert I[:, 0].tolist() == [0, 1, 2, 3, 4] and np.allclose(D[:, 0], 0.0, atol=1e-6)
