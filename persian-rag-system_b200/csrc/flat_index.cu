@@ -579,6 +579,15 @@ int prs_index_search_device(prs_index* idx, const void* q, int qdtype, int64_t n
     return search_device_impl(idx, q, qdtype, nq, k, D, I, (cudaStream_t)stream);
 }
 
+// page-locked host memory that the device can address (cudaHostAlloc / cudaHostRegister / torch pin_memory)
+static bool mapped_host_pointer(const void* p, void** dptr) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    if (a.type != cudaMemoryTypeHost || !a.devicePointer) return false;
+    *dptr = a.devicePointer;
+    return true;
+}
+
 int prs_index_search_host(prs_index* idx, const float* q, int64_t nq, int k, float* D, int64_t* I) {
     if (!idx) { set_error("null index"); return PRS_EINVAL; }
     if (k < 1 || k > PRS_MAX_K) { set_error("search: k=%d out of range [1, %d]", k, PRS_MAX_K); return PRS_EINVAL; }
@@ -591,6 +600,18 @@ int prs_index_search_host(prs_index* idx, const float* q, int64_t nq, int k, flo
     // the index's staging buffers and the legacy stream
     std::lock_guard<std::mutex> hl(idx->host_mu);
     void *dq, *dD, *dI;
+    // Pinned caller buffers + the tcgen05 path: no staging copies.  The query-preparation kernel reads
+    // every query element exactly once straight from the pinned host buffer (the host->device
+    // transfer of the step) and the merge kernel stores the k results per query straight into the
+    // caller's pinned D / I (the device->host transfer); one stream synchronisation ends the call.
+    // (The CUDA-core scan re-reads the queries in every CTA, so it keeps the staged copy.)
+    if (idx->path_force != 1 && idx->n > 0 &&
+        (umma_eligible(idx->storage, idx->d, idx->pitch, nq, k) || umma_wide_eligible(idx->storage, idx->pitch, nq, k, idx->n)) &&
+        mapped_host_pointer(q, &dq) && mapped_host_pointer(D, &dD) && mapped_host_pointer(I, &dI)) {
+        if ((rc = search_device_impl(idx, dq, PRS_F32, nq, k, (float*)dD, (int64_t*)dI, 0))) return rc;
+        PRS_CUDA(cudaStreamSynchronize(0));
+        return 0;
+    }
     {
         std::lock_guard<std::mutex> lock(idx->mu);
         if ((rc = idx->hQ.ensure((size_t)nq * idx->d * 4))) return rc;

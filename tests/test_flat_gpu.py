@@ -406,3 +406,23 @@ def test_full_size_1m_x_768_properties(P):
             better = np.nonzero(S[:, r] > kth + 2e-3)[0]
             assert set(better.tolist()) <= set(inside.tolist()), (storage, path, r)
         del idx
+
+
+def test_host_search_with_pinned_buffers_is_zero_copy_and_identical(P):
+    """prs_index_search_host with page-locked q / D / I (what bench.py's e2e leg passes) skips the
+    staging copies: kernels read the queries from, and write the results to, the caller's pinned memory.
+    Results must equal the ordinary pageable-buffer call bit for bit."""
+    import torch
+    rng = np.random.default_rng(21)
+    x = rng.standard_normal((30000, 384)).astype(np.float32)
+    q = rng.standard_normal((40, 384)).astype(np.float32)
+    for storage, k in (("fp16", 10), ("fp16", 50), ("fp32", 10)):
+        idx = P.FlatIndex(384, P.METRIC_L2, storage)
+        idx.add(x)
+        D0, I0 = idx.search(q, k)                                   # pageable numpy buffers
+        qp = torch.from_numpy(q).pin_memory()
+        Dp = torch.empty((40, k), dtype=torch.float32).pin_memory()
+        Ip = torch.empty((40, k), dtype=torch.int64).pin_memory()
+        Dp.fill_(-7.0); Ip.fill_(-7)
+        idx.search_into(qp.data_ptr(), 40, k, Dp.data_ptr(), Ip.data_ptr())
+        assert np.array_equal(Ip.numpy(), I0) and np.array_equal(Dp.numpy(), D0)
