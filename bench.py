@@ -390,6 +390,11 @@ def run_b200(a):
     def step_e2e(i):
         if world == 1:
             idx.search_into(Qh[i].data_ptr(), a.batch, a.k, Dh.data_ptr(), Ih.data_ptr())
+        elif a.exchange == "p2p":
+            # pinned host queries in, pinned host results out: the kernels address them directly (UVA)
+            st = torch.cuda.current_stream().cuda_stream
+            sh.search_into(Qh[i].data_ptr(), a.batch, a.k, Dh.data_ptr(), Ih.data_ptr(), st)
+            torch.cuda.synchronize()
         else:
             qd = Qh[i].to(dev, non_blocking=True)
             D, I = sh.search(qd, a.k)
@@ -421,6 +426,10 @@ def run_b200(a):
         sampler.stop()
     last_I = Ih.numpy().copy()
     last_D = Dh.numpy().copy()
+    # the host-buffer result of the last step must equal the device-resident search of the same batch
+    Dd, Id = sh.search(Qd[nbatches - 1], a.k)
+    torch.cuda.synchronize()
+    e2e_same = bool(np.array_equal(Id.cpu().numpy(), last_I) and np.array_equal(Dd.cpu().numpy(), last_D))
 
     # max over ranks
     t = torch.tensor([dev_ms, e2e_ms, scan_ms / max(scan_launches, 1)], dtype=torch.float64, device=dev)
@@ -455,8 +464,9 @@ def run_b200(a):
                      "frac_of_nominal_8TBs": achieved / 8000.0,
                      "share_of_step": scan_avg_ms * (scan_launches / max(a.steps, 1)) / (dev_ms / a.steps)},
         "e2e": {"value": qps_e2e, "unit": "queries/s", "h2d_bytes_per_step": a.batch * a.d * 4,
-                "d2h_bytes_per_step": a.batch * a.k * 12, "ms_per_step": e2e_ms / a.steps,
-                "api": "prs_index_search_host (pinned host q, D, I)" if world == 1 else "ShardedFlatIndex.search with pinned H2D/D2H"},
+                "d2h_bytes_per_step": a.batch * a.k * 12, "ms_per_step": e2e_ms / a.steps, "equals_device_resident_result": e2e_same,
+                "api": "prs_index_search_host (pinned host q, D, I)" if world == 1 else
+                       ("ShardedFlatIndex.search_into (pinned host q, D, I addressed by the kernels)" if a.exchange == "p2p" else "ShardedFlatIndex.search with pinned H2D/D2H")},
         "step_breakdown_ms": {"prep_kernel": prep_ms / a.steps, "scan_kernel": scan_ms / a.steps, "merge_kernel": merge_ms / a.steps,
                               "rest (launch gaps, event records)": dev_ms / a.steps - (prep_ms + scan_ms + merge_ms) / a.steps},
         "gpu_launches": launches,

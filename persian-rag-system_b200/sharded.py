@@ -88,6 +88,23 @@ class ShardedFlatIndex:
         self.dist.barrier(group=self.group)
         return x
 
+    def search_into(self, q_ptr: int, nq: int, k: int, D_ptr: int, I_ptr: int, stream: int = 0) -> None:
+        """Raw-pointer variant for page-locked host buffers (or device buffers): float32 queries at
+        `q_ptr`, results written to `D_ptr` / `I_ptr`.  Under unified addressing pinned host memory is
+        directly readable and writable by the kernels, so a search needs no staging copies; the caller
+        synchronises `stream` before reading the results.  Falls back to an error when the fused
+        exchange is not available (use `search` with CUDA tensors then)."""
+        if not (self.world > 1 and self._xs and int(nq) <= self._cap[0] and int(nq) * int(k) <= self._cap[1]):
+            if self.world == 1:
+                check(_lib.lib().prs_index_search_device(self.local._h, ctypes.c_void_p(q_ptr), _lib.F32, int(nq), int(k),
+                                                         ctypes.c_void_p(D_ptr), ctypes.c_void_p(I_ptr), ctypes.c_void_p(stream)))
+                return
+            raise _lib.PrsError(_lib.EINVAL, "search_into needs the p2p exchange and nq, k within its capacity")
+        x = self._xs[self._calls % len(self._xs)]
+        self._calls += 1
+        check(_lib.lib().prs_index_search_sharded_device(self.local._h, x, ctypes.c_void_p(q_ptr), _lib.F32, int(nq), int(k),
+                                                         ctypes.c_void_p(D_ptr), ctypes.c_void_p(I_ptr), ctypes.c_void_p(stream)))
+
     def check_exchange(self) -> None:
         """Raises if any fused search timed out waiting for a peer (synchronises the device)."""
         for x in self._xs:
