@@ -345,8 +345,6 @@ def run_b200(a):
         evs = []
         for s in range(a.steps):
             l2_flush(s)
-            if world > 1:
-                dist.barrier()                      # the flushes take different times per rank: start every step together
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             step_device(a.warmup + s)
