@@ -812,16 +812,6 @@ static inline int search_umma_wide(UmmaState& st, const void* x, const float* xn
     int h_over = 0;
     PRS_CUDA(cudaMemcpyAsync(&h_over, overflow, 4, cudaMemcpyDeviceToHost, stream));
     PRS_CUDA(cudaStreamSynchronize(stream));
-    if (getenv("PRS_WIDE_DEBUG")) {
-        std::vector<float> ht((size_t)nq);
-        std::vector<int> hc((size_t)parts * nq);
-        cudaMemcpy(ht.data(), st.tau.p, (size_t)nq * 4, cudaMemcpyDeviceToHost);
-        cudaMemcpy(hc.data(), st.coll_cnt.p, (size_t)parts * nq * 4, cudaMemcpyDeviceToHost);
-        long long tot0 = 0; int mx = 0;
-        for (int p2 = 0; p2 < parts; ++p2) { tot0 += hc[(size_t)p2 * nq]; mx = std::max(mx, hc[(size_t)p2 * nq]); }
-        fprintf(stderr, "[wide] n=%lld k=%d parts=%d S=%lld M=%lld cap=%d tau[0]=%g tau[last]=%g q0: total=%lld max=%d overflow=%d\n",
-                n, k, parts, S, M, cap, ht[0], ht[(size_t)nq - 1], tot0, mx, h_over);
-    }
     *overflowed = h_over != 0;
     return 0;
 }
