@@ -72,27 +72,39 @@ struct DevBuf {
 struct ScanTimer {
     bool enabled = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev;
+    std::vector<cudaEvent_t> pool;                 // events are reused: creating one costs microseconds of host time
+    cudaEvent_t take() {
+        if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
+        cudaEvent_t e = nullptr;
+        cudaEventCreate(&e);
+        return e;
+    }
     void begin(cudaStream_t st) {
         if (!enabled) return;
-        cudaEvent_t a, b;
-        cudaEventCreate(&a); cudaEventCreate(&b);
+        cudaEvent_t a = take(), b = take();
         cudaEventRecord(a, st);
         ev.emplace_back(a, b);
     }
     void end(cudaStream_t st) { if (enabled && !ev.empty()) cudaEventRecord(ev.back().second, st); }
     int collect(double* total_ms, long long* launches) {
         double tot = 0.0;
+        cudaError_t bad = cudaSuccess;
         for (auto& e : ev) {
             float ms = 0.f;
             cudaError_t r = cudaEventSynchronize(e.second);
             if (r == cudaSuccess) r = cudaEventElapsedTime(&ms, e.first, e.second);
-            cudaEventDestroy(e.first); cudaEventDestroy(e.second);
-            if (r != cudaSuccess) { ev.clear(); set_error("scan timer: %s", cudaGetErrorString(r)); return PRS_ECUDA; }
+            pool.push_back(e.first); pool.push_back(e.second);
+            if (r != cudaSuccess) bad = r;
             tot += ms;
         }
         *total_ms = tot; *launches = (long long)ev.size();
         ev.clear();
+        if (bad != cudaSuccess) { cudaGetLastError(); set_error("scan timer: %s", cudaGetErrorString(bad)); return PRS_ECUDA; }
         return 0;
+    }
+    ~ScanTimer() {
+        for (auto& e : ev) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+        for (auto e : pool) cudaEventDestroy(e);
     }
 };
 
