@@ -145,8 +145,13 @@ int prs_xchg_handle_bytes(void);
 int prs_xchg_get_handle(prs_xchg* x, void* handle_out);
 /* handles: n_ranks consecutive handles in rank order (this rank's own entry is ignored) */
 int prs_xchg_open_peers(prs_xchg* x, const void* handles);
-/* 0, or PRS_ECUDA if a search timed out waiting for a peer (synchronises the device) */
+/* 0, or PRS_ECUDA if a search timed out waiting for a peer (synchronises the device, then resets the
+ * report).  A query whose peer lists did not arrive returns the empty-result sentinel (ids -1), never a
+ * merge of stale lists; the report also surfaces, without a synchronisation, as the return code of the
+ * NEXT prs_index_search_sharded_device call on the same exchange context. */
 int prs_xchg_status(prs_xchg* x);
+/* how long a search waits for a peer's lists before giving up (default 2000 ms) */
+int prs_xchg_set_timeout_ms(prs_xchg* x, int64_t ms);
 void prs_xchg_free(prs_xchg* x);
 int prs_index_search_sharded_device(prs_index* idx, prs_xchg* x, const void* q, int qdtype, int64_t nq, int k,
                                     float* D, int64_t* I, void* stream);

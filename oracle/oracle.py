@@ -41,6 +41,45 @@ METRIC_IP = 0   # faiss METRIC_INNER_PRODUCT
 METRIC_L2 = 1   # faiss METRIC_L2
 
 # --------------------------------------------------------------------------------------
+# The real third-party libraries, when they exist (requirements.txt:5,9 of the reference pin
+# faiss-cpu==1.7.4 and rank_bm25==0.2.2; neither wheel is in this image and there is no network).
+# The moment one becomes importable -- in site-packages or under baseline/_ref/ -- the tests in
+# tests/test_oracle.py cross-check the restatements against it and bench.py's reference arm
+# times it (`cpu_baseline.kind: "reference"`).  Until then both stay "parity unpinned".
+# --------------------------------------------------------------------------------------
+_REF_DIRS = (os.path.join(os.path.dirname(_HERE), "baseline", "_ref"),)
+
+
+def reference_library(name: str):
+    """`faiss` / `rank_bm25` module if importable (also from baseline/_ref), else None."""
+    import importlib
+    import sys
+    for extra in (None,) + _REF_DIRS:
+        if extra is not None:
+            if not os.path.isdir(extra) or extra in sys.path:
+                continue
+            sys.path.append(extra)
+        try:
+            return importlib.import_module(name)
+        except Exception:                                  # ImportError, or a wheel built for another ABI
+            continue
+    return None
+
+
+def faiss_search(x, q, k: int, metric: int = METRIC_L2):
+    """The reference's own call chain (src/create_embeddings.py:130-133, src/retrieval.py:102) on real
+    faiss: IndexFlatL2/IP(d); add(x); search(q, k).  Raises RuntimeError when faiss is absent."""
+    faiss = reference_library("faiss")
+    if faiss is None:
+        raise RuntimeError("faiss is not importable here")
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    q = np.ascontiguousarray(q, dtype=np.float32)
+    index = faiss.IndexFlatL2(x.shape[1]) if metric == METRIC_L2 else faiss.IndexFlatIP(x.shape[1])
+    index.add(x)
+    return index.search(q, k)
+
+
+# --------------------------------------------------------------------------------------
 # C oracle loader
 # --------------------------------------------------------------------------------------
 _clib = None

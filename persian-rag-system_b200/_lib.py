@@ -49,6 +49,7 @@ SIGNATURES = {
     "prs_xchg_get_handle": (c_int, [c_void_p, c_void_p]),
     "prs_xchg_open_peers": (c_int, [c_void_p, c_void_p]),
     "prs_xchg_status": (c_int, [c_void_p]),
+    "prs_xchg_set_timeout_ms": (c_int, [c_void_p, c_i64]),
     "prs_xchg_free": (None, [c_void_p]),
     "prs_index_search_sharded_device": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_i64, c_int, c_void_p, c_void_p, c_void_p]),
     "prs_sparse_build": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_i64, ctypes.c_int32, c_int, ctypes.POINTER(c_void_p)]),

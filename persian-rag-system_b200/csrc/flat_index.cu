@@ -167,6 +167,7 @@ struct prs_index {
     float* xnorm = nullptr;
     long long id_offset = 0;
     int path_force = 0, last_path = 0;
+    int l2_rerank = 1;                   // 16-bit storage, L2: direct-form distances for the selected rows (see topk_merge.cuh)
     std::mutex mu, host_mu;
     // Search workspaces.  Two slots used round-robin so that two searches can be IN FLIGHT on two
     // streams (the merge / exchange kernel of one overlaps the scan of the next); a slot is reused
@@ -197,7 +198,14 @@ struct prs_xchg {
     bool opened[XCHG_MAX_RANKS] = {};
     uint32_t gen = 0;
     XchgView view{};
-    int* status = nullptr;
+    int* h_status = nullptr;              // page-locked, device-mapped: the kernel's timeout report, readable without a sync
+    int* d_status = nullptr;              // device alias of h_status
+    unsigned long long timeout_ns = 2000000000ull;
+    // consecutive searches on ONE exchange context must be stream-ordered on every rank (a peer may
+    // only overwrite a slot after this rank's read of it has finished): each search waits for the
+    // previous one's merge kernel through this event, whatever streams the caller uses
+    cudaEvent_t event = nullptr;
+    bool used = false;
 };
 
 static inline size_t xchg_vals_bytes(const prs_xchg* x) { return (size_t)2 * x->G * x->cap * 4; }
@@ -209,9 +217,9 @@ static void xchg_fill_view(prs_xchg* x) {
         unsigned char* b = (unsigned char*)x->peer_base[p];
         x->view.ids[p] = (long long*)b;                                  // 8-byte aligned first
         x->view.vals[p] = (float*)(b + xchg_ids_bytes(x));
-        x->view.flags[p] = (uint32_t*)(b + xchg_ids_bytes(x) + xchg_vals_bytes(x));
+        x->view.vals2[p] = (float*)(b + xchg_ids_bytes(x) + xchg_vals_bytes(x));
+        x->view.flags[p] = (uint32_t*)(b + xchg_ids_bytes(x) + 2 * xchg_vals_bytes(x));
     }
-    x->status = (int*)((unsigned char*)x->base + xchg_ids_bytes(x) + xchg_vals_bytes(x) + xchg_flags_bytes(x));
 }
 
 static int index_grow(prs_index* idx, long long n_total) {
@@ -294,22 +302,29 @@ static inline int merge_sortn(long long total, int k) {
 static int launch_merge(prs_index* idx, int parts, long long nq, int k, int out_mode, const float* qnorm,
                         float* D, int64_t* I, cudaStream_t st) {
     const int sortn = merge_sortn((long long)parts * k, k);
-    const size_t smem = (size_t)sortn * 8 + MERGE_THREADS * 8 + 16;
+    const size_t smem = (size_t)sortn * 8 + MERGE_THREADS * 8 + 16 + (size_t)(k + 2) * 12;
     struct T { ScanTimer& t; cudaStream_t s; T(ScanTimer& t_, cudaStream_t s_) : t(t_), s(s_) { t.begin(s); } ~T() { t.end(s); } } tm(idx->timer_merge, st);
+    // 16-bit storage + L2 (tcgen05 scan, expanded form): the merge recomputes the selected rows' distances in
+    // the direct form from the stored rows and the 16-bit queries the prep kernel left behind
+    Rerank rr{nullptr, nullptr, idx->pitch, idx->storage == PRS_BF16 ? 1 : 0};
+    if (out_mode == 2 && idx->l2_rerank) { rr.x = (const unsigned char*)idx->x; rr.qlow = (const uint16_t*)idx->cur->umma.qlow.p; }
     if (t_xchg) {
         prs_xchg* x = t_xchg;
         ++x->gen;
+        if (x->used) PRS_CUDA(cudaStreamWaitEvent(st, x->event, 0));
         PRS_CUDA(cudaFuncSetAttribute(merge_xchg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         merge_xchg_kernel<<<(unsigned)nq, MERGE_THREADS, smem, st>>>((const u64*)idx->cur->cand.p, parts,
                                                                     (int)nq, k, sortn, out_mode, qnorm, idx->id_offset,
-                                                                    idx->metric == PRS_METRIC_IP ? 1 : 0, x->view, x->gen, D,
-                                                                    (long long*)I, x->status);
+                                                                    idx->metric == PRS_METRIC_IP ? 1 : 0, rr, x->view, x->gen,
+                                                                    x->timeout_ns, D, (long long*)I, x->d_status);
         PRS_LAUNCH_CHECK();
+        PRS_CUDA(cudaEventRecord(x->event, st));
+        x->used = true;
         return 0;
     }
     PRS_CUDA(cudaFuncSetAttribute(merge_cand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     merge_cand_kernel<<<(unsigned)nq, MERGE_THREADS, smem, st>>>((const u64*)idx->cur->cand.p, parts,
-                                                                (int)nq, k, sortn, out_mode, qnorm, idx->id_offset, D,
+                                                                (int)nq, k, sortn, out_mode, qnorm, idx->id_offset, rr, D,
                                                                 (long long*)I);
     PRS_LAUNCH_CHECK();
     return 0;
@@ -401,17 +416,21 @@ static int search_device_impl(prs_index* idx, const void* q, int qdtype, long lo
     const bool wide = umma_wide_eligible(idx->storage, idx->pitch, nq, k, idx->n);
     if (path == 0) path = (umma_eligible(idx->storage, idx->d, idx->pitch, nq, k) || wide) ? 2 : 1;
     if (path == 2 && wide) {
-        // 16 < k <= 1024: sample -> threshold -> collect -> select (flat_umma.cuh), then the usual merge of ONE part
-        if ((rc = idx->cur->qnorm.ensure((size_t)nq * 4))) return rc;
-        bool overflowed = false;
-        if ((rc = search_umma_wide(idx->cur->umma, idx->x, idx->xnorm, idx->n, idx->d, idx->pitch, idx->storage, idx->metric, idx->sm_count,
-                                   q, qdtype, nq, k, (float*)idx->cur->qnorm.p, idx->cur->cand, idx->cur->cand_cnt, &overflowed, st, &idx->timer, &idx->timer_prep))) return rc;
-        if (!overflowed) {
-            idx->last_path = 2;
-            return launch_merge(idx, 1, nq, k, idx->metric == PRS_METRIC_L2 ? 2 : 0, (const float*)idx->cur->qnorm.p, D, I, st);
+        // 16 < k <= 1024: sample -> threshold -> collect -> select (flat_umma.cuh), then the usual merge of ONE
+        // part; large batches go through in chunks so that the collection buffer stays bounded
+        idx->last_path = 2;
+        const long long chunk = umma_wide_chunk(k);
+        const size_t qes = elem_size(qdtype);
+        for (long long q0 = 0; q0 < nq; q0 += chunk) {
+            const long long nqc = std::min<long long>(chunk, nq - q0);
+            if ((rc = idx->cur->qnorm.ensure((size_t)nqc * 4))) return rc;
+            if ((rc = search_umma_wide(idx->cur->umma, idx->x, idx->xnorm, idx->n, idx->d, idx->pitch, idx->storage, idx->metric, idx->sm_count,
+                                       (const unsigned char*)q + (size_t)q0 * idx->d * qes, qdtype, nqc, k, (float*)idx->cur->qnorm.p,
+                                       idx->cur->cand, idx->cur->cand_cnt, st, &idx->timer, &idx->timer_prep))) return rc;
+            if ((rc = launch_merge(idx, 1, nqc, k, idx->metric == PRS_METRIC_L2 ? 2 : 0, (const float*)idx->cur->qnorm.p,
+                                   D + (size_t)q0 * k, I + (size_t)q0 * k, st))) return rc;
         }
-        if (idx->path_force == 2) { set_error("tcgen05 wide-k path: candidate buffer overflow (too many rows tie with the threshold)"); return PRS_EUNSUP; }
-        path = 1;                                   // pathological input: exact CUDA-core scan instead
+        return 0;
     }
     if (path == 2) {
         if (!umma_eligible(idx->storage, idx->d, idx->pitch, nq, k)) {
@@ -679,7 +698,7 @@ int prs_xchg_create(int device, int n_ranks, int rank, int64_t nq_cap, int k_cap
     prs_xchg* x = new (std::nothrow) prs_xchg();
     if (!x) { set_error("out of host memory"); return PRS_ENOMEM; }
     x->device = device; x->G = n_ranks; x->rank = rank; x->nq_cap = (int)nq_cap; x->cap = nq_cap * k_cap;
-    x->bytes = xchg_ids_bytes(x) + xchg_vals_bytes(x) + xchg_flags_bytes(x) + 256;
+    x->bytes = xchg_ids_bytes(x) + 2 * xchg_vals_bytes(x) + xchg_flags_bytes(x) + 256;
     cudaError_t e = cudaMalloc(&x->base, x->bytes);
     if (e != cudaSuccess) {
         cudaGetLastError();
@@ -689,6 +708,17 @@ int prs_xchg_create(int device, int n_ranks, int rank, int64_t nq_cap, int k_cap
     }
     PRS_CUDA(cudaMemset(x->base, 0, x->bytes));
     PRS_CUDA(cudaDeviceSynchronize());
+    if (cudaHostAlloc((void**)&x->h_status, 64, cudaHostAllocMapped) != cudaSuccess ||
+        cudaHostGetDevicePointer((void**)&x->d_status, x->h_status, 0) != cudaSuccess ||
+        cudaEventCreateWithFlags(&x->event, cudaEventDisableTiming) != cudaSuccess) {
+        cudaGetLastError();
+        set_error("xchg_create: could not allocate the status word / event");
+        if (x->h_status) cudaFreeHost(x->h_status);
+        cudaFree(x->base);
+        delete x;
+        return PRS_ENOMEM;
+    }
+    *x->h_status = 0;
     x->peer_base[rank] = x->base;
     xchg_fill_view(x);
     *out = x;
@@ -721,12 +751,25 @@ int prs_xchg_open_peers(prs_xchg* x, const void* handles) {
     return 0;
 }
 
+// the kernel's report lives in mapped host memory: reading it costs nothing; it is reset once reported
+static int xchg_take_status(prs_xchg* x) {
+    if (*(volatile int*)x->h_status == 0) return 0;
+    *(volatile int*)x->h_status = 0;
+    set_error("sharded search: timed out (%.1f s) waiting for a peer rank's candidate lists; the affected queries returned ids -1",
+              (double)x->timeout_ns * 1e-9);
+    return PRS_ECUDA;
+}
+
 int prs_xchg_status(prs_xchg* x) {
     if (!x) { set_error("null exchange"); return PRS_EINVAL; }
     DeviceGuard g(x->device);
-    int st = 0;
-    PRS_CUDA(cudaMemcpy(&st, x->status, sizeof(int), cudaMemcpyDeviceToHost));
-    if (st) { set_error("sharded search: timed out waiting for a peer rank's candidate lists"); return PRS_ECUDA; }
+    PRS_CUDA(cudaDeviceSynchronize());
+    return xchg_take_status(x);
+}
+
+int prs_xchg_set_timeout_ms(prs_xchg* x, int64_t ms) {
+    if (!x || ms < 1) { set_error("xchg_set_timeout_ms: bad arguments"); return PRS_EINVAL; }
+    x->timeout_ns = (unsigned long long)ms * 1000000ull;
     return 0;
 }
 
@@ -736,6 +779,8 @@ void prs_xchg_free(prs_xchg* x) {
     cudaDeviceSynchronize();
     for (int p = 0; p < x->G; ++p) if (x->opened[p]) cudaIpcCloseMemHandle(x->peer_base[p]);
     if (x->base) cudaFree(x->base);
+    if (x->h_status) cudaFreeHost(x->h_status);
+    if (x->event) cudaEventDestroy(x->event);
     delete x;
 }
 
@@ -750,6 +795,8 @@ int prs_index_search_sharded_device(prs_index* idx, prs_xchg* x, const void* q, 
     for (int p = 0; p < x->G; ++p) if (!x->peer_base[p]) { set_error("sharded search: peer %d not opened", p); return PRS_EINVAL; }
     DeviceGuard g(idx->device);
     if (idx->n == 0) { set_error("sharded search: every rank must hold at least one row"); return PRS_EINVAL; }
+    // a timeout reported by an EARLIER search on this context surfaces here (cheap: mapped host word)
+    if (int rc = xchg_take_status(x)) return rc;
     struct Scope { ~Scope() { t_xchg = nullptr; } } scope;
     t_xchg = x;               // read by launch_merge on this thread
     return search_device_impl(idx, q, qdtype, nq, k, D, I, (cudaStream_t)stream);

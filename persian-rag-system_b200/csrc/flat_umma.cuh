@@ -14,7 +14,7 @@
 //   D  = fp32 accumulators in TMEM, double buffered (2 x TILE_N columns).
 //   epilogue (4 warps, one thread per query): tcgen05.ld its lane's TILE_N scores, apply the L2
 //        bias (2 q.x - ||x||^2), compare with the thread's k-th best, and on the rare hit insert
-//        into a thread-private sorted list in shared memory.  The score matrix never exists in
+//        into a thread-private sorted list held in 16 registers.  The score matrix never exists in
 //        HBM; each CTA emits one sorted top-k per query (cand[cta][query][k]).
 //
 // TMEM budget (512 columns): A uses pitch/2 columns (two 16-bit values per column), D uses
@@ -24,6 +24,8 @@
 // warps 2..5 = epilogue (TMEM lane quarter = warp % 4).
 #pragma once
 #include <algorithm>
+#include <map>
+#include <mutex>
 #include <type_traits>
 #include <vector>
 
@@ -31,9 +33,17 @@
 #include "host_common.h"
 #include "topk_merge.cuh"
 
+// Timing experiments (profiles/r1_umma_variant_experiments.log) change what the kernel computes, so they
+// exist only in builds made with -DPRS_EXPERIMENTS; the shipped library has no such switches.
+#ifdef PRS_EXPERIMENTS
+#define UMMA_DBG(p) ((p).dbg)
+#else
+#define UMMA_DBG(p) 0
+#endif
+
 namespace prs {
 
-constexpr int UMMA_MAX_K = 16;         // thread-private sorted lists live in shared memory
+constexpr int UMMA_MAX_K = 16;         // thread-private sorted lists are 16 registers per thread
 constexpr int UMMA_THREADS = 192;
 constexpr int UMMA_M = 128;            // queries per pass
 constexpr int UMMA_MAX_STAGES = 24;
@@ -58,8 +68,7 @@ struct UmmaParams {
     const float* tau;       // mode 1: [nq_total] admission threshold per query (a lower bound of its k-th best)
     u64* coll;              // mode 1: [parts][nq_total][coll_cap] unsorted keys
     int* coll_cnt;          // mode 1: [parts][nq_total]
-    int coll_cap;
-    int* overflow;          // mode 1: set to 1 when a (part, query) buffer was too small
+    int coll_cap;           // mode 1: entries per (part, query) slice, >= 2k (a full slice is compacted to its k best)
     uint32_t* boot;         // per query block: [parts][128] ord(best score of the first tile) + 1 counter; zeroed per search
     long long boot_stride;  // words between the bootstrap arrays of consecutive query blocks
 };
@@ -134,6 +143,19 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 // (cute::UMMA::SmemDescriptor: start[0,14) LBO[16,30) SBO[32,46) version[46,48)=1 layout[61,64)=2)
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
     return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+
+// k-th largest of n distinct 64-bit keys (n >= k), by bisection on the key bits.  One thread, rare path
+// (a collection slice of the wide-k scan filled up); kept out of line so the hot loop stays small.
+__device__ __noinline__ u64 slice_kth_largest(const u64* s, int n, int k) {
+    u64 prefix = 0ull;
+    for (int b = 63; b >= 0; --b) {
+        const u64 c = prefix | (1ull << b);
+        int cnt = 0;
+        for (int i = 0; i < n; ++i) cnt += s[i] >= c;
+        if (cnt >= k) prefix = c;
+    }
+    return prefix;
 }
 
 // CL = thread-block cluster size.  CL == 1: one CTA per SM streams its own tiles (bandwidth-bound
@@ -253,7 +275,7 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) flat_scan_umma_kernel(const U
                             const uint32_t a_tmem = tmem_base + (uint32_t)(kb * 32 + k4 * 8);
                             // dbg 128 (timing experiment, wrong results): odd MMAs accumulate into the OTHER buffer,
                             // i.e. two independent accumulation chains instead of one
-                            const uint32_t d_use = ((p.dbg & 128) && (k4 & 1)) ? (tmem_base + D_OFF + (uint32_t)((b ^ 1) * TILE_N)) : d_tmem;
+                            const uint32_t d_use = ((UMMA_DBG(p) & 128) && (k4 & 1)) ? (tmem_base + D_OFF + (uint32_t)((b ^ 1) * TILE_N)) : d_tmem;
                             umma_ts_f16(d_use, a_tmem, bdesc, idesc, (kb | k4) != 0 ? 1u : 0u);
                         }
                     }
@@ -400,9 +422,18 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) flat_scan_umma_kernel(const U
                     for (int jj = 0; jj < BLK_ROWS; ++jj) bits = (jj == j) ? v[jj] : bits;
                     const float sc = __uint_as_float(bits);
                     if (collect) {
-                        if (ccount < p.coll_cap) cslice[ccount] = make_key<PRS_TIE_LOW_ID>(sc, (uint32_t)(rbase + j));
-                        else *p.overflow = 1;
-                        ++ccount;
+                        if (ccount == p.coll_cap) {
+                            // slice full (thousands of rows tie with tau): keep exactly its k best and raise
+                            // the admission threshold.  This thread visits rows in ascending id order, so a
+                            // later row that only TIES with the k-th kept score can never displace it
+                            // (lower id wins): from here on a score must be strictly better.
+                            const u64 kth = slice_kth_largest(cslice, p.coll_cap, p.k);
+                            int w = 0;
+                            for (int i = 0; i < p.coll_cap; ++i) { const u64 kk = cslice[i]; if (kk >= kth) cslice[w++] = kk; }
+                            ccount = w;
+                            thr = fmaxf(thr, nextafterf(key_score(kth), INFINITY));
+                        }
+                        if (sc >= thr) cslice[ccount++] = make_key<PRS_TIE_LOW_ID>(sc, (uint32_t)(rbase + j));
                     } else if (sc >= thr) {
                         // branch-free sorted insertion (descending); the key that falls off the end is dropped
                         u64 key = make_key<PRS_TIE_LOW_ID>(sc, (uint32_t)(rbase + j));
@@ -442,7 +473,7 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) flat_scan_umma_kernel(const U
             tc_fence_after();
             uint32_t v[BLK_ROWS];
             uint32_t hm[2];
-            if (p.dbg & 2) {
+            if (UMMA_DBG(p) & 2) {
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tmem_empty[b]);
@@ -466,7 +497,7 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) flat_scan_umma_kernel(const U
                 if (qvalid) p.gmax[qglobal * p.gmax_stride + ti] = sanitize(mx);
                 continue;
             }
-            if (p.dbg & 1) { thr = INFINITY; boot_done = true; }
+            if (UMMA_DBG(p) & 1) { thr = INFINITY; boot_done = true; }
             else if (it == 0 && p.mode == 0) {
                 // bootstrap pass over the first tile (both halves): best score per query, then the bound
                 float mx = -INFINITY;
@@ -489,7 +520,7 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) flat_scan_umma_kernel(const U
                 }
                 __threadfence();
                 refresh_boot();
-                if (p.dbg & 8) thr = INFINITY;
+                if (UMMA_DBG(p) & 8) thr = INFINITY;
             } else if (!boot_done && (it & (it + 1)) == 0) {
                 refresh_boot();          // it = 1, 3, 7, 15, ...
             }
@@ -507,7 +538,7 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) flat_scan_umma_kernel(const U
                 if (hm[0] | hm[1]) insert_hits(v, hm, row0 + h * BLK_ROWS);
             }
         }
-        if (qvalid && collect) p.coll_cnt[(size_t)part * p.nq_total + qglobal] = ccount < p.coll_cap ? ccount : p.coll_cap;
+        if (qvalid && collect) p.coll_cnt[(size_t)part * p.nq_total + qglobal] = ccount;
         if (qvalid && p.mode == 0) {
             const size_t o = (size_t)part * p.nq_total + p.q0 + crank * UMMA_M + qi;
             int n = 0;
@@ -595,12 +626,18 @@ static inline int umma_launch(const UmmaParams& p, int n_clusters, size_t smem, 
     return 0;
 }
 
-// how many clusters of CL CTAs (1 CTA per SM at this shared-memory size) the device runs at once
+// how many clusters of CL CTAs (1 CTA per SM at this shared-memory size) the device runs at once.
+// Cached per (device, shared-memory size) under a mutex: indices on different devices and threads
+// plan concurrently.
 template <int CL, int NB>
 static inline int umma_max_clusters(size_t smem, int sm_count) {
-    static int cached = -1;
-    static size_t cached_smem = 0;
-    if (cached > 0 && cached_smem == smem) return cached;
+    static std::mutex mu;
+    static std::map<std::pair<int, size_t>, int> cache;
+    int device = 0;
+    cudaGetDevice(&device);
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = cache.find({device, smem});
+    if (it != cache.end()) return it->second;
     if (cudaFuncSetAttribute(flat_scan_umma_kernel<CL, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return 0; }
     int n = sm_count / CL;
     if (CL > 1) {
@@ -616,7 +653,7 @@ static inline int umma_max_clusters(size_t smem, int sm_count) {
         if (cudaOccupancyMaxActiveClusters(&q, flat_scan_umma_kernel<CL, NB>, &cfg) != cudaSuccess) { cudaGetLastError(); return 0; }
         n = q;
     }
-    cached = n; cached_smem = smem;
+    cache[{device, smem}] = n;
     return n;
 }
 
@@ -628,10 +665,14 @@ struct UmmaPlan {
 };
 
 static inline int umma_plan(long long n, int pitch, long long nq, int sm_count, UmmaPlan& pl, bool no_clusters = false) {
+#ifdef PRS_EXPERIMENTS
     static const int dbg = getenv("PRS_UMMA_DEBUG") ? atoi(getenv("PRS_UMMA_DEBUG")) : 0;
     static const int dbg_kbs = getenv("PRS_UMMA_KBS") ? atoi(getenv("PRS_UMMA_KBS")) : 0;
     static const int dbg_cl = getenv("PRS_UMMA_CLUSTER") ? atoi(getenv("PRS_UMMA_CLUSTER")) : 0;
     static const int dbg_nb = getenv("PRS_UMMA_NB") ? atoi(getenv("PRS_UMMA_NB")) : 0;
+#else
+    const int dbg = 0, dbg_kbs = 0, dbg_cl = 0, dbg_nb = 0;
+#endif
     if (n > 0x7FFFFFFFll - 2 * BLK_ROWS) { set_error("tcgen05 path: more than 2^31 rows per shard"); return PRS_EUNSUP; }
     pl.dbg = dbg;
     const int kblocks = pitch >> 6;
@@ -642,7 +683,7 @@ static inline int umma_plan(long long n, int pitch, long long nq, int sm_count, 
     // stages 3443 GB/s, 16 KB 4431, 48 KB 4513 -> see profiles/)
     pl.kbs = 1;
     for (int c = 2; c <= 6 / pl.NB; ++c) if (kblocks % c == 0) pl.kbs = c;
-    if (dbg_kbs > 0 && kblocks % dbg_kbs == 0) pl.kbs = dbg_kbs;
+    if (dbg_kbs > 0 && kblocks % (dbg_kbs > 0 ? dbg_kbs : 1) == 0) pl.kbs = dbg_kbs;
     const size_t stage_bytes = (size_t)pl.kbs * pl.NB * KBLOCK_BYTES;
     const size_t fixed = 4 * (size_t)pl.NB * BLK_ROWS * 4 + (2 * UMMA_MAX_STAGES + 4) * 8 + 16;
     pl.stages = (int)((226 * 1024 - 1024 - fixed) / stage_bytes);
@@ -696,7 +737,7 @@ static inline int umma_prep(UmmaState& st, const UmmaPlan& pl, const void* q, in
 // all passes of one scan over the corpus (mode 0: sorted top-k lists of k <= 16; mode 1: collect >= tau)
 static inline int umma_scan(UmmaState& st, const UmmaPlan& pl, const void* x, const float* xnorm, long long n, int pitch, int storage,
                             int metric, long long nq, int k, int tile_step, int mode, u64* cand, int* cand_cnt, const float* tau,
-                            u64* coll, int* coll_cnt, int coll_cap, int* overflow, cudaStream_t stream, ScanTimer* timer,
+                            u64* coll, int* coll_cnt, int coll_cap, cudaStream_t stream, ScanTimer* timer,
                             float* gmax = nullptr, long long gmax_stride = 0) {
     for (long long q0 = 0; q0 < nq; q0 += pl.qblock) {
         UmmaParams p;
@@ -708,7 +749,7 @@ static inline int umma_scan(UmmaState& st, const UmmaPlan& pl, const void* x, co
         p.nbuf = 2;
         p.nq_total = (int)nq; p.q0 = (int)q0;
         p.cand = cand; p.cand_cnt = cand_cnt;
-        p.tile_step = tile_step; p.mode = mode; p.tau = tau; p.coll = coll; p.coll_cnt = coll_cnt; p.coll_cap = coll_cap; p.overflow = overflow;
+        p.tile_step = tile_step; p.mode = mode; p.tau = tau; p.coll = coll; p.coll_cnt = coll_cnt; p.coll_cap = coll_cap;
         p.gmax = gmax; p.gmax_stride = gmax_stride;
         p.boot = (uint32_t*)st.boot.p + (size_t)(q0 / UMMA_M) * pl.boot_words;
         p.boot_stride = pl.boot_words;
@@ -735,7 +776,7 @@ static inline int search_umma(UmmaState& st, const void* x, const float* xnorm, 
     if ((rc = cand.ensure((size_t)pl.n_clusters * nq * k * 8))) return rc;
     if ((rc = cand_cnt.ensure((size_t)pl.n_clusters * nq * 4))) return rc;
     if ((rc = umma_scan(st, pl, x, xnorm, n, pitch, storage, metric, nq, k, 1, 0, (u64*)cand.p, (int*)cand_cnt.p, nullptr, nullptr, nullptr, 0,
-                        nullptr, stream, timer))) return rc;
+                        stream, timer))) return rc;
     *parts_out = pl.n_clusters;
     return 0;
 }
@@ -747,48 +788,55 @@ static inline int search_umma(UmmaState& st, const void* x, const float* xnorm, 
 //   2. tau[q] = k-th largest of those M tile maxima -- scores of k distinct rows, hence a lower bound of
 //      the true k-th best (with few qualifying rows per tile this is as tight as the sample's own k-th);
 //   3. the full scan runs in collect mode: every score >= tau[q] is appended, unsorted, to the
-//      (part, query) slice of a collection buffer -- about k * S candidates per query in total;
+//      (part, query) slice of a collection buffer -- about k * S candidates per query in total.  A slice
+//      holds >= 2k entries; if it ever fills (thousands of rows tying with tau) its owner thread keeps
+//      the slice's k best and raises its threshold, so the result stays exact without any fallback;
 //   4. one CTA per query selects the k best of its slices into a single sorted list (then the
 //      ordinary merge / merge+exchange kernel finishes it).
-// Cost: (1 + 1/S) scans.  If a slice overflows (pathological duplicates) *overflowed is set and the
-// caller falls back to the CUDA-core scan.  Synchronises `stream` to read that flag.
+// Cost: (1 + 1/S) scans.  Fully asynchronous on `stream` (no host synchronisation).
 // ---------------------------------------------------------------------------------------------------
 constexpr int UMMA_WIDE_MAX_K = PRS_MAX_K;
 static inline bool umma_wide_eligible(int storage, int pitch, long long nq, int k, long long n) {
     return (storage == PRS_F16 || storage == PRS_BF16) && pitch <= 768 && k > UMMA_MAX_K && k <= UMMA_WIDE_MAX_K && nq >= 1 &&
            n >= 256ll * k && n >= 16384;                      // >= 2k tiles of 128 rows to sample a threshold from
 }
+// queries per call of search_umma_wide such that the collection buffer stays below ~2 GB whatever the
+// shard looks like (depends on k only: every rank of a sharded search must chunk identically)
+static inline long long umma_wide_chunk(int k) {
+    const long long cap = next_pow2(std::max(64, 2 * k));
+    const long long per_query = 160ll * cap * 8;
+    long long c = (2ll << 30) / per_query;
+    c = c / UMMA_M * UMMA_M;
+    return std::max<long long>(UMMA_M, c);
+}
 
 static inline int search_umma_wide(UmmaState& st, const void* x, const float* xnorm, long long n, int d, int pitch, int storage,
                                    int metric, int sm_count, const void* q, int qdtype, long long nq, int k, float* qnorm,
-                                   DevBuf& cand, DevBuf& cand_cnt, bool* overflowed, cudaStream_t stream,
+                                   DevBuf& cand, DevBuf& cand_cnt, cudaStream_t stream,
                                    ScanTimer* timer = nullptr, ScanTimer* timer_prep = nullptr) {
     UmmaPlan pl;
     int rc;
-    *overflowed = false;
     // no clusters: 148 independent parts keep the collection slices short
     if ((rc = umma_plan(n, pitch, nq, sm_count, pl, true))) return rc;
     const int parts = pl.n_clusters;
     // sampling step S: the sample must hold M >= 2k tiles (each contributes its best score = one
     // distinct row); at most every 16th tile so that the collecting pass sees <= ~16 k candidates per query
     long long S = std::min<long long>(16, pl.n_tiles / (2ll * k));
-    if (S < 1) { *overflowed = true; return 0; }                     // corpus too small for a sampled bound
+    if (S < 1) S = 1;                                                // (eligibility guarantees n_tiles >= 2k)
     const long long M = (pl.n_tiles + S - 1) / S;                    // sampled tiles
     const double expect = (double)k * (double)S / parts;             // survivors per (part, query)
-    int cap = next_pow2((int)std::min<double>(1 << 20, std::max<double>(64.0, 6.0 * expect + 32.0)));
+    const int cap = next_pow2((int)std::min<double>(1 << 20, std::max<double>(std::max(64, 2 * k), 6.0 * expect + 32.0)));
     const size_t coll_bytes = (size_t)parts * nq * cap * 8;
-    if (coll_bytes > (4ull << 30)) { *overflowed = true; return 0; }  // would not fit: let the caller use the CUDA-core scan
     if ((rc = umma_prep(st, pl, q, qdtype, nq, d, pitch, storage, qnorm, stream, timer_prep))) return rc;
     if ((rc = cand.ensure((size_t)nq * k * 8))) return rc;
     if ((rc = st.tau.ensure((size_t)nq * 4 + 16))) return rc;
     if ((rc = st.gmax.ensure((size_t)nq * M * 4))) return rc;
     if ((rc = st.coll.ensure(coll_bytes))) return rc;
     if ((rc = st.coll_cnt.ensure((size_t)parts * nq * 4))) return rc;
-    int* overflow = (int*)((unsigned char*)st.tau.p + (size_t)nq * 4 + 8 - (((size_t)nq * 4) & 7));
-    PRS_CUDA(cudaMemsetAsync(overflow, 0, 4, stream));
+    (void)cand_cnt;
     // 1. sampling pass: best score of every S-th tile
     if ((rc = umma_scan(st, pl, x, xnorm, n, pitch, storage, metric, nq, k, (int)S, 2, nullptr, nullptr, nullptr, nullptr, nullptr, 0,
-                        nullptr, stream, nullptr, (float*)st.gmax.p, M))) return rc;
+                        stream, nullptr, (float*)st.gmax.p, M))) return rc;
     // 2. thresholds: k-th largest of the M tile maxima
     {
         const int sortn = next_pow2(k + MERGE_THREADS);
@@ -799,7 +847,7 @@ static inline int search_umma_wide(UmmaState& st, const void* x, const float* xn
     }
     // 3. collecting pass (the dominant kernel: timed)
     if ((rc = umma_scan(st, pl, x, xnorm, n, pitch, storage, metric, nq, k, 1, 1, nullptr, nullptr, (const float*)st.tau.p, (u64*)st.coll.p,
-                        (int*)st.coll_cnt.p, cap, overflow, stream, timer))) return rc;
+                        (int*)st.coll_cnt.p, cap, stream, timer))) return rc;
     // 4. select into one sorted list per query: cand[1][nq][k]
     {
         const int sortn = next_pow2(k + MERGE_THREADS);
@@ -809,10 +857,6 @@ static inline int search_umma_wide(UmmaState& st, const void* x, const float* xn
                                                                              sortn, (u64*)cand.p);
         PRS_LAUNCH_CHECK();
     }
-    int h_over = 0;
-    PRS_CUDA(cudaMemcpyAsync(&h_over, overflow, 4, cudaMemcpyDeviceToHost, stream));
-    PRS_CUDA(cudaStreamSynchronize(stream));
-    *overflowed = h_over != 0;
     return 0;
 }
 

@@ -62,14 +62,67 @@ __device__ __forceinline__ int block_topk_lists(Fetch fetch, int parts, int L, i
     return cnt < k ? cnt : k;
 }
 
+// ---------------------------------------------------------------------------------------------
+// 16-bit storage, squared L2: exact values for the selected rows.
+// The tcgen05 scan ranks rows by the EXPANDED form 2 q.x - ||x||^2 accumulated in fp32; its
+// cancellation error (~1e-7 * ||x||^2) is far below the distance of ordinary neighbours but not of
+// near-duplicate ones (the reference's fine-tuned indices: ||x||^2 ~ 25, nearest distances down to
+// 5e-5, SURVEY.md findings 2/7).  The merge therefore recomputes the squared distance of the k
+// selected rows in the DIRECT form sum (q~ - x)^2 -- what faiss does for nq < 20 -- from the stored
+// rows and the query rounded to the storage type, and orders the result by (distance, id).
+// ---------------------------------------------------------------------------------------------
+struct Rerank {
+    const unsigned char* x;   // corpus, T64 layout (nullptr = no re-rank)
+    const uint16_t* qlow;     // [nq padded][pitch] 16-bit queries in TMEM-slot order (prep kernel)
+    int pitch, is_bf16;
+};
+
+// slot row of query q in qlow (inverse of the lane spreading in the scan kernel's epilogue)
+__device__ __forceinline__ long long qlow_row(int q) {
+    const int qi = q & 127;
+    return (long long)(q & ~127) + (long long)((qi & 3) * 32 + (qi >> 2));
+}
+
+__device__ __forceinline__ void cvt8(const uint4& v, int is_bf16, float (&f)[8]) {
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        if (is_bf16) { f[2 * i] = __uint_as_float(w[i] << 16); f[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u); }
+        else { const float2 t = __half22float2(*reinterpret_cast<const __half2*>(&w[i])); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+    }
+}
+
+// dd[j] = sum (q~ - x_row(j))^2 for the n keys in buf (one warp per key, 16-byte pieces per lane)
+__device__ __forceinline__ void direct_l2_of_keys(const u64* buf, int n, const Rerank& rr, int q, float* dd, int tid) {
+    const int warp = tid >> 5, lane = tid & 31;
+    const uint16_t* qrow = rr.qlow + (size_t)qlow_row(q) * rr.pitch;
+    for (int j = warp; j < n; j += MERGE_THREADS / 32) {
+        const long long row = (long long)key_id<PRS_TIE_LOW_ID>(buf[j]);
+        float acc = 0.f;
+        for (int ch = lane; ch < (rr.pitch >> 3); ch += 32) {
+            const uint4 xv = __ldg(reinterpret_cast<const uint4*>(rr.x + t64_offset(row, ch, rr.pitch)));
+            const uint4 qv = __ldg(reinterpret_cast<const uint4*>(qrow + ch * 8));
+            float xf[8], qf[8];
+            cvt8(xv, rr.is_bf16, xf);
+            cvt8(qv, rr.is_bf16, qf);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { const float t = qf[e] - xf[e]; acc = fmaf(t, t, acc); }
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) dd[j] = (acc == acc) ? acc : INFINITY;          // NaN rows sort last, ordered by id
+    }
+}
+
 __global__ void __launch_bounds__(MERGE_THREADS) merge_cand_kernel(
     const u64* __restrict__ cand, int parts, int nq, int k, int sortn,
-    int out_mode, const float* __restrict__ qnorm, long long id_offset, float* __restrict__ D,
+    int out_mode, const float* __restrict__ qnorm, long long id_offset, const Rerank rr, float* __restrict__ D,
     long long* __restrict__ I) {
     extern __shared__ __align__(16) unsigned char msm[];
     u64* buf = reinterpret_cast<u64*>(msm);
     u64* heads = buf + sortn;
     int* s_n = reinterpret_cast<int*>(heads + MERGE_THREADS);
+    float* dd = reinterpret_cast<float*>(s_n + 4);               // [k] direct-form distances (re-rank only)
     const int q = blockIdx.x, tid = threadIdx.x;
     // every (part, query) list has all k slots written, empty ones as key 0 (scan kernels' contract)
     auto fetch = [&](long long i) -> u64 {
@@ -77,6 +130,29 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_cand_kernel(
         return __ldcg(cand + ((size_t)part * nq + q) * k + j);
     };
     const int n = block_topk_lists(fetch, parts, k, k, buf, sortn, heads, s_n, tid);
+    if (out_mode == 2 && rr.x) {
+        __syncthreads();
+        direct_l2_of_keys(buf, n, rr, q, dd, tid);
+        __syncthreads();
+        // order by (distance asc, id asc): rank counting (n <= 1024; ids are unique)
+        for (int j = tid; j < k; j += MERGE_THREADS) {
+            if (j < n) {
+                const float dj = dd[j];
+                const uint32_t idj = key_id<PRS_TIE_LOW_ID>(buf[j]);
+                int rank = 0;
+                for (int i = 0; i < n; ++i) {
+                    const float di = dd[i];
+                    rank += (di < dj) || (di == dj && key_id<PRS_TIE_LOW_ID>(buf[i]) < idj);
+                }
+                D[(size_t)q * k + rank] = dj;
+                I[(size_t)q * k + rank] = (long long)idj + id_offset;
+            } else {
+                D[(size_t)q * k + j] = 3.402823466e+38f;
+                I[(size_t)q * k + j] = -1;
+            }
+        }
+        return;
+    }
     for (int j = tid; j < k; j += MERGE_THREADS) {
         float dv;
         long long iv;

@@ -3,7 +3,7 @@
 //
 // Every rank owns an exchange buffer (cudaMalloc, shared with the other ranks of the box through
 // CUDA IPC, i.e. mapped peer memory over NVLink / NVSwitch):
-//     vals [2 slots][G ranks][cap] float      ids [2][G][cap] int64      flags [2][G][nq_cap] uint32
+//     vals, vals2 [2 slots][G ranks][cap] float      ids [2][G][cap] int64      flags [2][G][nq_cap] uint32
 // CTA q of rank r merges the per-CTA candidate lists of its local scan into the local top-k of
 // query q, STORES that list into slot[.][r] of every rank's buffer (plain st.global on mapped peer
 // pointers, 12*k bytes per peer), fences at system scope and publishes flag = generation; then it
@@ -22,6 +22,7 @@ constexpr int XCHG_MAX_RANKS = 16;
 
 struct XchgView {
     float* vals[XCHG_MAX_RANKS];          // base of rank p's vals array (peer-mapped; [rank] is local)
+    float* vals2[XCHG_MAX_RANKS];         // second value per entry: the direct-form L2 distance (16-bit L2 re-rank)
     long long* ids[XCHG_MAX_RANKS];
     uint32_t* flags[XCHG_MAX_RANKS];
     long long cap;                        // entries per (slot, rank)
@@ -41,18 +42,32 @@ __device__ __forceinline__ uint32_t ld_relaxed_sys(const uint32_t* p) {
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 
 // out_mode as in merge_cand_kernel.  largest: 1 for IP, 0 for L2 (order of the exchanged values).
+// rr.x != nullptr (16-bit storage, L2): the global SELECTION still runs on the expanded-form values
+// -- so the selected set is the unsharded index's, whatever the partition -- while each entry also
+// carries its direct-form distance (vals2), which becomes the output value and the final order.
+// status: host-mapped word; set to 1 when a peer's lists did not arrive within timeout_ns -- the
+// query's output is then the empty-result sentinel (ids -1), never a merge of stale lists.
 __global__ void __launch_bounds__(MERGE_THREADS) merge_xchg_kernel(
     const u64* __restrict__ cand, int parts, int nq, int k, int sortn,
-    int out_mode, const float* __restrict__ qnorm, long long id_offset, int largest,
-    const XchgView xv, uint32_t gen, float* __restrict__ D, long long* __restrict__ I, int* __restrict__ status) {
+    int out_mode, const float* __restrict__ qnorm, long long id_offset, int largest, const Rerank rr,
+    const XchgView xv, uint32_t gen, unsigned long long timeout_ns, float* __restrict__ D, long long* __restrict__ I,
+    volatile int* status) {
     extern __shared__ __align__(16) unsigned char msm[];
     u64* buf = reinterpret_cast<u64*>(msm);
     u64* heads = buf + sortn;
-    int* s_n = reinterpret_cast<int*>(heads + MERGE_THREADS);
+    int* s_n = reinterpret_cast<int*>(heads + MERGE_THREADS);      // [0..1] block_topk_lists, [2] timeout flag
+    float* dd = reinterpret_cast<float*>(s_n + 4);                 // [k]
+    long long* ids_s = reinterpret_cast<long long*>(dd + ((k + 1) & ~1));   // [k]
     const int q = blockIdx.x, tid = threadIdx.x;
     const int G = xv.G, slot = (int)(gen & 1u);
+    const bool rerank = out_mode == 2 && rr.x != nullptr;
 
     // ---- 1. local merge over this rank's CTAs ----
     auto fetch = [&](long long i) -> u64 {
@@ -60,12 +75,20 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_xchg_kernel(
         return __ldcg(cand + ((size_t)part * nq + q) * k + j);
     };
     const int n = block_topk_lists(fetch, parts, k, k, buf, sortn, heads, s_n, tid);
+    if (tid == 0) s_n[2] = 0;
+    if (rerank) {
+        __syncthreads();
+        direct_l2_of_keys(buf, n, rr, q, dd, tid);
+    }
+    __syncthreads();
     // keep the local list in registers: buf is reused by the second merge
     u64 mine[(PRS_MAX_K + MERGE_THREADS - 1) / MERGE_THREADS];
+    float mine_dd[(PRS_MAX_K + MERGE_THREADS - 1) / MERGE_THREADS];
 #pragma unroll
     for (int r = 0; r < (PRS_MAX_K + MERGE_THREADS - 1) / MERGE_THREADS; ++r) {
         const int j = tid + r * MERGE_THREADS;
         mine[r] = (j < n) ? buf[j] : 0ull;
+        mine_dd[r] = (rerank && j < n) ? dd[j] : 0.f;
     }
 
     // ---- 2. push the local list into every rank's buffer (slot, my rank, query q) ----
@@ -88,6 +111,7 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_xchg_kernel(
         for (int p = 0; p < G; ++p) {
             xv.vals[p][ebase + j] = dv;
             xv.ids[p][ebase + j] = iv;
+            if (rerank) xv.vals2[p][ebase + j] = mine_dd[r];
         }
     }
     // bar.sync orders the CTA's stores before the flag writers; st.release.sys is cumulative, so the
@@ -97,17 +121,32 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_xchg_kernel(
     // ---- 3. wait for the other ranks' lists of this query (they arrive in MY memory) ----
     if (tid < G) {
         const uint32_t* f = xv.flags[xv.rank] + ((size_t)slot * G + tid) * xv.nq_cap + q;
-        long long spins = 0;
+        unsigned long long t0 = 0;
+        int spins = 0;
         while (ld_relaxed_sys(f) != gen) {
             __nanosleep(32);
-            if (++spins > (1ll << 24)) { atomicExch(status, 1); break; }      // ~1 s: a peer died or never searched
+            if ((++spins & 1023) == 0) {                                      // look at the clock every ~50 us
+                const unsigned long long now = global_timer_ns();
+                if (!t0) t0 = now;
+                else if (now - t0 > timeout_ns) { s_n[2] = 1; break; }        // a peer died or never searched
+            }
         }
         (void)ld_acquire_sys(f);                                              // order the list reads after the flag
     }
     __syncthreads();
+    if (s_n[2]) {
+        // never merge stale or partial lists: this query answers "nothing found" and the host is told
+        for (int j = tid; j < k; j += MERGE_THREADS) {
+            D[(size_t)q * k + j] = largest ? -3.402823466e+38f : 3.402823466e+38f;
+            I[(size_t)q * k + j] = -1;
+        }
+        if (tid == 0) { *status = 1; __threadfence_system(); }
+        return;
+    }
 
     // ---- 4. merge the G lists (positions order ties like the global id does: shards hold ascending blocks) ----
     const float* Dp = xv.vals[xv.rank] + (size_t)slot * G * (size_t)xv.cap;
+    const float* Dp2 = xv.vals2[xv.rank] + (size_t)slot * G * (size_t)xv.cap;
     const long long* Ip = xv.ids[xv.rank] + (size_t)slot * G * (size_t)xv.cap;
     auto fetch2 = [&](long long i) -> u64 {
         const int part = (int)(i / k), j = (int)(i - (long long)part * k);
@@ -117,8 +156,33 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_xchg_kernel(
         const float s = sanitize(largest ? v : -v);
         return ((u64)f2ord(s) << 32) | (u64)(~(uint32_t)(part * k + j));
     };
-    __syncthreads();
     const int n2 = block_topk_lists(fetch2, G, k, k, buf, sortn, heads, s_n, tid);
+    if (rerank) {
+        // selected by the expanded form; output the direct-form distances ordered by (distance, global id)
+        __syncthreads();
+        for (int j = tid; j < n2; j += MERGE_THREADS) {
+            const uint32_t pos = ~(uint32_t)buf[j];
+            const int part = (int)(pos / k), jj = (int)(pos - (uint32_t)part * k);
+            const size_t o = (size_t)part * (size_t)xv.cap + (size_t)q * k + jj;
+            dd[j] = __ldcg(Dp2 + o);
+            ids_s[j] = __ldcg(Ip + o);
+        }
+        __syncthreads();
+        for (int j = tid; j < k; j += MERGE_THREADS) {
+            if (j < n2) {
+                const float dj = dd[j];
+                const long long idj = ids_s[j];
+                int rank = 0;
+                for (int i = 0; i < n2; ++i) rank += (dd[i] < dj) || (dd[i] == dj && ids_s[i] < idj);
+                D[(size_t)q * k + rank] = dj;
+                I[(size_t)q * k + rank] = idj;
+            } else {
+                D[(size_t)q * k + j] = 3.402823466e+38f;
+                I[(size_t)q * k + j] = -1;
+            }
+        }
+        return;
+    }
     for (int j = tid; j < k; j += MERGE_THREADS) {
         if (j < n2) {
             const uint32_t pos = ~(uint32_t)buf[j];

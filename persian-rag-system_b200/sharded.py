@@ -125,6 +125,16 @@ class ShardedFlatIndex:
         self.offset = int(global_offset)
         self.local.set_id_offset(self.offset)
         self.ntotal_global = int(n_total_global)
+        # every rank must hold its block before anyone searches: the fused exchange waits (bounded) for
+        # the peers' lists, and a rank still building its shard would make the others time out
+        if self.world > 1:
+            self.dist.barrier(group=self.group)
+
+    def set_exchange_timeout(self, seconds: float) -> None:
+        """How long a fused search waits for a peer's lists (default 2 s).  A search that gives up
+        returns ids -1 for the affected queries and the NEXT search (or `check_exchange`) raises."""
+        for x in self._xs:
+            check(_lib.lib().prs_xchg_set_timeout_ms(x, max(1, int(seconds * 1000))))
 
     @property
     def ntotal(self) -> int:

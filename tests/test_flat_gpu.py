@@ -95,6 +95,71 @@ def test_write_index_is_byte_exact_faiss_file(P, gold_dir, tmp_path):
     assert m2 == O.METRIC_IP and np.array_equal(x2, x)
 
 
+# ------------------------------------------------------------------ BASELINE configs[0] on 16-bit storage
+@pytest.mark.parametrize("storage", ["fp16", "bf16"])
+def test_golden_indices_16bit_l2_c1_queries(P, golden_indices, storage):
+    """The reference's own indices (125/121 rows, d = 384/512/768, ||x||^2 up to ~25), squared L2 like
+    the reference (src/retrieval.py:102), 1 000 C1 queries (seeded Gaussian perturbations of
+    cyclic rows), k = 5, 16-bit storage on the tcgen05 scan.  Checked tie-aware at the north-star
+    tolerance (1e-3 relative) against float64 scores of the STORED rows and rounded queries."""
+    from oracle.make_golden import make_queries
+    for t, (name, (x, _)) in enumerate(sorted(golden_indices.items())):
+        q = make_queries(x, 1000, seed=100 + t)
+        idx = P.FlatIndex(x.shape[1], P.METRIC_L2, storage)
+        idx.add(x)
+        D, I = idx.search(q, 5)
+        assert idx.last_path == "tcgen05"
+        xs, qs = _round_to(x, storage), _round_to(q, storage)
+        S = O.flat_scores_f64(xs, qs, O.METRIC_L2)
+        flips = 0
+        for r in range(q.shape[0]):
+            flips += O.check_topk_against_scores(I[r], D[r], S[r], 5, False, rtol=RTOL_16, atol=1e-6, what=f"{name} {storage} q{r}")
+        assert flips <= 5, (name, flips)                    # positions where two distances tie within fp32 rounding
+        # the reference's call shape: one query per search (nq = 1 takes the same kernel, no cluster)
+        for r in range(0, 1000, 97):
+            D1, I1 = idx.search(q[r:r + 1], 5)
+            assert np.array_equal(I1[0], I[r]) and np.array_equal(D1[0], D[r])
+        # the fp32 exact-parity index on the same queries: same neighbours wherever 16-bit rounding keeps
+        # the distances apart (sanity of the storage mode, not a parity claim)
+        ref = P.FlatIndex(x.shape[1], P.METRIC_L2, "fp32")
+        ref.add(x)
+        D32, I32 = ref.search(q, 5)
+        assert (I32[:, 0] == I[:, 0]).mean() > 0.98
+
+
+@pytest.mark.parametrize("storage", ["fp16", "bf16"])
+def test_16bit_l2_near_duplicate_rows_get_direct_form_distances(P, golden_indices, storage):
+    """SURVEY findings 2/7: fine-tuned indices hold near-duplicate rows (squared distances down to 5e-5
+    at ||x||^2 ~ 25) where the expanded form ||q||^2 + ||x||^2 - 2q.x loses every digit in fp32.  The
+    merge recomputes the selected rows' distances in the direct form: self-distance is exactly 0 and the
+    neighbours' distances are right to 1e-3 relative even at 1e-5 absolute."""
+    name = "paraphrase-multilingual-MiniLM-L12-v2_finetuned_drugs_word_chunks.index"
+    x, _ = golden_indices[name]
+    rng = np.random.default_rng(5)
+    xs = _round_to(x, storage)
+    # rows 0..19 get a twin that differs by a few storage ulps in 8 coordinates
+    twins = xs[:20].copy()
+    cols = rng.integers(0, x.shape[1], size=(20, 8))
+    for i in range(20):
+        twins[i, cols[i]] = np.nextafter(_round_to(twins[i, cols[i]] * (1 + 2.0 ** (-7 if storage == "bf16" else -10)), storage),
+                                         np.float32(np.inf)).astype(np.float32)
+    twins = _round_to(twins, storage)
+    corpus = np.concatenate([xs, twins])
+    idx = P.FlatIndex(x.shape[1], P.METRIC_L2, storage)
+    idx.add(corpus)
+    q = corpus[:40].copy()
+    q[20:40] = twins
+    D, I = idx.search(q, 4)
+    assert idx.last_path == "tcgen05"
+    S = O.flat_scores_f64(corpus, q, O.METRIC_L2)
+    for r in range(40):
+        O.check_topk_against_scores(I[r], D[r], S[r], 4, False, rtol=RTOL_16, atol=1e-7, what=f"twin q{r}")
+    assert (D[:, 0] == 0).all()                              # direct form: the row itself is at exactly 0
+    assert (I[:20, 0] == np.arange(20)).all() and (I[20:40, 0] == corpus.shape[0] - 20 + np.arange(20)).all()
+    assert (I[:20, 1] == corpus.shape[0] - 20 + np.arange(20)).all()          # then its twin
+    assert ((D[:20, 1] > 0) & (D[:20, 1] < 1e-2)).all()
+
+
 # ------------------------------------------------------------------ shapes and edge cases
 @pytest.mark.parametrize("n,d,nq,k", [(1, 8, 1, 1), (3, 5, 2, 5), (257, 100, 3, 7), (1000, 384, 1, 10),
                                       (1000, 384, 17, 10), (4099, 512, 9, 100), (2500, 768, 5, 33),
@@ -245,20 +310,31 @@ def test_tcgen05_wide_k_vs_oracle(P, n, d, nq, k, metric, storage):
         O.check_topk_against_scores(I[r], D[r], S[r], k, metric == O.METRIC_IP, rtol=RTOL_16, atol=2e-5, what=f"wide q{r}")
 
 
-def test_tcgen05_wide_k_pathological_duplicates_fall_back_exactly(P):
-    """Thousands of identical rows tie with the threshold: the collection buffers overflow and the
-    search must fall back to the exact CUDA-core scan (ties then ordered by ascending row id)."""
+def test_tcgen05_wide_k_pathological_duplicates_stay_exact(P):
+    """Tens of thousands of identical rows tie with the threshold: the per-(CTA, query) collection slices
+    fill up, their owner threads compact them to their k best and raise the threshold, and the result is
+    still exact (ties ordered by ascending row id) -- on the tcgen05 path, with no host synchronisation."""
     rng = np.random.default_rng(3)
-    base = rng.standard_normal((40000, 128)).astype(np.float32)
+    base = rng.standard_normal((120000, 128)).astype(np.float32)
     base /= np.linalg.norm(base, axis=1, keepdims=True)
     x = base.copy()
-    x[5000:25000] = x[0]                               # 20 000 copies of row 0
+    x[5000:105000] = x[0]                              # 100 000 copies of row 0: ~675 per CTA against slices of 256
     idx = P.FlatIndex(128, P.METRIC_IP, "fp16")
     idx.add(x)
-    D, I = idx.search(x[:1], 100)
-    assert idx.last_path == "cuda-core"
-    want = [0] + list(range(5000, 5099))
-    assert I[0].tolist() == want and np.allclose(D[0], D[0, 0])
+    for k in (100, 17):
+        D, I = idx.search(x[:3], k)
+        assert idx.last_path == "tcgen05"
+        want = [0] + list(range(5000, 5000 + k - 1))
+        assert I[0].tolist() == want and np.allclose(D[0], D[0, 0])
+        xs, qs = _round_to(x, "fp16"), _round_to(x[:3], "fp16")
+        S = O.flat_scores_f64(xs, qs, O.METRIC_IP)
+        for r in (1, 2):
+            O.check_topk_against_scores(I[r], D[r], S[r], k, True, rtol=RTOL_16, atol=2e-5, what=f"dups q{r}")
+    # L2 as well (the merge re-ranks the selected rows in the direct form: all duplicates at exactly 0)
+    l2 = P.FlatIndex(128, P.METRIC_L2, "fp16")
+    l2.add(x)
+    D, I = l2.search(x[:1], 40)
+    assert I[0].tolist() == [0] + list(range(5000, 5039)) and (D[0] == 0).all()
 
 
 @pytest.mark.parametrize("storage", ["fp16", "bf16"])

@@ -163,3 +163,49 @@ def test_threshold_restatement_equals_blocked_numpy_restatement():
             assert np.array_equal(Ia, Ib) and np.array_equal(Da, Db)
     Da, Ia = O.flat_search_np_threshold(x[:7], q, 10, O.METRIC_L2)
     assert (Ia[:, 7:] == -1).all() and (Ia[:, :7] >= 0).all()
+
+
+# ------------------------------------------------------------------------------------------------
+# Pins against the REAL third-party libraries.  They are absent from this image (no wheel, no
+# network), so these tests skip today; the day faiss-cpu / rank_bm25 become importable (site-packages
+# or baseline/_ref/) they run and the "parity unpinned" note in oracle/ and DESIGN.md can go.
+# ------------------------------------------------------------------------------------------------
+def test_restated_flat_search_equals_real_faiss(gold_dir, golden_indices):
+    if O.reference_library("faiss") is None:
+        pytest.skip("faiss-cpu (requirements.txt:9 of the reference) is not importable here: parity unpinned")
+    g = np.load(os.path.join(gold_dir, "flat_golden.npz"))
+    for t, f in enumerate(g["files"].tolist()):
+        x, _ = golden_indices[f]
+        q = g[f"q_{t}"]
+        for metric in (O.METRIC_L2, O.METRIC_IP):
+            for nq in (1, 19, 64):                          # < 20: direct form; >= 20: expanded (sgemm) form
+                for k in (1, 5, 20, x.shape[0] + 3):        # k > N: -1 padding
+                    Df, If = O.faiss_search(x, q[:nq], k, metric)
+                    Dc, Ic = O.flat_search_c(x, q[:nq], k, metric, form=0)
+                    O.check_topk_lists(Ic, Dc, If, Df, rtol=1e-5, atol=1e-6, what=f"{f} nq{nq} k{k}")
+                    assert np.array_equal(If == -1, Ic == -1)
+    # duplicates: at equal value faiss keeps the lower id (scan order)
+    base = np.random.default_rng(3).standard_normal((5, 48)).astype(np.float32)
+    x = np.concatenate([base, base, base])
+    for metric in (O.METRIC_L2, O.METRIC_IP):
+        Df, If = O.faiss_search(x, base, 3, metric)
+        Dc, Ic = O.flat_search_c(x, base, 3, metric)
+        assert np.array_equal(np.sort(If, 1), np.sort(Ic, 1))
+
+
+def test_restated_bm25_equals_real_rank_bm25(golden_texts):
+    mod = O.reference_library("rank_bm25")
+    if mod is None:
+        pytest.skip("rank_bm25 (requirements.txt:5 of the reference) is not importable here: parity unpinned")
+    chunks, queries = golden_texts
+    corpus = [c["text"].split() for c in chunks]
+    real, mine = mod.BM25Okapi(corpus), O.BM25OkapiOracle(corpus)
+    for q in queries:
+        assert np.array_equal(real.get_scores(q.split()), mine.get_scores(q.split()))
+
+
+def test_reference_library_probe_is_quiet_when_absent():
+    assert O.reference_library("surely_not_a_module_of_this_image") is None
+    if O.reference_library("faiss") is None:
+        with pytest.raises(RuntimeError):
+            O.faiss_search(np.zeros((2, 4), np.float32), np.zeros((1, 4), np.float32), 1)

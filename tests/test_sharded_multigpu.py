@@ -1,0 +1,109 @@
+"""GPU, >= 2 devices: the row-sharded search on REAL peer GPUs (one process per GPU, spawned here) --
+`merge_xchg_kernel` (fused local merge + NVLink peer-memory exchange + global merge) and the NCCL
+all-gather variant -- must equal the unsharded index bit for bit on every rank, including ties on
+global ids across shard boundaries, 16-bit L2 (direct-form re-rank), wide k and slot alternation.
+Skipped on a single-GPU box (there `test_retrieval_gpu.py::test_sharded_equals_unsharded` runs emulated
+shards through the non-fused merge kernel)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _ngpu():
+    try:
+        import torch
+        return torch.cuda.device_count() if torch.cuda.is_available() else 0
+    except Exception:
+        return 0
+
+
+CASES = [  # n, d, nq, k, storage, metric (0 IP, 1 L2)
+    (20000, 128, 33, 10, "fp16", 0), (20000, 128, 33, 10, "fp16", 1), (5000, 64, 7, 100, "fp16", 1),
+    (3000, 96, 5, 10, "fp32", 1), (50000, 768, 128, 10, "bf16", 0), (1000, 64, 300, 16, "fp16", 0),
+    (40000, 384, 64, 5, "bf16", 1),
+]
+
+
+def _worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    import persian_rag_system_b200 as P
+    from persian_rag_system_b200.sharded import ShardedFlatIndex, shard_bounds
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    bad = []
+    for exchange in ("p2p", "nccl"):
+        for (n, d, nq, k, storage, metric) in CASES:
+            rng = np.random.default_rng(n + d)                 # same data on every rank
+            base = rng.standard_normal((n, d)).astype(np.float32)
+            base[n // 2: n // 2 + 50] = base[:50]              # duplicates across shard boundaries -> ties on global id
+            q = rng.standard_normal((nq, d)).astype(np.float32)
+            q[:5] = base[:5]
+            whole = P.FlatIndex(d, metric, storage, device=rank)
+            whole.add(base)
+            qd = torch.from_numpy(q).to(dev)
+            Dw, Iw = whole.search(qd, k)
+            sh = ShardedFlatIndex(d, metric, storage, device=rank, exchange=exchange, nq_cap=512, k_cap=128)
+            lo, hi = shard_bounds(n, world, rank)
+            sh.add_local(base[lo:hi], lo, n)
+            ok = True
+            for rep in range(3):                               # slot alternation / generation counter
+                D, I = sh.search(qd, k)
+                ok = ok and bool(torch.equal(I, Iw)) and bool(torch.equal(D, Dw))
+            sh.check_exchange()
+            flag = torch.tensor([1 if ok else 0], device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if not flag.item():
+                bad.append((exchange, n, d, nq, k, storage, metric))
+            del sh, whole
+    # a peer that never searches: the fused exchange gives up after the timeout, answers -1 and reports
+    sh = ShardedFlatIndex(32, 1, "fp16", device=rank, exchange="p2p", nq_cap=8, k_cap=16, lanes=1)
+    x = np.random.default_rng(1).standard_normal((256, 32)).astype(np.float32)
+    lo, hi = shard_bounds(256, world, rank)
+    sh.add_local(x[lo:hi], lo, 256)
+    sh.set_exchange_timeout(0.2)
+    timeout_ok = True
+    if rank == 0:
+        D, I = sh.search(torch.from_numpy(x[:4]).to(dev), 5)
+        torch.cuda.synchronize()
+        timeout_ok = bool((I == -1).all().item())
+        try:
+            sh.check_exchange()
+            timeout_ok = False                                  # must raise
+        except P.PrsError:
+            pass
+    dist.barrier()
+    np.save(os.path.join(out_dir, f"r{rank}.npy"), np.array([len(bad), int(timeout_ok)]))
+    if bad:
+        print(f"rank {rank}: MISMATCH {bad}", flush=True)
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(_ngpu() < 2, reason="needs >= 2 GPUs on one box (gpurun --gpus 2)")
+@pytest.mark.timeout(900)
+def test_sharded_search_on_real_gpus_equals_unsharded(tmp_path):
+    import torch.multiprocessing as mp
+    world = min(_ngpu(), 8)
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        res = np.load(tmp_path / f"r{r}.npy")
+        assert res[0] == 0, f"rank {r}: {res[0]} sharded cases differ from the unsharded index"
+        assert res[1] == 1, f"rank {r}: timeout handling"
