@@ -179,9 +179,34 @@ int64_t prs_sparse_nnz(const prs_sparse* sp);
  * S: [nq, k] float64 scores, I: [nq, k] int64 doc ids (-1 padded).  Host pointers. */
 int prs_sparse_search_host(prs_sparse* sp, const int64_t* q_indptr, const int32_t* q_terms,
                            const double* q_weights, int64_t nq, int k, double* S, int64_t* I);
+/* same with the query CSR and the outputs on the device; asynchronous on `stream` (searches on one index are
+ * ordered one after the other: they share its workspace).  This is what the hybrid fusion consumes. */
+int prs_sparse_search_device(prs_sparse* sp, const int64_t* q_indptr, const int32_t* q_terms,
+                             const double* q_weights, int64_t nq, int k, double* S, int64_t* I, void* stream);
+/* scoring kernel: 0 = exact order (default: float64 accumulation in query-entry order, the summation order of
+ * rank_bm25 / scipy), 1 = throughput (queries batched per CTA share their postings, fixed-point accumulation
+ * with shared-memory integer atomics, k + 16 candidates).  Both re-score their candidates exactly in float64,
+ * so the returned scores are bit-identical; the id lists can differ only among docs whose scores tie to ~1e-7. */
+int prs_sparse_set_mode(prs_sparse* sp, int mode);
+int prs_sparse_mode(const prs_sparse* sp);
 /* sum of postings touched by the last search (8 or 12 bytes each): the algorithmic bytes */
 int64_t prs_sparse_last_postings(const prs_sparse* sp);
 int prs_sparse_set_id_offset(prs_sparse* sp, int64_t id_offset);
+
+/* ---------------------------------------------------------------------------------------
+ * Hybrid fusion (dense + BM25), batched, on the device.
+ * replaces: the fusion loop of retrieve_hybrid        src/retrieval.py:181-216
+ * Inputs are the two top-2k lists of every query as the search entry points above leave them on the
+ * device: D_dense/I_dense [nq, kd] (squared L2 ascending -> similarity 1/(1+d), src/retrieval.py:108) and
+ * S_sparse/I_sparse [nq, ks] (BM25 scores).  Row ids outside [0, n_chunks) are dropped (:106).  Each list is
+ * divided by its own maximum (0 if that is not positive), weighted, summed per row id; the union is ordered
+ * by fused score descending, ties in insertion order (dense hits first, then BM25-only hits -- Python's
+ * stable sort over the reference's dict), and cut to top_k.  S_out [nq, top_k] float64, I_out [nq, top_k]
+ * int64 (-1 padded).  Asynchronous on `stream`.
+ * ------------------------------------------------------------------------------------- */
+int prs_hybrid_fuse_device(const float* D_dense, const int64_t* I_dense, int kd, const double* S_sparse,
+                           const int64_t* I_sparse, int ks, int64_t nq, int64_t n_chunks, double dense_weight,
+                           double sparse_weight, int top_k, double* S_out, int64_t* I_out, int device, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * Encoder output epilogue: attention-masked mean pooling (+ optional L2 normalisation).

@@ -12,12 +12,13 @@ from .flat import FlatIndex, IndexFlatIP, IndexFlatL2, read_index, write_index
 from .index_build import create_model_embeddings, index_path_for, setup_faiss_index
 from .sparse import BM25Index, SparseIndex, TfidfIndex
 from .pooling import mean_pool_normalize
+from .hybrid import hybrid_fuse
 from .retrieval import MultiModelRetrieval, RetrievalSystem
 from .sharded import ShardedFlatIndex
 
 __all__ = [
     "FlatIndex", "IndexFlatL2", "IndexFlatIP", "read_index", "write_index",
-    "SparseIndex", "BM25Index", "TfidfIndex", "mean_pool_normalize",
+    "SparseIndex", "BM25Index", "TfidfIndex", "mean_pool_normalize", "hybrid_fuse",
     "RetrievalSystem", "MultiModelRetrieval", "ShardedFlatIndex", "create_model_embeddings", "setup_faiss_index", "index_path_for",
     "METRIC_L2", "METRIC_INNER_PRODUCT", "METRIC_IP", "F32", "F16", "BF16", "F64", "MAX_K", "PrsError", "build", "lib",
 ]

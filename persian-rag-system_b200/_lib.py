@@ -57,8 +57,13 @@ SIGNATURES = {
     "prs_sparse_ndocs": (c_i64, [c_void_p]),
     "prs_sparse_nnz": (c_i64, [c_void_p]),
     "prs_sparse_search_host": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_int, c_void_p, c_void_p]),
+    "prs_sparse_search_device": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_int, c_void_p, c_void_p, c_void_p]),
+    "prs_sparse_set_mode": (c_int, [c_void_p, c_int]),
+    "prs_sparse_mode": (c_int, [c_void_p]),
     "prs_sparse_last_postings": (c_i64, [c_void_p]),
     "prs_sparse_set_id_offset": (c_int, [c_void_p, c_i64]),
+    "prs_hybrid_fuse_device": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_i64, c_i64, ctypes.c_double, ctypes.c_double,
+                                       c_int, c_void_p, c_void_p, c_int, c_void_p]),
     "prs_pool_norm": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
 }
 

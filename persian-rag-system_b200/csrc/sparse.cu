@@ -13,11 +13,25 @@
 // doc ids and weights, no atomics: a term lists a doc once), then streams the tile's scores --
 // zero scores included, like the reference -- through a block-level top-k.  The dense score
 // vector never reaches HBM.  Ties: (score desc, doc id DESC) == np.argsort(kind="stable")[::-1].
+//
+// Two scoring kernels share the index, the merge and the exact re-score:
+//   sparse_score_kernel          "exact" mode: float64 accumulation in query-entry order (rank_bm25 /
+//                                scipy summation order), one query per CTA;
+//   sparse_score_batched_kernel  "throughput" mode: 8 queries per CTA share every posting they have in
+//                                common (one load feeds all of them), accumulation in 32-bit FIXED POINT
+//                                with native shared-memory integer atomics (order independent, hence
+//                                deterministic, no barriers between query entries), per-term tile offsets
+//                                precomputed at build time instead of searched.
+// Both select k + SP_MARGIN candidates per query on their (rounded) selection keys; the candidates are
+// then re-scored exactly in float64, ordered by (score desc, id desc) and cut to k -- so the returned
+// scores are bit-exact in both modes and the rounding of the selection key can only matter when more
+// than SP_MARGIN docs tie with the k-th score to ~1e-7 relative (inside the 1e-5 tolerance).
 #include <algorithm>
 #include <type_traits>
 #include <cerrno>
 #include <mutex>
 #include <new>
+#include <thread>
 #include <vector>
 
 #include "common.cuh"
@@ -268,11 +282,11 @@ __global__ void __launch_bounds__(SP_THREADS) sparse_merge_kernel(const u64* __r
 }
 
 // exact float64 score of each selected doc (same entry order as the scan), then order the k
-// results of a query by (score desc, id desc) on the float64 values.
+// candidates of a query by (score desc, id desc) on the float64 values and keep the k_out best.
 template <typename VT>
 __global__ void sparse_rescore_kernel(const long long* __restrict__ tptr, const int* __restrict__ pdoc, const VT* __restrict__ pval,
                                       int n_terms, const long long* __restrict__ q_indptr, const int* __restrict__ q_terms,
-                                      const double* __restrict__ q_weights, int k, const long long* __restrict__ I_in,
+                                      const double* __restrict__ q_weights, int k, int k_out, const long long* __restrict__ I_in,
                                       long long id_offset, double* __restrict__ S, long long* __restrict__ I) {
     extern __shared__ __align__(16) unsigned char rsm[];
     double* sc = reinterpret_cast<double*>(rsm);                 // [k]
@@ -307,9 +321,326 @@ __global__ void sparse_rescore_kernel(const long long* __restrict__ tptr, const 
                 if (sc[i] > s || (sc[i] == s && ids[i] > id)) ++rank;
             }
         }
-        S[(size_t)q * k + rank] = (id < 0) ? 0.0 : s;
-        I[(size_t)q * k + rank] = (id < 0) ? -1ll : id + id_offset;
+        if (rank < k_out) {                                  // k candidates (k_out + margin) in, the k_out best out
+            S[(size_t)q * k_out + rank] = (id < 0) ? 0.0 : s;
+            I[(size_t)q * k_out + rank] = (id < 0) ? -1ll : id + id_offset;
+        }
     }
+}
+
+// ==============================================================================================
+// Throughput mode
+// ==============================================================================================
+constexpr int SP_MARGIN = 16;          // extra candidates selected per query before the exact re-score
+constexpr int SB_QG = 8;               // queries per CTA
+constexpr int SB_TD = 2048;            // docs per accumulator tile
+constexpr int SB_THREADS = 512;
+constexpr int SB_NW = SB_THREADS / 32;
+constexpr int SB_QLEN = 64;            // query entries per slot resolved per round
+constexpr int SB_MAXE = SB_QG * SB_QLEN;
+constexpr int SB_CAP = 256;            // candidate keys per slot: 32 lanes x 8, compacted by a warp sort
+constexpr int SB_MAXKK = 96;           // k + SP_MARGIN this kernel supports (CAP - 32 - kk slots of headroom)
+constexpr int SB_CHUNK = 128;          // postings per warp step (4 per lane in flight)
+
+struct SbParams {
+    const long long* tptr; const int* pdoc; const float* pval; const float* maxw;
+    const int* skip_row; const uint32_t* skip; long long n_tiles;      // tiles of SB_TD docs
+    long long n_docs; int n_terms;
+    const long long* q_indptr; const int* q_terms; const double* q_weights;
+    int nq, kk;
+    u64* cand; int* cand_cnt;          // [parts][nq][kk]
+};
+
+constexpr size_t SB_SMEM = (size_t)SB_QG * SB_TD * 4 + (size_t)SB_QG * SB_CAP * 8 + (size_t)SB_MAXE * 8 /*skey*/ +
+                           (size_t)SB_MAXE * 8 /*u_base*/ + (size_t)SB_MAXE * 4 * 5 /*u_len,u_cur,u_end,u_row,w0*/ +
+                           (size_t)(SB_MAXE + 1) * 4 * 2 /*u_seg,pre*/ + (size_t)SB_MAXE * 4 /*e_scale*/ + SB_MAXE /*e_slot*/ + 256;
+
+__global__ void __launch_bounds__(SB_THREADS, 2) sparse_score_batched_kernel(const SbParams p) {
+    extern __shared__ __align__(16) unsigned char sbm[];
+    int* acc = reinterpret_cast<int*>(sbm);                                  // [QG][TD] fixed-point scores
+    u64* cbuf = reinterpret_cast<u64*>(acc + SB_QG * SB_TD);                 // [QG][CAP]
+    u64* skey = cbuf + SB_QG * SB_CAP;                                       // [MAXE]
+    long long* u_base = reinterpret_cast<long long*>(skey + SB_MAXE);        // [MAXE] tptr[t]
+    uint32_t* u_len = reinterpret_cast<uint32_t*>(u_base + SB_MAXE);         // [MAXE] df(t)
+    uint32_t* u_cur = u_len + SB_MAXE;                                       // [MAXE] tile range (relative to u_base)
+    uint32_t* u_end = u_cur + SB_MAXE;
+    int* u_row = reinterpret_cast<int*>(u_end + SB_MAXE);                    // [MAXE] row of the tile-offset table or -1
+    float* w0 = reinterpret_cast<float*>(u_row + SB_MAXE);                   // [MAXE] entry weights before the sort
+    int* u_seg = reinterpret_cast<int*>(w0 + SB_MAXE);                       // [MAXE+1] first sorted entry of unique term u
+    int* pre = u_seg + SB_MAXE + 1;                                          // [MAXE+1] postings of this tile before term u
+    float* e_scale = reinterpret_cast<float*>(pre + SB_MAXE + 1);            // [MAXE] sorted entries: weight * slot scale
+    unsigned char* e_slot = reinterpret_cast<unsigned char*>(e_scale + SB_MAXE);   // [MAXE]
+    int* misc = reinterpret_cast<int*>(e_slot + SB_MAXE);                    // [0] U, [1] E, [2..17] warp totals, [20..27] slot scale (float)
+    float* s_scale = reinterpret_cast<float*>(misc + 20);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int q0 = (int)blockIdx.x * SB_QG;                                  // first query of this group
+    const int part = blockIdx.y, nparts = gridDim.y;
+    const long long tiles_per = (p.n_tiles + nparts - 1) / nparts;
+    const long long tile0 = (long long)part * tiles_per;
+    const long long tile1 = (tile0 + tiles_per < p.n_tiles) ? tile0 + tiles_per : p.n_tiles;
+
+    // ---- per slot: entry count, fixed-point scale 2^30 / (upper bound of |score|) ----
+    int my_len = 0;                                                          // thread s < QG: entries of slot s
+    if (tid < SB_QG) {
+        const int q = q0 + tid;
+        float scale = 0.f;
+        if (q < p.nq) {
+            const long long a = p.q_indptr[q], b = p.q_indptr[q + 1];
+            my_len = (int)(b - a);
+            double bound = 0.0;
+            for (long long e = a; e < b; ++e) {
+                const int t = p.q_terms[e];
+                if (t >= 0 && t < p.n_terms) bound += fabs(p.q_weights[e]) * (double)p.maxw[t];
+            }
+            if (bound > 0.0) scale = (float)(1073741824.0 / bound);
+        }
+        s_scale[tid] = scale;
+        misc[2 + tid] = my_len;
+    }
+    __syncthreads();
+    int max_len = 0;
+#pragma unroll
+    for (int s = 0; s < SB_QG; ++s) max_len = max(max_len, misc[2 + s]);
+    const int rounds = (max_len + SB_QLEN - 1) / SB_QLEN;
+    const bool persistent = rounds <= 1;                                     // the usual case: cursors live across tiles
+    __syncthreads();
+
+    // ---- table of the unique terms of round r: sorted entries, segments, posting-list geometry ----
+    auto build_table = [&](int r) {
+        {
+            const int slot = tid / SB_QLEN, j = tid % SB_QLEN + r * SB_QLEN;
+            const int q = q0 + slot;
+            u64 key = 0ull;
+            float w = 0.f;
+            if (q < p.nq) {
+                const long long a = p.q_indptr[q], b = p.q_indptr[q + 1];
+                if (a + j < b) {
+                    const int t = p.q_terms[a + j];
+                    if (t >= 0 && t < p.n_terms && p.tptr[t + 1] > p.tptr[t]) {
+                        key = ((u64)(uint32_t)(t + 1) << 32) | (u64)(uint32_t)tid;
+                        w = (float)p.q_weights[a + j];
+                    }
+                }
+            }
+            skey[tid] = key;
+            w0[tid] = w;
+        }
+        __syncthreads();
+        block_sort_desc(skey, SB_MAXE, tid, SB_THREADS, 1);
+        // heads of the unique-term segments (sorted descending by term; empty keys last)
+        const u64 key = skey[tid];
+        const bool valid = key != 0ull;
+        const bool head = valid && (tid == 0 || (uint32_t)(skey[tid - 1] >> 32) != (uint32_t)(key >> 32));
+        const unsigned hb = __ballot_sync(0xffffffffu, head), vb = __ballot_sync(0xffffffffu, valid);
+        if (lane == 0) { misc[2 + warp] = __popc(hb); }
+        if (tid == 0) { misc[1] = 0; }
+        __syncthreads();
+        int before = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < SB_NW; ++w) { const int c = misc[2 + w]; before += (w < warp) ? c : 0; total += c; }
+        const int u = before + __popc(hb & ((1u << lane) - 1u));
+        if (valid) {
+            const int orig = (int)(uint32_t)key;
+            const int slot = orig / SB_QLEN;
+            e_slot[tid] = (unsigned char)slot;
+            e_scale[tid] = w0[orig] * s_scale[slot];
+        }
+        if (lane == 0 && vb) atomicAdd(&misc[1], __popc(vb));
+        if (head) {
+            const int t = (int)(uint32_t)(key >> 32) - 1;
+            const long long b0 = p.tptr[t];
+            u_seg[u] = tid;
+            u_base[u] = b0;
+            u_len[u] = (uint32_t)(p.tptr[t + 1] - b0);
+            u_row[u] = p.skip_row[t];
+        }
+        if (tid == 0) misc[0] = total;
+        __syncthreads();
+        if (tid == 0) u_seg[misc[0]] = misc[1];
+        __syncthreads();
+    };
+    // first posting of term u (relative) whose doc is >= bound
+    auto lower_bound_rel = [&](int u, long long bound, uint32_t l, uint32_t r) -> uint32_t {
+        const int* d = p.pdoc + u_base[u];
+        while (l < r) { const uint32_t mid = (l + r) >> 1; if ((long long)d[mid] < bound) l = mid + 1; else r = mid; }
+        return l;
+    };
+
+    // candidate list of slot `warp` (warps 0..QG-1): count and admission key live in registers
+    int ccount = 0;
+    u64 cthr = 0ull;
+    u64* myc = cbuf + (size_t)(warp < SB_QG ? warp : 0) * SB_CAP;
+    auto compact = [&]() {                                 // warp-level: keep the kk best of the slot's list
+        u64 v[SB_CAP / 32];
+#pragma unroll
+        for (int i = 0; i < SB_CAP / 32; ++i) { const int e = lane * (SB_CAP / 32) + i; v[i] = e < ccount ? myc[e] : 0ull; }
+        __syncwarp();
+        warp_sort_desc<SB_CAP / 32>(v, lane);
+#pragma unroll
+        for (int i = 0; i < SB_CAP / 32; ++i) myc[lane * (SB_CAP / 32) + i] = v[i];
+        __syncwarp();
+        ccount = ccount < p.kk ? ccount : p.kk;
+        cthr = ccount == p.kk ? myc[p.kk - 1] : 0ull;
+    };
+
+    if (persistent && rounds == 1) {
+        build_table(0);
+        const int U = misc[0];
+        if (tid < U && u_row[tid] < 0) u_end[tid] = lower_bound_rel(tid, tile1 * SB_TD, 0u, u_len[tid]);
+        __syncthreads();
+    }
+
+    // Tiles are visited in DESCENDING doc order: a later doc then has a lower id and loses every tie
+    // (score desc, id DESC), so floods of equal scores (all-zero queries) stop entering the lists once
+    // they hold kk entries.
+    for (long long tile = tile1 - 1; tile >= tile0; --tile) {
+        const long long lo = tile * SB_TD;
+        const long long hi = (lo + SB_TD < p.n_docs) ? lo + SB_TD : p.n_docs;
+        const int nd = (int)(hi - lo);
+        {
+            int4* z = reinterpret_cast<int4*>(acc);
+            for (int i = tid; i < SB_QG * SB_TD / 4; i += SB_THREADS) z[i] = make_int4(0, 0, 0, 0);
+        }
+        for (int r = 0; r < (rounds > 0 ? rounds : 0); ++r) {
+            if (!persistent) build_table(r);
+            const int U = misc[0];
+            // ---- this tile's posting range of every unique term ----
+            int cnt = 0;
+            if (tid < U) {
+                uint32_t c, e;
+                const int row = u_row[tid];
+                if (row >= 0) {
+                    const uint32_t* sk = p.skip + (size_t)row * (size_t)(p.n_tiles + 1) + tile;
+                    c = __ldg(sk); e = __ldg(sk + 1);
+                } else if (persistent) {
+                    e = u_end[tid];
+                    if (e == 0u || (long long)p.pdoc[u_base[tid] + e - 1] < lo) c = e;               // nothing in this tile
+                    else c = lower_bound_rel(tid, lo, e > (uint32_t)SB_TD ? e - SB_TD : 0u, e);
+                } else {
+                    c = lower_bound_rel(tid, lo, 0u, u_len[tid]);
+                    e = lower_bound_rel(tid, hi, c, u_len[tid]);
+                }
+                u_cur[tid] = c; u_end[tid] = e;
+                cnt = (int)(e - c);
+            }
+            // exclusive prefix over the U counts
+            int inc = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+            if (lane == 31) misc[2 + warp] = inc;
+            __syncthreads();
+            int before = 0, total = 0;
+#pragma unroll
+            for (int w = 0; w < SB_NW; ++w) { const int c = misc[2 + w]; before += (w < warp) ? c : 0; total += c; }
+            if (tid < U) pre[tid] = before + inc - cnt;
+            if (tid == 0) pre[U] = total;
+            __syncthreads();
+            // ---- posting phase: warps take chunks of the flattened postings of this tile ----
+            const int P = total;
+            for (int i0 = warp * SB_CHUNK; i0 < P; i0 += SB_NW * SB_CHUNK) {
+                const int i1 = (i0 + SB_CHUNK < P) ? i0 + SB_CHUNK : P;
+                int ul = 0, ur = U;                                 // last u with pre[u] <= i0
+                while (ur - ul > 1) { const int mid = (ul + ur) >> 1; if (pre[mid] <= i0) ul = mid; else ur = mid; }
+                int u = ul, i = i0;
+                while (i < i1) {
+                    while (pre[u + 1] <= i) ++u;
+                    const int segend = (i1 < pre[u + 1]) ? i1 : pre[u + 1];
+                    const long long g = u_base[u] + (long long)u_cur[u] + (i - pre[u]);
+                    const int n = segend - i;
+                    int dl[SB_CHUNK / 32];
+                    float pv[SB_CHUNK / 32];
+#pragma unroll
+                    for (int j = 0; j < SB_CHUNK / 32; ++j) {
+                        const int off = lane + 32 * j;
+                        dl[j] = off < n ? __ldg(p.pdoc + g + off) - (int)lo : -1;
+                        pv[j] = off < n ? __ldg(p.pval + g + off) : 0.f;
+                    }
+                    const int e1 = u_seg[u + 1];
+                    for (int e = u_seg[u]; e < e1; ++e) {
+                        const float sc = e_scale[e];
+                        int* row = acc + (int)e_slot[e] * SB_TD;
+#pragma unroll
+                        for (int j = 0; j < SB_CHUNK / 32; ++j)
+                            if (dl[j] >= 0) atomicAdd(row + dl[j], __float2int_rn(pv[j] * sc));
+                    }
+                    i = segend;
+                }
+            }
+            __syncthreads();
+            if (persistent && tid < U) u_end[tid] = u_cur[tid];      // descending tiles: this tile's start is the next one's end
+        }
+        __syncthreads();
+        // ---- selection: warp s scans the tile's scores of slot s ----
+        if (warp < SB_QG && q0 + warp < p.nq) {
+            const int* row = acc + warp * SB_TD;
+            for (int b = 0; b < nd; b += 32) {
+                const int i = b + lane;
+                u64 key = 0ull;
+                if (i < nd) key = ((u64)((uint32_t)row[i] ^ 0x80000000u) << 32) | (u64)(uint32_t)(lo + i);
+                const bool pred = key > cthr;
+                const unsigned m = __ballot_sync(0xffffffffu, pred);
+                if (m) {
+                    if (pred) myc[ccount + __popc(m & ((1u << lane) - 1u))] = key;
+                    ccount += __popc(m);
+                    __syncwarp();
+                    if (ccount > SB_CAP - 32) compact();
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (warp < SB_QG && q0 + warp < p.nq) {
+        compact();
+        const size_t o = (size_t)part * p.nq + (q0 + warp);
+        for (int j = lane; j < p.kk; j += 32) p.cand[o * p.kk + j] = j < ccount ? myc[j] : 0ull;
+        if (lane == 0) p.cand_cnt[o] = ccount;
+    }
+}
+
+// ---- build-time helpers of the throughput mode ----
+// largest |weight| of every term (one warp per term): bounds a query's score for the fixed-point scale
+template <typename VT>
+__global__ void term_maxw_kernel(const long long* __restrict__ tptr, const VT* __restrict__ pval, int n_terms, float* __restrict__ maxw) {
+    const int t = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    if (t >= n_terms) return;
+    float m = 0.f;
+    for (long long i = tptr[t] + lane; i < tptr[t + 1]; i += 32) m = fmaxf(m, fabsf((float)pval[i]));
+#pragma unroll
+    for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    // round up so that float rounding of the weights can never exceed the bound
+    if (lane == 0) maxw[t] = m * 1.0000002f;
+}
+// tile-offset rows of the frequent terms: skip[row][j] = first posting (relative) with doc >= j * SB_TD
+__global__ void skip_fill_kernel(const long long* __restrict__ tptr, const int* __restrict__ pdoc, const int* __restrict__ row_term,
+                                 int n_rows, long long n_tiles, uint32_t* __restrict__ skip) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)n_rows * (n_tiles + 1)) return;
+    const int row = (int)(i / (n_tiles + 1));
+    const long long j = i - (long long)row * (n_tiles + 1);
+    const int t = row_term[row];
+    const long long b0 = tptr[t];
+    long long l = 0, r = tptr[t + 1] - b0;
+    const long long bound = j * SB_TD;
+    while (l < r) { const long long mid = (l + r) >> 1; if ((long long)pdoc[b0 + mid] < bound) l = mid + 1; else r = mid; }
+    skip[i] = (uint32_t)l;
+}
+__global__ void f64_to_f32_kernel(const double* __restrict__ in, long long n, float* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (float)in[i];
+}
+// postings a batch of queries touches (the algorithmic bytes of the search / 8): sum of df over its entries
+__global__ void count_postings_kernel(const long long* __restrict__ tptr, int n_terms, const long long* __restrict__ q_indptr,
+                                      const int* __restrict__ q_terms, int nq, unsigned long long* __restrict__ out) {
+    const long long ne = q_indptr[nq];
+    unsigned long long s = 0;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < ne; e += (long long)gridDim.x * blockDim.x) {
+        const int t = q_terms[e];
+        if (t >= 0 && t < n_terms) s += (unsigned long long)(tptr[t + 1] - tptr[t]);
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0 && s) atomicAdd(out, s);
 }
 
 }  // namespace prs
@@ -317,16 +648,152 @@ __global__ void sparse_rescore_kernel(const long long* __restrict__ tptr, const 
 using namespace prs;
 
 struct prs_sparse {
-    int device = 0, sm_count = 0, vdtype = PRS_F32;
+    int device = 0, sm_count = 0, vdtype = PRS_F32, mode = 0;
     long long n_docs = 0, nnz = 0, id_offset = 0, last_postings = 0;
     int n_terms = 0;
     long long* tptr = nullptr;
     int* pdoc = nullptr;
     void* pval = nullptr;
+    // throughput mode (built on first use): fp32 weights, per-term max |weight|, tile-offset rows
+    float* pval32 = nullptr;
+    float* maxw = nullptr;
+    int* skip_row = nullptr;
+    uint32_t* skip = nullptr;
+    long long n_tiles_td = 0;
+    bool fast_ready = false;
     std::vector<long long> h_tptr;
     std::mutex mu;
     DevBuf cand, cand_cnt, qptr, qterms, qw, dI, dI2, dS;
+    unsigned long long* h_count = nullptr;     // mapped host word: postings touched by the last device-side search
+    unsigned long long* d_count = nullptr;
+    bool count_on_device = false;
+    cudaEvent_t event = nullptr;               // searches share the workspace: each waits for the previous one
+    bool used = false;
 };
+
+// throughput-mode structures (needs a CUDA context on sp->device; called under sp->mu)
+static int sparse_prepare_fast(prs_sparse* sp) {
+    if (sp->fast_ready) return 0;
+    const long long nnz = std::max<long long>(sp->nnz, 1);
+    if (sp->vdtype == PRS_F64) {
+        PRS_CUDA(cudaMalloc(&sp->pval32, (size_t)nnz * 4));
+        f64_to_f32_kernel<<<(unsigned)((nnz + 255) / 256), 256>>>((const double*)sp->pval, sp->nnz, sp->pval32);
+        PRS_LAUNCH_CHECK();
+    }
+    PRS_CUDA(cudaMalloc(&sp->maxw, ((size_t)sp->n_terms + 1) * 4));
+    if (sp->n_terms > 0) {
+        const unsigned blocks = (unsigned)(((long long)sp->n_terms * 32 + 255) / 256);
+        if (sp->vdtype == PRS_F64) term_maxw_kernel<double><<<blocks, 256>>>(sp->tptr, (const double*)sp->pval, sp->n_terms, sp->maxw);
+        else term_maxw_kernel<float><<<blocks, 256>>>(sp->tptr, (const float*)sp->pval, sp->n_terms, sp->maxw);
+        PRS_LAUNCH_CHECK();
+    }
+    // tile-offset rows for terms frequent enough that a row (4 bytes per tile) is small next to their
+    // postings; the threshold doubles until the table fits a quarter of the index (at least 64 MB)
+    sp->n_tiles_td = (sp->n_docs + SB_TD - 1) / SB_TD;
+    const size_t row_bytes = (size_t)(sp->n_tiles_td + 1) * 4;
+    const size_t budget = std::max<size_t>((size_t)64 << 20, (size_t)sp->nnz * 2);
+    long long min_df = std::max<long long>(4096, 2 * sp->n_tiles_td);
+    std::vector<int> rows;
+    for (;;) {
+        rows.clear();
+        for (int t = 0; t < sp->n_terms; ++t) if (sp->h_tptr[(size_t)t + 1] - sp->h_tptr[t] >= min_df) rows.push_back(t);
+        if (rows.size() * row_bytes <= budget) break;
+        min_df *= 2;
+    }
+    std::vector<int> skip_row((size_t)sp->n_terms + 1, -1);
+    for (size_t r = 0; r < rows.size(); ++r) skip_row[rows[r]] = (int)r;
+    PRS_CUDA(cudaMalloc(&sp->skip_row, ((size_t)sp->n_terms + 1) * 4));
+    PRS_CUDA(cudaMemcpy(sp->skip_row, skip_row.data(), ((size_t)sp->n_terms + 1) * 4, cudaMemcpyHostToDevice));
+    PRS_CUDA(cudaMalloc(&sp->skip, std::max<size_t>(rows.size() * row_bytes, 256)));
+    if (!rows.empty()) {
+        int* d_rows = nullptr;
+        PRS_CUDA(cudaMalloc(&d_rows, rows.size() * 4));
+        PRS_CUDA(cudaMemcpy(d_rows, rows.data(), rows.size() * 4, cudaMemcpyHostToDevice));
+        const long long tot = (long long)rows.size() * (sp->n_tiles_td + 1);
+        skip_fill_kernel<<<(unsigned)((tot + 255) / 256), 256>>>(sp->tptr, sp->pdoc, d_rows, (int)rows.size(), sp->n_tiles_td, sp->skip);
+        PRS_LAUNCH_CHECK();
+        PRS_CUDA(cudaDeviceSynchronize());
+        cudaFree(d_rows);
+    }
+    PRS_CUDA(cudaDeviceSynchronize());
+    sp->fast_ready = true;
+    return 0;
+}
+
+// scoring + merge + exact re-score; all pointers on the device; asynchronous on `st` (called under sp->mu)
+static int sparse_search_core(prs_sparse* sp, const long long* d_qptr, const int* d_qterms, const double* d_qw, long long nq, int k,
+                              double* dS, long long* dI, cudaStream_t st) {
+    int rc;
+    const int kk = std::min(k + SP_MARGIN, PRS_MAX_K + SP_MARGIN);
+    const bool fast = sp->mode == 1 && kk <= SB_MAXKK;
+    if (fast && (rc = sparse_prepare_fast(sp))) return rc;
+    if (!sp->event) PRS_CUDA(cudaEventCreateWithFlags(&sp->event, cudaEventDisableTiming));
+    if (sp->used) PRS_CUDA(cudaStreamWaitEvent(st, sp->event, 0));
+    int parts;
+    const int sortn = next_pow2(kk + SP_THREADS);
+    if (fast) {
+        const long long groups = (nq + SB_QG - 1) / SB_QG;
+        long long want = ((long long)sp->sm_count * 2 * 8 + groups - 1) / groups;      // ~8 waves of 2 CTAs per SM
+        parts = (int)std::max<long long>(1, std::min<long long>(sp->n_tiles_td, want));
+    } else {
+        const long long n_tiles = (sp->n_docs + SP_TILE - 1) / SP_TILE;
+        long long want = ((long long)sp->sm_count * 3 * 4 + nq - 1) / nq;              // ~4 waves of 3 CTAs per SM
+        parts = (int)std::max<long long>(1, std::min<long long>(n_tiles, want));
+    }
+    if ((rc = sp->cand.ensure((size_t)parts * nq * kk * 8))) return rc;
+    if ((rc = sp->cand_cnt.ensure((size_t)parts * nq * 4))) return rc;
+    if ((rc = sp->dI.ensure((size_t)nq * kk * 8))) return rc;
+    if (fast) {
+        SbParams p;
+        p.tptr = sp->tptr; p.pdoc = sp->pdoc; p.pval = sp->vdtype == PRS_F64 ? sp->pval32 : (const float*)sp->pval; p.maxw = sp->maxw;
+        p.skip_row = sp->skip_row; p.skip = sp->skip; p.n_tiles = sp->n_tiles_td; p.n_docs = sp->n_docs; p.n_terms = sp->n_terms;
+        p.q_indptr = d_qptr; p.q_terms = d_qterms; p.q_weights = d_qw; p.nq = (int)nq; p.kk = kk;
+        p.cand = (u64*)sp->cand.p; p.cand_cnt = (int*)sp->cand_cnt.p;
+        PRS_CUDA(cudaFuncSetAttribute(sparse_score_batched_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SB_SMEM));
+        dim3 grid((unsigned)((nq + SB_QG - 1) / SB_QG), (unsigned)parts);
+        sparse_score_batched_kernel<<<grid, SB_THREADS, SB_SMEM, st>>>(p);
+        PRS_LAUNCH_CHECK();
+    } else {
+        const size_t smem = (size_t)SP_TILE * 8 + (size_t)sortn * 8 + SP_QCHUNK * 32 + 16;
+        dim3 grid((unsigned)parts, (unsigned)nq);
+        if (sp->vdtype == PRS_F64) {
+            PRS_CUDA(cudaFuncSetAttribute(sparse_score_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            sparse_score_kernel<double><<<grid, SP_THREADS, smem, st>>>(sp->tptr, sp->pdoc, (const double*)sp->pval, sp->n_docs, sp->n_terms,
+                                                                        d_qptr, d_qterms, d_qw, (int)nq, kk, sortn, (u64*)sp->cand.p, (int*)sp->cand_cnt.p);
+        } else {
+            PRS_CUDA(cudaFuncSetAttribute(sparse_score_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            sparse_score_kernel<float><<<grid, SP_THREADS, smem, st>>>(sp->tptr, sp->pdoc, (const float*)sp->pval, sp->n_docs, sp->n_terms,
+                                                                       d_qptr, d_qterms, d_qw, (int)nq, kk, sortn, (u64*)sp->cand.p, (int*)sp->cand_cnt.p);
+        }
+        PRS_LAUNCH_CHECK();
+    }
+    {
+        const size_t msmem = (size_t)sortn * 8 + 16;
+        PRS_CUDA(cudaFuncSetAttribute(sparse_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem));
+        sparse_merge_kernel<<<(unsigned)nq, SP_THREADS, msmem, st>>>((const u64*)sp->cand.p, (const int*)sp->cand_cnt.p, parts, (int)nq, kk,
+                                                                     sortn, (long long*)sp->dI.p);
+        PRS_LAUNCH_CHECK();
+    }
+    {
+        const size_t rsmem = (size_t)kk * 16;
+        const int nt = kk < 32 ? 32 : (kk > 256 ? 256 : (kk + 31) / 32 * 32);
+        if (sp->vdtype == PRS_F64)
+            sparse_rescore_kernel<double><<<(unsigned)nq, nt, rsmem, st>>>(sp->tptr, sp->pdoc, (const double*)sp->pval, sp->n_terms, d_qptr, d_qterms,
+                                                                           d_qw, kk, k, (const long long*)sp->dI.p, sp->id_offset, dS, dI);
+        else
+            sparse_rescore_kernel<float><<<(unsigned)nq, nt, rsmem, st>>>(sp->tptr, sp->pdoc, (const float*)sp->pval, sp->n_terms, d_qptr, d_qterms,
+                                                                          d_qw, kk, k, (const long long*)sp->dI.p, sp->id_offset, dS, dI);
+        PRS_LAUNCH_CHECK();
+    }
+    PRS_CUDA(cudaEventRecord(sp->event, st));
+    sp->used = true;
+    return 0;
+}
+
+__global__ void sparse_fill_empty_kernel(double* S, long long* I, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { S[i] = 0.0; I[i] = -1; }
+}
 
 extern "C" {
 
@@ -335,7 +802,7 @@ int prs_sparse_build(const int64_t* indptr, const int32_t* indices, const void* 
     if (!out) { set_error("sparse_build: out is null"); return PRS_EINVAL; }
     *out = nullptr;
     if (!indptr || n_docs < 0 || n_terms < 0 || (vdtype != PRS_F32 && vdtype != PRS_F64)) { set_error("sparse_build: bad arguments"); return PRS_EINVAL; }
-    if (n_docs > 0xFFFFFFFFll) { set_error("sparse_build: more than 2^32-1 docs per shard"); return PRS_EINVAL; }
+    if (n_docs > 0x7FFFFFFFll) { set_error("sparse_build: more than 2^31-1 docs per shard"); return PRS_EINVAL; }
     const long long nnz = indptr[n_docs];
     if (nnz < 0 || (nnz > 0 && (!indices || !values))) { set_error("sparse_build: bad CSR"); return PRS_EINVAL; }
     int arch = prs_device_arch(device);
@@ -344,7 +811,9 @@ int prs_sparse_build(const int64_t* indptr, const int32_t* indices, const void* 
     prs_sparse* sp = new (std::nothrow) prs_sparse();
     if (!sp) { set_error("out of host memory"); return PRS_ENOMEM; }
     sp->device = device; sp->vdtype = vdtype; sp->n_docs = n_docs; sp->n_terms = n_terms; sp->nnz = nnz;
-    // host transpose (counting sort by term; doc order inside a term stays ascending)
+    // host transpose (counting sort by term; doc order inside a term stays ascending).  The scatter is
+    // split over the host cores by TERM range: every thread walks the whole CSR but only places the
+    // postings of its own terms, so the writes of different threads never meet and no atomics are needed.
     const size_t vs = vdtype == PRS_F64 ? 8 : 4;
     std::vector<long long>& tptr = sp->h_tptr;
     std::vector<int> pdoc;
@@ -354,6 +823,8 @@ int prs_sparse_build(const int64_t* indptr, const int32_t* indices, const void* 
         pdoc.resize((size_t)std::max<long long>(nnz, 1));
         pval.resize((size_t)std::max<long long>(nnz, 1) * vs);
     } catch (...) { delete sp; set_error("out of host memory"); return PRS_ENOMEM; }
+    for (long long dct = 0; dct < n_docs; ++dct)
+        if (indptr[dct + 1] < indptr[dct]) { delete sp; set_error("sparse_build: indptr not monotone"); return PRS_EINVAL; }
     for (long long i = 0; i < nnz; ++i) {
         const int t = indices[i];
         if (t < 0 || t >= n_terms) { delete sp; set_error("sparse_build: term id %d out of range at nnz %lld", t, i); return PRS_EINVAL; }
@@ -361,14 +832,37 @@ int prs_sparse_build(const int64_t* indptr, const int32_t* indices, const void* 
     }
     for (int t = 0; t < n_terms; ++t) tptr[(size_t)t + 1] += tptr[t];
     {
-        std::vector<long long> fill(tptr.begin(), tptr.end() - 1);
-        for (long long dct = 0; dct < n_docs; ++dct) {
-            if (indptr[dct + 1] < indptr[dct]) { delete sp; set_error("sparse_build: indptr not monotone"); return PRS_EINVAL; }
-            for (long long i = indptr[dct]; i < indptr[dct + 1]; ++i) {
-                const long long pos = fill[indices[i]]++;
-                pdoc[(size_t)pos] = (int)dct;
-                memcpy(&pval[(size_t)pos * vs], (const unsigned char*)values + (size_t)i * vs, vs);
+        unsigned nthr = std::thread::hardware_concurrency();
+        if (nthr < 1) nthr = 1;
+        if (nthr > 32) nthr = 32;
+        if (nnz < (1 << 22)) nthr = 1;
+        // term ranges with about equal posting counts
+        std::vector<int> cut(nthr + 1, n_terms);
+        cut[0] = 0;
+        for (unsigned w = 1; w < nthr; ++w) {
+            const long long target = nnz / nthr * w;
+            cut[w] = (int)(std::lower_bound(tptr.begin(), tptr.end(), target) - tptr.begin());
+            if (cut[w] > n_terms) cut[w] = n_terms;
+            if (cut[w] < cut[w - 1]) cut[w] = cut[w - 1];
+        }
+        auto work = [&](int t_lo, int t_hi) {
+            if (t_lo >= t_hi) return;
+            std::vector<long long> fill(tptr.begin() + t_lo, tptr.begin() + t_hi);
+            for (long long dct = 0; dct < n_docs; ++dct) {
+                for (long long i = indptr[dct]; i < indptr[dct + 1]; ++i) {
+                    const int t = indices[i];
+                    if (t < t_lo || t >= t_hi) continue;
+                    const long long pos = fill[(size_t)(t - t_lo)]++;
+                    pdoc[(size_t)pos] = (int)dct;
+                    memcpy(&pval[(size_t)pos * vs], (const unsigned char*)values + (size_t)i * vs, vs);
+                }
             }
+        };
+        if (nthr == 1) work(0, n_terms);
+        else {
+            std::vector<std::thread> pool;
+            for (unsigned w = 0; w < nthr; ++w) pool.emplace_back(work, cut[w], cut[w + 1]);
+            for (auto& th : pool) th.join();
         }
     }
     DeviceGuard g(device);
@@ -383,12 +877,15 @@ int prs_sparse_build(const int64_t* indptr, const int32_t* indices, const void* 
         ok = cudaMemcpy(sp->pdoc, pdoc.data(), (size_t)nnz * 4, cudaMemcpyHostToDevice) == cudaSuccess &&
              cudaMemcpy(sp->pval, pval.data(), (size_t)nnz * vs, cudaMemcpyHostToDevice) == cudaSuccess;
     }
+    ok = ok && cudaHostAlloc((void**)&sp->h_count, 64, cudaHostAllocMapped) == cudaSuccess &&
+         cudaHostGetDevicePointer((void**)&sp->d_count, sp->h_count, 0) == cudaSuccess;
     if (!ok) {
         cudaGetLastError();
         set_error("sparse_build: device allocation / upload failed (%lld postings)", nnz);
         prs_sparse_free(sp);
         return PRS_ENOMEM;
     }
+    *sp->h_count = 0;
     *out = sp;
     return 0;
 }
@@ -396,9 +893,16 @@ int prs_sparse_build(const int64_t* indptr, const int32_t* indices, const void* 
 void prs_sparse_free(prs_sparse* sp) {
     if (!sp) return;
     DeviceGuard g(sp->device);
+    cudaDeviceSynchronize();
     if (sp->tptr) cudaFree(sp->tptr);
     if (sp->pdoc) cudaFree(sp->pdoc);
     if (sp->pval) cudaFree(sp->pval);
+    if (sp->pval32) cudaFree(sp->pval32);
+    if (sp->maxw) cudaFree(sp->maxw);
+    if (sp->skip_row) cudaFree(sp->skip_row);
+    if (sp->skip) cudaFree(sp->skip);
+    if (sp->h_count) cudaFreeHost(sp->h_count);
+    if (sp->event) cudaEventDestroy(sp->event);
     sp->cand.release(); sp->cand_cnt.release(); sp->qptr.release(); sp->qterms.release(); sp->qw.release();
     sp->dI.release(); sp->dI2.release(); sp->dS.release();
     delete sp;
@@ -406,18 +910,61 @@ void prs_sparse_free(prs_sparse* sp) {
 
 int64_t prs_sparse_ndocs(const prs_sparse* sp) { return sp ? sp->n_docs : -1; }
 int64_t prs_sparse_nnz(const prs_sparse* sp) { return sp ? sp->nnz : -1; }
-int64_t prs_sparse_last_postings(const prs_sparse* sp) { return sp ? sp->last_postings : -1; }
+int64_t prs_sparse_last_postings(const prs_sparse* sp) {
+    if (!sp) return -1;
+    if (sp->count_on_device) {                 // counted by a kernel of the last device-side search
+        DeviceGuard g(sp->device);
+        cudaDeviceSynchronize();
+        return (int64_t)*(volatile unsigned long long*)sp->h_count;
+    }
+    return sp->last_postings;
+}
 int prs_sparse_set_id_offset(prs_sparse* sp, int64_t off) {
     if (!sp) { set_error("null sparse index"); return PRS_EINVAL; }
     sp->id_offset = off;
     return 0;
 }
+int prs_sparse_set_mode(prs_sparse* sp, int mode) {
+    if (!sp || (mode != 0 && mode != 1)) { set_error("sparse_set_mode: mode must be 0 (exact order) or 1 (throughput)"); return PRS_EINVAL; }
+    DeviceGuard g(sp->device);
+    std::lock_guard<std::mutex> lock(sp->mu);
+    sp->mode = mode;
+    return mode == 1 ? sparse_prepare_fast(sp) : 0;
+}
+int prs_sparse_mode(const prs_sparse* sp) { return sp ? sp->mode : -1; }
 
-int prs_sparse_search_host(prs_sparse* sp, const int64_t* q_indptr, const int32_t* q_terms, const double* q_weights,
-                           int64_t nq, int k, double* S, int64_t* I) {
+static int sparse_check_args(prs_sparse* sp, int64_t nq, int k) {
     if (!sp) { set_error("null sparse index"); return PRS_EINVAL; }
     if (k < 1 || k > PRS_MAX_K) { set_error("sparse_search: k=%d out of range [1, %d]", k, PRS_MAX_K); return PRS_EINVAL; }
     if (nq < 0 || nq > 65535) { set_error("sparse_search: nq=%lld out of range [0, 65535] per call", (long long)nq); return PRS_EINVAL; }
+    return 0;
+}
+
+int prs_sparse_search_device(prs_sparse* sp, const int64_t* q_indptr, const int32_t* q_terms, const double* q_weights,
+                             int64_t nq, int k, double* S, int64_t* I, void* stream) {
+    int rc = sparse_check_args(sp, nq, k);
+    if (rc) return rc;
+    if (nq == 0) return 0;
+    if (!q_indptr || !S || !I) { set_error("sparse_search: null pointer"); return PRS_EINVAL; }
+    DeviceGuard g(sp->device);
+    std::lock_guard<std::mutex> lock(sp->mu);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (sp->n_docs == 0) {
+        sparse_fill_empty_kernel<<<(unsigned)((nq * k + 255) / 256), 256, 0, st>>>(S, (long long*)I, nq * k);
+        PRS_LAUNCH_CHECK();
+        return 0;
+    }
+    PRS_CUDA(cudaMemsetAsync(sp->d_count, 0, 8, st));
+    count_postings_kernel<<<64, 256, 0, st>>>(sp->tptr, sp->n_terms, (const long long*)q_indptr, q_terms, (int)nq, sp->d_count);
+    PRS_LAUNCH_CHECK();
+    sp->count_on_device = true;
+    return sparse_search_core(sp, (const long long*)q_indptr, q_terms, q_weights, nq, k, S, (long long*)I, st);
+}
+
+int prs_sparse_search_host(prs_sparse* sp, const int64_t* q_indptr, const int32_t* q_terms, const double* q_weights,
+                           int64_t nq, int k, double* S, int64_t* I) {
+    int rc = sparse_check_args(sp, nq, k);
+    if (rc) return rc;
     if (nq == 0) return 0;
     if (!q_indptr || !S || !I) { set_error("sparse_search: null pointer"); return PRS_EINVAL; }
     const long long ne = q_indptr[nq];
@@ -434,18 +981,10 @@ int prs_sparse_search_host(prs_sparse* sp, const int64_t* q_indptr, const int32_
         if (t >= 0 && t < sp->n_terms) touched += sp->h_tptr[(size_t)t + 1] - sp->h_tptr[t];
     }
     sp->last_postings = touched;
-    int rc;
-    const long long n_tiles = (sp->n_docs + SP_TILE - 1) / SP_TILE;
-    // enough CTAs to fill the machine, but never more parts than tiles
-    long long want = ((long long)sp->sm_count * 3 * 4 + nq - 1) / nq;       // ~4 waves of 3 CTAs per SM
-    if (want < 1) want = 1;
-    const int parts = (int)std::min<long long>(n_tiles, want);
+    sp->count_on_device = false;
     if ((rc = sp->qptr.ensure((size_t)(nq + 1) * 8))) return rc;
     if ((rc = sp->qterms.ensure((size_t)std::max<long long>(ne, 1) * 4))) return rc;
     if ((rc = sp->qw.ensure((size_t)std::max<long long>(ne, 1) * 8))) return rc;
-    if ((rc = sp->cand.ensure((size_t)parts * nq * k * 8))) return rc;
-    if ((rc = sp->cand_cnt.ensure((size_t)parts * nq * 4))) return rc;
-    if ((rc = sp->dI.ensure((size_t)nq * k * 8))) return rc;
     if ((rc = sp->dI2.ensure((size_t)nq * k * 8))) return rc;
     if ((rc = sp->dS.ensure((size_t)nq * k * 8))) return rc;
     PRS_CUDA(cudaMemcpyAsync(sp->qptr.p, q_indptr, (size_t)(nq + 1) * 8, cudaMemcpyHostToDevice, 0));
@@ -453,45 +992,8 @@ int prs_sparse_search_host(prs_sparse* sp, const int64_t* q_indptr, const int32_
         PRS_CUDA(cudaMemcpyAsync(sp->qterms.p, q_terms, (size_t)ne * 4, cudaMemcpyHostToDevice, 0));
         PRS_CUDA(cudaMemcpyAsync(sp->qw.p, q_weights, (size_t)ne * 8, cudaMemcpyHostToDevice, 0));
     }
-    const int sortn = next_pow2(k + SP_THREADS);
-    const size_t smem = (size_t)SP_TILE * 8 + (size_t)sortn * 8 + SP_QCHUNK * 32 + 16;
-    dim3 grid((unsigned)parts, (unsigned)nq);
-    if (sp->vdtype == PRS_F64) {
-        PRS_CUDA(cudaFuncSetAttribute(sparse_score_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        sparse_score_kernel<double><<<grid, SP_THREADS, smem, 0>>>(sp->tptr, sp->pdoc, (const double*)sp->pval, sp->n_docs, sp->n_terms,
-                                                                   (const long long*)sp->qptr.p, (const int*)sp->qterms.p,
-                                                                   (const double*)sp->qw.p, (int)nq, k, sortn, (u64*)sp->cand.p,
-                                                                   (int*)sp->cand_cnt.p);
-    } else {
-        PRS_CUDA(cudaFuncSetAttribute(sparse_score_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        sparse_score_kernel<float><<<grid, SP_THREADS, smem, 0>>>(sp->tptr, sp->pdoc, (const float*)sp->pval, sp->n_docs, sp->n_terms,
-                                                                  (const long long*)sp->qptr.p, (const int*)sp->qterms.p,
-                                                                  (const double*)sp->qw.p, (int)nq, k, sortn, (u64*)sp->cand.p,
-                                                                  (int*)sp->cand_cnt.p);
-    }
-    PRS_LAUNCH_CHECK();
-    {
-        const size_t msmem = (size_t)sortn * 8 + 16;
-        PRS_CUDA(cudaFuncSetAttribute(sparse_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem));
-        sparse_merge_kernel<<<(unsigned)nq, SP_THREADS, msmem, 0>>>((const u64*)sp->cand.p, (const int*)sp->cand_cnt.p, parts, (int)nq, k,
-                                                                    sortn, (long long*)sp->dI.p);
-        PRS_LAUNCH_CHECK();
-    }
-    {
-        const size_t rsmem = (size_t)k * 16;
-        const int nt = k < 32 ? 32 : (k > 256 ? 256 : (k + 31) / 32 * 32);
-        if (sp->vdtype == PRS_F64)
-            sparse_rescore_kernel<double><<<(unsigned)nq, nt, rsmem, 0>>>(sp->tptr, sp->pdoc, (const double*)sp->pval, sp->n_terms,
-                                                                          (const long long*)sp->qptr.p, (const int*)sp->qterms.p,
-                                                                          (const double*)sp->qw.p, k, (const long long*)sp->dI.p,
-                                                                          sp->id_offset, (double*)sp->dS.p, (long long*)sp->dI2.p);
-        else
-            sparse_rescore_kernel<float><<<(unsigned)nq, nt, rsmem, 0>>>(sp->tptr, sp->pdoc, (const float*)sp->pval, sp->n_terms,
-                                                                         (const long long*)sp->qptr.p, (const int*)sp->qterms.p,
-                                                                         (const double*)sp->qw.p, k, (const long long*)sp->dI.p,
-                                                                         sp->id_offset, (double*)sp->dS.p, (long long*)sp->dI2.p);
-        PRS_LAUNCH_CHECK();
-    }
+    if ((rc = sparse_search_core(sp, (const long long*)sp->qptr.p, (const int*)sp->qterms.p, (const double*)sp->qw.p, nq, k,
+                                 (double*)sp->dS.p, (long long*)sp->dI2.p, 0))) return rc;
     PRS_CUDA(cudaMemcpyAsync(S, sp->dS.p, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, 0));
     PRS_CUDA(cudaMemcpyAsync(I, sp->dI2.p, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, 0));
     PRS_CUDA(cudaStreamSynchronize(0));

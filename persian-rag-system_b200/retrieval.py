@@ -135,13 +135,50 @@ class RetrievalSystem:
         n = len(self.chunks)
         return [(self.chunks[int(r)], s) for r, s in zip(rows, scores) if 0 <= int(r) < n]
 
+    # ---------------------------------------------------------------- encoder hand-off
+    def _embed(self, texts: List[str]):
+        """Query embeddings the way the engine wants them: a CUDA tensor whenever the encoder can give one
+        (`encode_device` of pooling.FusedPoolingEncoder, or SentenceTransformer's `convert_to_tensor=True`),
+        so that the reference's device -> host -> device round trip at src/retrieval.py:98-102 disappears;
+        otherwise whatever `encode` returns (numpy for the stock call)."""
+        enc = self.embedding_model
+        if hasattr(enc, "encode_device"):
+            return enc.encode_device(list(texts))
+        try:
+            return enc.encode(list(texts), device=self.device, convert_to_tensor=True)
+        except TypeError:                                   # an encoder with the bare reference signature
+            return enc.encode(list(texts), device=self.device)
+
+    @staticmethod
+    def _on_device(x) -> bool:
+        return hasattr(x, "is_cuda") and bool(x.is_cuda)
+
+    def _dense_search(self, texts: List[str], k: int, want_device: bool = False):
+        """One encoder call and ONE corpus scan for all `texts`.  Embeddings that are already on the GPU go
+        straight into the scan kernel; only the [nq, k] results come back (numpy), unless `want_device`."""
+        emb = self._embed(texts)
+        if self._on_device(emb) or want_device:
+            import torch
+            if not self._on_device(emb):
+                if hasattr(emb, "detach"):
+                    emb = emb.detach().cpu().numpy()
+                emb = torch.from_numpy(np.ascontiguousarray(np.asarray(emb), dtype=np.float32)).to(f"cuda:{self.faiss_index.device}")
+            if emb.dim() == 1:
+                emb = emb[None, :]
+            if emb.dtype not in (torch.float32, torch.float16, torch.bfloat16):
+                emb = emb.float()
+            D, I = self.faiss_index.search(emb, k)
+            return (D, I) if want_device else (D.cpu().numpy(), I.cpu().numpy())
+        if hasattr(emb, "detach"):
+            emb = emb.detach().cpu().numpy()
+        return self.faiss_index.search(np.asarray(emb).astype("float32"), k)
+
     # ---------------------------------------------------------------- dense, src/retrieval.py:92-115
     @_guarded("dense retrieval", list)
     def retrieve_dense(self, query: str, top_k: int = 10) -> List[Tuple[Dict, float]]:
         if not self.embedding_model or not self.faiss_index:
             return []
-        q = np.asarray(self.embedding_model.encode([query], device=self.device)).astype("float32")
-        sq_l2, rows = self.faiss_index.search(q, top_k)
+        sq_l2, rows = self._dense_search([query], top_k)
         return self._rows_to_results(rows[0], 1 / (1 + sq_l2[0]))      # score = 1/(1+d), :108
 
     @_guarded("batched dense retrieval", list)
@@ -150,8 +187,7 @@ class RetrievalSystem:
         queries -- the reference loops `retrieve` per question (src/evaluation.py:273-299)."""
         if not self.embedding_model or not self.faiss_index or not queries:
             return [[] for _ in queries]
-        q = np.asarray(self.embedding_model.encode(list(queries), device=self.device)).astype("float32")
-        sq_l2, rows = self.faiss_index.search(q, top_k)
+        sq_l2, rows = self._dense_search(list(queries), top_k)
         return [self._rows_to_results(rows[i], 1 / (1 + sq_l2[i])) for i in range(len(queries))]
 
     # ---------------------------------------------------------------- sparse, src/retrieval.py:117-172
@@ -162,6 +198,14 @@ class RetrievalSystem:
         scores, rows = self.bm25_index.get_top_k(query.split(), top_k)
         return self._rows_to_results(rows, scores)
 
+    @_guarded("batched BM25 retrieval", list)
+    def retrieve_bm25_batch(self, queries: List[str], top_k: int = 10) -> List[List[Tuple[Dict, float]]]:
+        """Extension: every query of the batch in one scoring launch."""
+        if not self.bm25_index or not queries:
+            return [[] for _ in queries]
+        S, I = self.bm25_index.search([q.split() for q in queries], top_k)
+        return [self._rows_to_results(I[i][I[i] >= 0], S[i][I[i] >= 0]) for i in range(len(queries))]
+
     @_guarded("TF-IDF retrieval", list)
     def retrieve_tfidf(self, query: str, top_k: int = 10) -> List[Tuple[Dict, float]]:
         if not self.tfidf_vectorizer or self.tfidf_matrix is None:
@@ -169,23 +213,51 @@ class RetrievalSystem:
         scores, rows = self.tfidf_vectorizer.get_top_k(query, top_k)
         return self._rows_to_results(rows, scores)
 
+    @_guarded("batched TF-IDF retrieval", list)
+    def retrieve_tfidf_batch(self, queries: List[str], top_k: int = 10) -> List[List[Tuple[Dict, float]]]:
+        if not self.tfidf_vectorizer or self.tfidf_matrix is None or not queries:
+            return [[] for _ in queries]
+        S, I = self.tfidf_vectorizer.search(list(queries), top_k)
+        return [self._rows_to_results(I[i][I[i] >= 0], S[i][I[i] >= 0]) for i in range(len(queries))]
+
     # ---------------------------------------------------------------- hybrid, src/retrieval.py:174-220
     @_guarded("hybrid retrieval", list)
     def retrieve_hybrid(self, query: str, top_k: int = 10, dense_weight: float = 0.6,
                         bm25_weight: float = 0.4) -> List[Tuple[Dict, float]]:
-        # top-2k from each retriever, each list divided by its own maximum, weighted sum keyed by
-        # chunk id; dict order = dense hits first, then BM25-only hits; stable descending sort.
-        fused: Dict[Any, list] = {}
-        for hits, weight in ((self.retrieve_dense(query, 2 * top_k), dense_weight),
-                             (self.retrieve_bm25(query, 2 * top_k), bm25_weight)):
-            if not hits:
-                continue
-            peak = max(score for _, score in hits)
-            for chunk, score in hits:
-                entry = fused.setdefault(chunk["id"], [chunk, 0])
-                entry[1] = entry[1] + (score / peak if peak > 0 else 0) * weight
-        ranked = sorted(((c, s) for c, s in fused.values()), key=lambda cs: cs[1], reverse=True)
-        return ranked[:top_k]
+        out = self.retrieve_hybrid_batch([query], top_k, dense_weight, bm25_weight)
+        return out[0] if out else []
+
+    @_guarded("batched hybrid retrieval", list)
+    def retrieve_hybrid_batch(self, queries: List[str], top_k: int = 10, dense_weight: float = 0.6,
+                              bm25_weight: float = 0.4) -> List[List[Tuple[Dict, float]]]:
+        """The reference's fusion (top-2k of each retriever, each list divided by its own maximum, 0.6 / 0.4
+        weighted sum keyed by chunk, stable descending sort, src/retrieval.py:181-216) for a whole batch:
+        both top-2k lists stay in HBM and one kernel (csrc/hybrid.cu) fuses every query; only the final
+        [nq, k] lists are copied back.  A retriever that is missing or fails contributes an empty list,
+        exactly like the reference's guarded sub-calls."""
+        import torch
+        from .hybrid import hybrid_fuse
+        if not queries:
+            return []
+        nq, k2 = len(queries), 2 * int(top_k)
+        dev = torch.device("cuda", self.faiss_index.device if self.faiss_index else self.bm25_index.index.device)
+        D = torch.empty((nq, 0), dtype=torch.float32, device=dev)
+        Id = torch.empty((nq, 0), dtype=torch.int64, device=dev)
+        S = torch.empty((nq, 0), dtype=torch.float64, device=dev)
+        Is = torch.empty((nq, 0), dtype=torch.int64, device=dev)
+        if self.embedding_model and self.faiss_index:
+            try:
+                D, Id = self._dense_search(list(queries), k2, want_device=True)
+            except Exception as exc:                        # noqa: BLE001 - retrieve_dense's own net (:113-115)
+                print(f"Error in dense retrieval: {exc}")
+        if self.bm25_index:
+            try:
+                S, Is = self.bm25_index.search_device([q.split() for q in queries], k2)
+            except Exception as exc:                        # noqa: BLE001 - retrieve_bm25's own net (:141-143)
+                print(f"Error in BM25 retrieval: {exc}")
+        fused, rows = hybrid_fuse(D, Id, S, Is, len(self.chunks), top_k, dense_weight, bm25_weight)
+        fused, rows = fused.cpu().numpy(), rows.cpu().numpy()
+        return [[(self.chunks[int(r)], float(v)) for r, v in zip(rows[i], fused[i]) if r >= 0] for i in range(nq)]
 
     # ---------------------------------------------------------------- dispatcher, src/retrieval.py:222-238
     def retrieve(self, query: str, top_k: int = 10) -> List[Tuple[Dict, float]]:
@@ -197,11 +269,24 @@ class RetrievalSystem:
             return []
         return getattr(self, f"retrieve_{self.method}")(query, top_k)
 
+    def retrieve_batch(self, queries: List[str], top_k: int = 10) -> List[List[Tuple[Dict, float]]]:
+        """Extension: `retrieve` for a list of queries with ONE pass of the engine (one corpus scan / one
+        scoring launch for all of them).  Element i equals `retrieve(queries[i], top_k)`."""
+        queries = list(queries)
+        if not self.is_ready:
+            print("Retrieval system is not ready. Please load chunks and index first.")
+            return [[] for _ in queries]
+        if self.method not in _METHODS:
+            print(f"Unknown retrieval method: {self.method}")
+            return [[] for _ in queries]
+        out = getattr(self, f"retrieve_{self.method}_batch")(queries, top_k)
+        return out if len(out) == len(queries) else [[] for _ in queries]     # a failed batch == every query failed
+
     # ---------------------------------------------------------------- RAG contexts, src/retrieval.py:240-272
-    def get_contexts_for_rag(self, query: str, top_k: int = 5,
-                             max_context_length: int = 2000) -> Tuple[List[str], List[Dict]]:
+    @staticmethod
+    def _pack_contexts(retrieved, max_context_length: int) -> Tuple[List[str], List[Dict]]:
         contexts, metadata, budget = [], [], max_context_length
-        for chunk, score in self.retrieve(query, top_k):
+        for chunk, score in retrieved:
             text = chunk["text"]
             if len(text) > budget:                 # does not fit: keep a truncated tail only if > 100 chars remain
                 if budget <= 100:
@@ -215,17 +300,28 @@ class RetrievalSystem:
                 break
         return contexts, metadata
 
+    def get_contexts_for_rag(self, query: str, top_k: int = 5,
+                             max_context_length: int = 2000) -> Tuple[List[str], List[Dict]]:
+        return self._pack_contexts(self.retrieve(query, top_k), max_context_length)
+
+    def get_contexts_for_rag_batch(self, queries: List[str], top_k: int = 5,
+                                   max_context_length: int = 2000) -> List[Tuple[List[str], List[Dict]]]:
+        """Extension: the evaluator's per-question loop (src/evaluation.py:273-299) as one
+        batched retrieval; element i equals `get_contexts_for_rag(queries[i], ...)`."""
+        return [self._pack_contexts(hits, max_context_length) for hits in self.retrieve_batch(queries, top_k)]
+
     # ---------------------------------------------------------------- Hit@K / MRR, src/retrieval.py:274-323
     def evaluate_retrieval_quality(self, test_queries: List[Dict],
                                    relevant_chunks: Dict[str, List[str]]) -> Dict[str, float]:
         cuts = (1, 3, 5)
         hit_flags = {c: [] for c in cuts}
         reciprocal_ranks = []
-        for pos, item in enumerate(test_queries):
-            wanted = relevant_chunks.get(item.get("id", str(pos)), [])
-            if not wanted:                          # queries without labels are skipped (:291-292)
-                continue
-            got = [chunk["id"] for chunk, _ in self.retrieve(item["question"], top_k=10)]
+        # queries without labels are skipped (:291-292); all the others are retrieved in ONE batch
+        labelled = [(item, relevant_chunks.get(item.get("id", str(pos)), [])) for pos, item in enumerate(test_queries)]
+        labelled = [(item, wanted) for item, wanted in labelled if wanted]
+        batch = self.retrieve_batch([item["question"] for item, _ in labelled], top_k=10) if labelled else []
+        for (item, wanted), hits in zip(labelled, batch):
+            got = [chunk["id"] for chunk, _ in hits]
             for c in cuts:
                 hit_flags[c].append(any(cid in wanted for cid in got[:c]))
             first = next((rank for rank, cid in enumerate(got, 1) if cid in wanted), None)

@@ -24,7 +24,7 @@ from ._lib import F32, F64, PrsError, check
 class SparseIndex:
     """Doc-by-term CSR weights resident in HBM as term-major postings."""
 
-    def __init__(self, indptr, indices, values, n_terms: int, device: int | None = None):
+    def __init__(self, indptr, indices, values, n_terms: int, device: int | None = None, mode: str = "exact"):
         from .flat import _default_device
         self._L = _lib.lib()
         self._h = ctypes.c_void_p()
@@ -44,6 +44,19 @@ class SparseIndex:
         check(self._L.prs_sparse_build(indptr.ctypes.data_as(ctypes.c_void_p), indices.ctypes.data_as(ctypes.c_void_p),
                                        values.ctypes.data_as(ctypes.c_void_p), vd, int(indptr.shape[0] - 1), int(n_terms),
                                        self.device, ctypes.byref(self._h)))
+        self.set_mode(mode)
+
+    def set_mode(self, mode: str) -> None:
+        """"exact": float64 accumulation in query-entry order (rank_bm25 / scipy summation order), one
+        query per CTA.  "throughput": 8 queries per CTA share the postings they have in common,
+        fixed-point accumulation, k + 16 candidates.  Both re-score their candidates exactly in float64
+        (identical scores); id lists can differ only among docs whose scores tie to ~1e-7 relative."""
+        code = {"exact": 0, "throughput": 1, "fast": 1, 0: 0, 1: 1}[mode]
+        check(self._L.prs_sparse_set_mode(self._h, code))
+
+    @property
+    def mode(self) -> str:
+        return {0: "exact", 1: "throughput"}[int(self._L.prs_sparse_mode(self._h))]
 
     @property
     def ndocs(self) -> int:
@@ -82,6 +95,24 @@ class SparseIndex:
                                                  qw.ctypes.data_as(ctypes.c_void_p), b - a, int(k),
                                                  Sa.ctypes.data_as(ctypes.c_void_p), Ia.ctypes.data_as(ctypes.c_void_p)))
             S[a:b], I[a:b] = Sa, Ia
+        return S, I
+
+    def search_device(self, q_indptr, q_terms, q_weights, k: int):
+        """Same search with the query CSR given as CUDA tensors (int64 / int32 / float64) and the results
+        left on the device: (S float64 [nq, k], I int64 [nq, k]) CUDA tensors, asynchronous on the current
+        stream.  What the hybrid fusion kernel consumes (at most 65 535 queries per call)."""
+        import torch
+        dev = q_indptr.device
+        q_indptr = q_indptr.to(torch.int64).contiguous()
+        q_terms = q_terms.to(torch.int32).contiguous()
+        q_weights = q_weights.to(torch.float64).contiguous()
+        nq = int(q_indptr.shape[0] - 1)
+        S = torch.empty((nq, int(k)), dtype=torch.float64, device=dev)
+        I = torch.empty((nq, int(k)), dtype=torch.int64, device=dev)
+        st = torch.cuda.current_stream(dev).cuda_stream
+        check(self._L.prs_sparse_search_device(self._h, ctypes.c_void_p(q_indptr.data_ptr()), ctypes.c_void_p(q_terms.data_ptr()),
+                                               ctypes.c_void_p(q_weights.data_ptr()), nq, int(k), ctypes.c_void_p(S.data_ptr()),
+                                               ctypes.c_void_p(I.data_ptr()), ctypes.c_void_p(st)))
         return S, I
 
     def __del__(self):
@@ -156,14 +187,14 @@ class BM25Index:
     (8 B per posting, throughput mode)."""
 
     def __init__(self, corpus: Sequence[Sequence[str]], k1: float = 1.5, b: float = 0.75, epsilon: float = 0.25,
-                 dtype="float64", device: int | None = None):
+                 dtype="float64", device: int | None = None, mode: str = "exact"):
         self.k1, self.b, self.epsilon = k1, b, epsilon
         built = build_bm25_csr(corpus, k1, b, epsilon)
         self.corpus_size = len(corpus)
         self.vocab, self.idf, self.doc_len = built["vocab"], built["idf"], built["doc_len"]
         self.avgdl, self.average_idf = built["avgdl"], built["average_idf"]
         self.dtype = np.dtype(dtype)
-        self.index = SparseIndex(built["indptr"], built["indices"], built["weights"].astype(self.dtype), len(self.vocab), device)
+        self.index = SparseIndex(built["indptr"], built["indices"], built["weights"].astype(self.dtype), len(self.vocab), device, mode)
 
     def encode_queries(self, queries: Sequence[Sequence[str]]):
         q_indptr = np.zeros(len(queries) + 1, dtype=np.int64)
@@ -177,6 +208,13 @@ class BM25Index:
     def search(self, queries: Sequence[Sequence[str]], k: int):
         """Batch of tokenised queries -> (scores float64 [nq,k], doc ids int64 [nq,k])."""
         return self.index.search(*self.encode_queries(queries), k)
+
+    def search_device(self, queries: Sequence[Sequence[str]], k: int):
+        """Same, results left on the device as CUDA tensors (hybrid fusion input)."""
+        import torch
+        dev = torch.device("cuda", self.index.device)
+        ip, qt, qw = self.encode_queries(queries)
+        return self.index.search_device(torch.from_numpy(ip).to(dev), torch.from_numpy(qt).to(dev), torch.from_numpy(qw).to(dev), k)
 
     def get_top_k(self, query_tokens: Sequence[str], k: int):
         S, I = self.search([query_tokens], k)
@@ -329,11 +367,11 @@ class TfidfIndex(TfidfVectorizerHost):
     argsort top-k, with scoring and selection on the GPU."""
 
     def __init__(self, texts: Sequence[str], max_features: int | None = 10000, ngram_range=(1, 2), dtype="float64",
-                 device: int | None = None):
+                 device: int | None = None, mode: str = "exact"):
         super().__init__(max_features, ngram_range)
         indptr, indices, data = self.fit(texts)
         self.dtype = np.dtype(dtype)
-        self.index = SparseIndex(indptr, indices, data.astype(self.dtype), self.n_features, device)
+        self.index = SparseIndex(indptr, indices, data.astype(self.dtype), self.n_features, device, mode)
 
     def search(self, queries: Sequence[str], k: int):
         return self.index.search(*self.encode_queries(queries), k)

@@ -140,6 +140,75 @@ def test_hybrid_matches_reference_fusion(P, world):
         np.testing.assert_allclose([s for _, s in got], [s for _, s in want], rtol=1e-6)
 
 
+def test_hybrid_batch_on_device_equals_per_query_and_oracle(P, world):
+    """f-1: top-2k dense and top-2k BM25 lists stay in HBM, one kernel fuses the whole batch."""
+    import torch
+    r = P.RetrievalSystem(method="hybrid", encoder=FakeEncoder(world["table"], 384))
+    assert r.load_chunks_and_index(world["csv"], world["index"])
+    qs = [qd["question"] for qd in world["queries"]]
+    batch = r.retrieve_batch(qs, top_k=5)
+    assert len(batch) == len(qs)
+    bm = O.BM25OkapiOracle([t.split() for t in world["texts"]])
+    chunks = r.chunks
+    for i in range(0, len(qs), 5):
+        Dr, Ir = O.flat_search_c(world["x"], world["q"][i:i + 1], 10, O.METRIC_L2, form=1)
+        dense = [(chunks[j], 1 / (1 + d)) for d, j in zip(Dr[0], Ir[0])]
+        sc = bm.get_scores(qs[i].split())
+        sparse = [(chunks[j], sc[j]) for j in O.argsort_topk_canonical(sc, 10)]
+        want = O.hybrid_fuse(dense, sparse, 5)
+        assert [c["id"] for c, _ in batch[i]] == [c["id"] for c, _ in want]
+        np.testing.assert_allclose([s for _, s in batch[i]], [s for _, s in want], rtol=1e-6)
+        assert [c["id"] for c, _ in r.retrieve(qs[i], top_k=5)] == [c["id"] for c, _ in batch[i]]
+    # raw kernel: rows outside [0, n_chunks) are dropped before the maxima, stable order on ties, -1 padding
+    D = torch.tensor([[0.0, 1.0, 3.0, 7.0]], dtype=torch.float32, device="cuda")
+    Id = torch.tensor([[3, 99, 1, -1]], dtype=torch.int64, device="cuda")
+    S = torch.tensor([[4.0, 2.0, 0.0, 0.0]], dtype=torch.float64, device="cuda")
+    Is = torch.tensor([[1, 2, 0, 77]], dtype=torch.int64, device="cuda")
+    F, I = P.hybrid_fuse(D, Id, S, Is, n_chunks=10, top_k=6)
+    ch = [{"id": f"c{i}"} for i in range(10)]
+    want = O.hybrid_fuse([(ch[3], 1.0), (ch[1], 0.25)], [(ch[1], 4.0), (ch[2], 2.0), (ch[0], 0.0)], 6)
+    assert I[0].tolist() == [int(c["id"][1:]) for c, _ in want] + [-1, -1]
+    np.testing.assert_allclose(F[0, :4].cpu().numpy(), [s for _, s in want], rtol=1e-12)
+    # one retriever missing: the other list alone (reference: guarded sub-call returns [])
+    F, I = P.hybrid_fuse(D[:, :0], Id[:, :0], S, Is, n_chunks=10, top_k=3)
+    assert I[0].tolist() == [1, 2, 0] and F[0].tolist() == [0.4, 0.2, 0.0]
+    nodense = P.RetrievalSystem(method="hybrid", encoder=FakeEncoder(world["table"], 384))
+    assert nodense.load_chunks_and_index(world["csv"], "/no/such.index")
+    got = nodense.retrieve(qs[0], top_k=5)
+    sc = bm.get_scores(qs[0].split())
+    want = O.hybrid_fuse([], [(chunks[j], sc[j]) for j in O.argsort_topk_canonical(sc, 10)], 5)
+    assert [c["id"] for c, _ in got] == [c["id"] for c, _ in want]
+
+
+class DeviceEncoder(FakeEncoder):
+    """An encoder whose output is already on the GPU (what pooling.FusedPoolingEncoder.encode_device or
+    SentenceTransformer.encode(convert_to_tensor=True) return): no host copy of the embeddings may happen."""
+
+    def encode(self, sentences, device=None, convert_to_tensor=False, **_):
+        import torch
+        out = super().encode(sentences)
+        if not convert_to_tensor:
+            raise AssertionError("the retriever must ask for a tensor (convert_to_tensor=True)")
+        return torch.from_numpy(out).cuda()
+
+
+def test_device_resident_embeddings_go_straight_into_the_scan(P, world):
+    """f-3: src/retrieval.py:98-102 does device -> host -> device; here CUDA embeddings feed the scan kernel."""
+    host = P.RetrievalSystem(method="dense", encoder=FakeEncoder(world["table"], 384))
+    devr = P.RetrievalSystem(method="dense", encoder=DeviceEncoder(world["table"], 384), storage="fp32")
+    assert host.load_chunks_and_index(world["csv"], world["index"]) and devr.load_chunks_and_index(world["csv"], world["index"])
+    qs = [qd["question"] for qd in world["queries"][:24]]
+    a = host.retrieve_batch(qs, 7)
+    b = devr.retrieve_batch(qs, 7)
+    assert [[c["id"] for c, _ in h] for h in a] == [[c["id"] for c, _ in h] for h in b]
+    np.testing.assert_allclose([[s for _, s in h] for h in a], [[s for _, s in h] for h in b], rtol=1e-6)
+    assert [c["id"] for c, _ in devr.retrieve(qs[3], 7)] == [c["id"] for c, _ in b[3]]
+    # the evaluator's loop as one batch (src/evaluation.py:273-299): same contexts as the per-query calls
+    ctx = devr.get_contexts_for_rag_batch(qs[:6], top_k=5, max_context_length=2000)
+    assert ctx == [devr.get_contexts_for_rag(q, top_k=5, max_context_length=2000) for q in qs[:6]]
+    assert devr.evaluate_retrieval_quality(world["queries"], world["relevant"]) == host.evaluate_retrieval_quality(world["queries"], world["relevant"])
+
+
 def test_multi_model_retrieval(P, world):
     m = P.MultiModelRetrieval(["models/a-model"], encoders={"a-model": FakeEncoder(world["table"], 384)})
     m.setup_retrievers(world["csv"], {"a-model": world["index"]})

@@ -122,6 +122,98 @@ def test_sparse_raw_csr_api_large_docs_multi_tile(P):
         assert np.array_equal(S[r], sc[I[r]])
 
 
+# ------------------------------------------------------------------ throughput mode (batched queries, fixed-point selection)
+def test_throughput_mode_on_reference_chunks_equals_exact_mode(P, gold_dir, golden_texts):
+    chunks, queries = golden_texts
+    texts = [c["text"] for c in chunks]
+    gold = np.load(os.path.join(gold_dir, "bm25_golden.npz"))["scores"]
+    bm = P.BM25Index([t.split() for t in texts], mode="throughput")
+    assert bm.index.mode == "throughput"
+    n = len(texts)
+    for k in (1, 5, 10, n, n + 5):
+        S, I = bm.search([q.split() for q in queries], k)
+        for r in range(len(queries)):
+            want = O.argsort_topk_canonical(gold[r], k)
+            kk = min(k, n)
+            assert I[r, :kk].tolist() == want.tolist(), f"q{r} k{k}"
+            assert np.array_equal(S[r, :kk], gold[r][want])                    # exact float64 re-score
+            assert (I[r, kk:] == -1).all()
+    tgold = np.load(os.path.join(gold_dir, "tfidf_golden.npz"))["scores"]
+    tf = P.TfidfIndex(texts, mode="throughput")
+    S, I = tf.search(queries, 10)
+    for r in range(len(queries)):
+        O.check_topk_against_scores(I[r], S[r], tgold[r], 10, True, rtol=1e-5, atol=1e-12, what=f"tfidf q{r}")
+        assert np.array_equal(S[r], tgold[r][I[r]])
+
+
+def test_throughput_mode_random_corpus_vs_oracle(P):
+    rng = np.random.default_rng(11)
+    vocab = [f"w{i}" for i in range(3000)]
+    p = 1.0 / np.arange(1, 3001) ** 1.07
+    p /= p.sum()
+    docs = [[vocab[j] for j in rng.choice(3000, size=int(rng.integers(1, 200)), p=p)] for _ in range(20011)]
+    qs = [[vocab[j] for j in rng.choice(3000, size=int(rng.integers(1, 9)), p=p)] for _ in range(43)] + [["zzz"], []]
+    qs.append([vocab[j] for j in rng.choice(3000, size=150, p=p)])            # > 64 entries: the multi-round path of its group
+    ob = O.BM25OkapiOracle(docs)
+    exact = P.BM25Index(docs)
+    fast = P.BM25Index(docs, mode="throughput")
+    Se, Ie = exact.search(qs, 10)
+    S, I = fast.search(qs, 10)
+    for r, q in enumerate(qs):
+        sc = ob.get_scores(q)
+        O.check_topk_against_scores(I[r], S[r], sc, 10, True, rtol=1e-5, atol=1e-12, what=f"q{r}")
+        assert np.array_equal(S[r], sc[I[r]])                                   # exact float64 scores
+    assert np.array_equal(S, Se) and (I == Ie).mean() > 0.99                    # same scores; ids differ at most inside ties
+    # no query token matches: every doc scores 0, order is id descending (stable argsort reversed)
+    assert I[-2].tolist() == list(range(20010, 20000, -1)) and I[-3].tolist() == I[-2].tolist()
+    assert fast.index.last_postings == exact.index.last_postings > 0
+    # device-side entry point: same answer, results stay on the GPU
+    Sd, Id = fast.search_device(qs, 10)
+    assert Sd.is_cuda and np.array_equal(Sd.cpu().numpy(), S) and np.array_equal(Id.cpu().numpy(), I)
+    assert fast.index.last_postings == exact.index.last_postings                # counted by a kernel on that path
+    Sd, Id = exact.search_device(qs[:5], 3)
+    assert np.array_equal(Sd.cpu().numpy(), Se[:5, :3]) and np.array_equal(Id.cpu().numpy(), Ie[:5, :3])
+
+
+def test_throughput_mode_raw_csr_many_tiles_negative_weights_and_shared_terms(P):
+    """150 000 docs (74 accumulator tiles of 2 048, several doc-range parts), a term present in every doc
+    (tile-offset row), query weights of both signs, duplicates of a term inside and across the queries of
+    one 8-query group, out-of-vocabulary ids, k + margin above and below the candidate-list sizes."""
+    rng = np.random.default_rng(17)
+    n_docs, n_terms = 150_000, 700
+    lens = rng.integers(1, 14, size=n_docs)
+    indptr = np.zeros(n_docs + 1, np.int64)
+    indptr[1:] = np.cumsum(lens + 1)
+    indices = np.empty(indptr[-1], np.int32)
+    for dct in range(n_docs):
+        t = rng.choice(n_terms - 1, size=lens[dct], replace=False) + 1
+        indices[indptr[dct]:indptr[dct + 1]] = np.sort(np.concatenate([[0], t]))
+    vals = (rng.random(indices.shape[0]) + 0.1) * np.where(rng.random(indices.shape[0]) < 0.1, -1.0, 1.0)
+    import scipy.sparse as ssp
+    M = ssp.csr_matrix((vals, indices, indptr), shape=(n_docs, n_terms)).tocsc()
+    nq = 21
+    qlen = rng.integers(1, 12, size=nq)
+    q_indptr = np.zeros(nq + 1, np.int64)
+    q_indptr[1:] = np.cumsum(qlen)
+    q_terms = rng.integers(0, 40, size=q_indptr[-1]).astype(np.int32)          # few distinct terms: heavy sharing
+    q_terms[::7] = 0
+    q_terms[5] = 5000                                                           # out of vocabulary
+    q_w = rng.standard_normal(q_indptr[-1])
+    for dtype in (np.float64, np.float32):
+        v = vals.astype(dtype)
+        Md = ssp.csr_matrix((v.astype(np.float64), indices, indptr), shape=(n_docs, n_terms)).tocsc()
+        sp = P.SparseIndex(indptr, indices, v, n_terms, mode="throughput")
+        for k in (1, 10, 80, 200):                                             # 200 + 16 > 96: that call runs the exact kernel
+            S, I = sp.search(q_indptr, q_terms, q_w, k)
+            for r in range(nq):
+                sc = np.zeros(n_docs)
+                for e in range(q_indptr[r], q_indptr[r + 1]):
+                    if q_terms[e] < n_terms:
+                        sc += q_w[e] * Md[:, q_terms[e]].toarray().ravel()
+                O.check_topk_against_scores(I[r], S[r], sc, k, True, rtol=1e-5, atol=1e-9, what=f"{dtype.__name__} k{k} q{r}")
+                assert np.array_equal(S[r], sc[I[r]])
+
+
 # ------------------------------------------------------------------ pooling epilogue
 def test_pool_golden(P, gold_dir):
     import torch
