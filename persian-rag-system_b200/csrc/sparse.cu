@@ -338,8 +338,8 @@ constexpr int SB_THREADS = 512;
 constexpr int SB_NW = SB_THREADS / 32;
 constexpr int SB_QLEN = 64;            // query entries per slot resolved per round
 constexpr int SB_MAXE = SB_QG * SB_QLEN;
-constexpr int SB_CAP = 256;            // candidate keys per slot: 32 lanes x 8, compacted by a warp sort
-constexpr int SB_MAXKK = 96;           // k + SP_MARGIN this kernel supports (CAP - 32 - kk slots of headroom)
+constexpr int SB_CAP = 128;            // candidate keys per (slot, tile half): 32 lanes x 4, compacted by a warp sort
+constexpr int SB_MAXKK = 64;           // k + SP_MARGIN this kernel supports (compaction must free >= 32 places)
 constexpr int SB_CHUNK = 128;          // postings per warp step (4 per lane in flight)
 
 struct SbParams {
@@ -351,15 +351,15 @@ struct SbParams {
     u64* cand; int* cand_cnt;          // [parts][nq][kk]
 };
 
-constexpr size_t SB_SMEM = (size_t)SB_QG * SB_TD * 4 + (size_t)SB_QG * SB_CAP * 8 + (size_t)SB_MAXE * 8 /*skey*/ +
+constexpr size_t SB_SMEM = (size_t)SB_QG * SB_TD * 4 + (size_t)SB_NW * SB_CAP * 8 + (size_t)SB_MAXE * 8 /*skey*/ +
                            (size_t)SB_MAXE * 8 /*u_base*/ + (size_t)SB_MAXE * 4 * 5 /*u_len,u_cur,u_end,u_row,w0*/ +
-                           (size_t)(SB_MAXE + 1) * 4 * 2 /*u_seg,pre*/ + (size_t)SB_MAXE * 4 /*e_scale*/ + SB_MAXE /*e_slot*/ + 256;
+                           (size_t)(SB_MAXE + 1) * 4 * 2 /*u_seg,pre*/ + (size_t)SB_MAXE * 4 /*e_scale*/ + SB_MAXE /*e_slot*/ + 256 /*misc*/ + (size_t)(SB_MAXE + 1) * 4 /*nz_pre*/ + SB_MAXE * 2 /*nz_u*/ + 64;
 
 __global__ void __launch_bounds__(SB_THREADS, 2) sparse_score_batched_kernel(const SbParams p) {
     extern __shared__ __align__(16) unsigned char sbm[];
     int* acc = reinterpret_cast<int*>(sbm);                                  // [QG][TD] fixed-point scores
-    u64* cbuf = reinterpret_cast<u64*>(acc + SB_QG * SB_TD);                 // [QG][CAP]
-    u64* skey = cbuf + SB_QG * SB_CAP;                                       // [MAXE]
+    u64* cbuf = reinterpret_cast<u64*>(acc + SB_QG * SB_TD);                 // [NW][CAP]
+    u64* skey = cbuf + SB_NW * SB_CAP;                                       // [MAXE]
     long long* u_base = reinterpret_cast<long long*>(skey + SB_MAXE);        // [MAXE] tptr[t]
     uint32_t* u_len = reinterpret_cast<uint32_t*>(u_base + SB_MAXE);         // [MAXE] df(t)
     uint32_t* u_cur = u_len + SB_MAXE;                                       // [MAXE] tile range (relative to u_base)
@@ -370,8 +370,12 @@ __global__ void __launch_bounds__(SB_THREADS, 2) sparse_score_batched_kernel(con
     int* pre = u_seg + SB_MAXE + 1;                                          // [MAXE+1] postings of this tile before term u
     float* e_scale = reinterpret_cast<float*>(pre + SB_MAXE + 1);            // [MAXE] sorted entries: weight * slot scale
     unsigned char* e_slot = reinterpret_cast<unsigned char*>(e_scale + SB_MAXE);   // [MAXE]
-    int* misc = reinterpret_cast<int*>(e_slot + SB_MAXE);                    // [0] U, [1] E, [2..17] warp totals, [20..27] slot scale (float)
+    int* misc = reinterpret_cast<int*>(e_slot + SB_MAXE);                    // [0] U, [1] E, [2..17] warp totals, [18] P, [19] chunk, [20..27] slot scale (float), [28] K
     float* s_scale = reinterpret_cast<float*>(misc + 20);
+    int* s_K = misc + 28;
+    int* s_dummy = misc + 32;                                                // [32]
+    int* nz_pre = misc + 64;                                                 // [MAXE+1] postings before the k-th non-empty term
+    unsigned short* nz_u = reinterpret_cast<unsigned short*>(nz_pre + SB_MAXE + 1);   // [MAXE] its index u
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int q0 = (int)blockIdx.x * SB_QG;                                  // first query of this group
@@ -467,11 +471,15 @@ __global__ void __launch_bounds__(SB_THREADS, 2) sparse_score_batched_kernel(con
         return l;
     };
 
-    // candidate list of slot `warp` (warps 0..QG-1): count and admission key live in registers
+    // candidate list of (slot = warp % QG, tile half = warp / QG): every warp owns one list exclusively --
+    // count and admission key live in its registers, no atomics.  The two halves of a slot keep their
+    // own k' best; the merge kernel unites them like two more doc-range parts.
+    const int my_slot = warp % SB_QG, my_half = warp / SB_QG;
+    const bool my_valid = q0 + my_slot < p.nq;
     int ccount = 0;
     u64 cthr = 0ull;
-    u64* myc = cbuf + (size_t)(warp < SB_QG ? warp : 0) * SB_CAP;
-    auto compact = [&]() {                                 // warp-level: keep the kk best of the slot's list
+    u64* myc = cbuf + (size_t)warp * SB_CAP;
+    auto compact = [&]() {                                 // warp-level: keep the kk best of this warp's list
         u64 v[SB_CAP / 32];
 #pragma unroll
         for (int i = 0; i < SB_CAP / 32; ++i) { const int e = lane * (SB_CAP / 32) + i; v[i] = e < ccount ? myc[e] : 0ull; }
@@ -483,102 +491,131 @@ __global__ void __launch_bounds__(SB_THREADS, 2) sparse_score_batched_kernel(con
         ccount = ccount < p.kk ? ccount : p.kk;
         cthr = ccount == p.kk ? myc[p.kk - 1] : 0ull;
     };
+    int* s_P = misc + 18;            // postings of the current tile
+    int* s_chunk = misc + 19;        // next chunk to hand out
 
-    if (persistent && rounds == 1) {
-        build_table(0);
-        const int U = misc[0];
-        if (tid < U && u_row[tid] < 0) u_end[tid] = lower_bound_rel(tid, tile1 * SB_TD, 0u, u_len[tid]);
-        __syncthreads();
-    }
-
-    // Tiles are visited in DESCENDING doc order: a later doc then has a lower id and loses every tie
-    // (score desc, id DESC), so floods of equal scores (all-zero queries) stop entering the lists once
-    // they hold kk entries.
-    for (long long tile = tile1 - 1; tile >= tile0; --tile) {
-        const long long lo = tile * SB_TD;
-        const long long hi = (lo + SB_TD < p.n_docs) ? lo + SB_TD : p.n_docs;
-        const int nd = (int)(hi - lo);
-        {
-            int4* z = reinterpret_cast<int4*>(acc);
-            for (int i = tid; i < SB_QG * SB_TD / 4; i += SB_THREADS) z[i] = make_int4(0, 0, 0, 0);
+    // ---- phase A: this tile's posting range of every unique term (thread u).  Split in two so that the
+    // loads (tile-offset rows / posting probes) of the NEXT tile are in flight during the posting phase
+    // of the current one: range_load() returns (start, end) in registers, range_store() publishes them.
+    auto range_load = [&](long long tile, long long lo, long long hi, uint32_t& c, uint32_t& e) {
+        c = 0u; e = 0u;
+        if (tid < misc[0]) {
+            const int row = u_row[tid];
+            if (row >= 0) {
+                const uint32_t* sk = p.skip + (size_t)row * (size_t)(p.n_tiles + 1) + tile;
+                c = __ldg(sk); e = __ldg(sk + 1);
+            } else if (persistent) {
+                e = u_end[tid];                                                  // descending tiles: the previous tile's start
+                if (e == 0u || (long long)p.pdoc[u_base[tid] + e - 1] < lo) c = e;               // nothing in this tile
+                else c = lower_bound_rel(tid, lo, e > (uint32_t)SB_TD ? e - SB_TD : 0u, e);
+            } else {
+                c = lower_bound_rel(tid, lo, 0u, u_len[tid]);
+                e = lower_bound_rel(tid, hi, c, u_len[tid]);
+            }
         }
-        for (int r = 0; r < (rounds > 0 ? rounds : 0); ++r) {
-            if (!persistent) build_table(r);
+    };
+    auto range_store = [&](uint32_t c, uint32_t e) {
+        if (tid < misc[0]) {
+            u_cur[tid] = c;
+            u_end[tid] = persistent ? c : e;                                     // persistent: becomes the next tile's end
+            pre[tid + 1] = (int)(e - c);
+        }
+    };
+    // ---- phase B: warp 0 compacts the NON-EMPTY terms of the tile (most tail terms have no posting in a
+    // given 2 048-doc tile) and turns their counts into a prefix: nz_u[k] = term, pre[k] = postings before it ----
+    auto prefix = [&]() {
+        if (warp == 0) {
             const int U = misc[0];
-            // ---- this tile's posting range of every unique term ----
-            int cnt = 0;
-            if (tid < U) {
-                uint32_t c, e;
-                const int row = u_row[tid];
-                if (row >= 0) {
-                    const uint32_t* sk = p.skip + (size_t)row * (size_t)(p.n_tiles + 1) + tile;
-                    c = __ldg(sk); e = __ldg(sk + 1);
-                } else if (persistent) {
-                    e = u_end[tid];
-                    if (e == 0u || (long long)p.pdoc[u_base[tid] + e - 1] < lo) c = e;               // nothing in this tile
-                    else c = lower_bound_rel(tid, lo, e > (uint32_t)SB_TD ? e - SB_TD : 0u, e);
-                } else {
-                    c = lower_bound_rel(tid, lo, 0u, u_len[tid]);
-                    e = lower_bound_rel(tid, hi, c, u_len[tid]);
+            int carry = 0, kbase = 0;
+            for (int b = 0; b < U; b += 32) {
+                const int cnt = (b + lane < U) ? pre[b + lane + 1] : 0;
+                const unsigned nzm = __ballot_sync(0xffffffffu, cnt > 0);
+                int v = cnt;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += t; }
+                __syncwarp();
+                if (cnt > 0) {
+                    const int k = kbase + __popc(nzm & ((1u << lane) - 1u));
+                    nz_u[k] = (unsigned short)(b + lane);
+                    nz_pre[k] = carry + v - cnt;                                 // exclusive
                 }
-                u_cur[tid] = c; u_end[tid] = e;
-                cnt = (int)(e - c);
+                carry += __shfl_sync(0xffffffffu, v, 31);
+                kbase += __popc(nzm);
             }
-            // exclusive prefix over the U counts
-            int inc = cnt;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
-            if (lane == 31) misc[2 + warp] = inc;
-            __syncthreads();
-            int before = 0, total = 0;
-#pragma unroll
-            for (int w = 0; w < SB_NW; ++w) { const int c = misc[2 + w]; before += (w < warp) ? c : 0; total += c; }
-            if (tid < U) pre[tid] = before + inc - cnt;
-            if (tid == 0) pre[U] = total;
-            __syncthreads();
-            // ---- posting phase: warps take chunks of the flattened postings of this tile ----
-            const int P = total;
-            for (int i0 = warp * SB_CHUNK; i0 < P; i0 += SB_NW * SB_CHUNK) {
-                const int i1 = (i0 + SB_CHUNK < P) ? i0 + SB_CHUNK : P;
-                int ul = 0, ur = U;                                 // last u with pre[u] <= i0
-                while (ur - ul > 1) { const int mid = (ul + ur) >> 1; if (pre[mid] <= i0) ul = mid; else ur = mid; }
-                int u = ul, i = i0;
-                while (i < i1) {
-                    while (pre[u + 1] <= i) ++u;
-                    const int segend = (i1 < pre[u + 1]) ? i1 : pre[u + 1];
-                    const long long g = u_base[u] + (long long)u_cur[u] + (i - pre[u]);
-                    const int n = segend - i;
-                    int dl[SB_CHUNK / 32];
-                    float pv[SB_CHUNK / 32];
-#pragma unroll
-                    for (int j = 0; j < SB_CHUNK / 32; ++j) {
-                        const int off = lane + 32 * j;
-                        dl[j] = off < n ? __ldg(p.pdoc + g + off) - (int)lo : -1;
-                        pv[j] = off < n ? __ldg(p.pval + g + off) : 0.f;
-                    }
-                    const int e1 = u_seg[u + 1];
-                    for (int e = u_seg[u]; e < e1; ++e) {
-                        const float sc = e_scale[e];
-                        int* row = acc + (int)e_slot[e] * SB_TD;
-#pragma unroll
-                        for (int j = 0; j < SB_CHUNK / 32; ++j)
-                            if (dl[j] >= 0) atomicAdd(row + dl[j], __float2int_rn(pv[j] * sc));
-                    }
-                    i = segend;
-                }
-            }
-            __syncthreads();
-            if (persistent && tid < U) u_end[tid] = u_cur[tid];      // descending tiles: this tile's start is the next one's end
+            if (lane == 0) { nz_pre[kbase] = carry; *s_P = carry; *s_chunk = 0; *s_K = kbase; }
         }
-        __syncthreads();
-        // ---- selection: warp s scans the tile's scores of slot s ----
-        if (warp < SB_QG && q0 + warp < p.nq) {
-            const int* row = acc + warp * SB_TD;
-            for (int b = 0; b < nd; b += 32) {
-                const int i = b + lane;
-                u64 key = 0ull;
-                if (i < nd) key = ((u64)((uint32_t)row[i] ^ 0x80000000u) << 32) | (u64)(uint32_t)(lo + i);
-                const bool pred = key > cthr;
+    };
+    // ---- posting phase: warps grab chunks of the tile's flattened postings; one load feeds every query
+    // of the group that has the term (shared-memory integer atomics, order independent) ----
+    auto postings = [&](long long lo) {
+        const int P = *s_P, K = *s_K;
+        const int nchunks = (P + SB_CHUNK - 1) / SB_CHUNK;
+        const int s1 = (K + 31) >> 5;                                            // first-level stride of the 32-ary search
+        int* const dummy = s_dummy + lane;                                        // lanes without a posting add 0 here (no branch)
+        for (;;) {
+            int c = 0;
+            if (lane == 0) c = atomicAdd(s_chunk, 1);
+            c = __shfl_sync(0xffffffffu, c, 0);
+            if (c >= nchunks) break;
+            const int i0 = c * SB_CHUNK;
+            const int i1 = (i0 + SB_CHUNK < P) ? i0 + SB_CHUNK : P;
+            // last k with nz_pre[k] <= i0, two 32-wide probes
+            int idx = lane * s1;
+            const int klo = (__popc(__ballot_sync(0xffffffffu, idx < K && nz_pre[idx] <= i0)) - 1) * s1;
+            idx = klo + lane;
+            int k = klo + __popc(__ballot_sync(0xffffffffu, lane < s1 && idx < K && nz_pre[idx] <= i0)) - 1;
+            int i = i0;
+            while (i < i1) {
+                const int pk = nz_pre[k], pn = nz_pre[k + 1];
+                const int u = nz_u[k];
+                const int segend = (i1 < pn) ? i1 : pn;
+                const int n = segend - i;
+                const long long g = u_base[u] + (long long)u_cur[u] + (i - pk);
+                const int* dp = p.pdoc + g + lane;
+                const float* vp = p.pval + g + lane;
+                int dl[SB_CHUNK / 32];
+                float pv[SB_CHUNK / 32];
+#pragma unroll
+                for (int j = 0; j < SB_CHUNK / 32; ++j) {
+                    const bool in = lane + 32 * j < n;
+                    dl[j] = in ? __ldg(dp + 32 * j) : -1;
+                    pv[j] = in ? __ldg(vp + 32 * j) : 0.f;
+                }
+                const int ilo = (int)lo;
+                const int e1 = u_seg[u + 1];
+                for (int e = u_seg[u]; e < e1; ++e) {
+                    const float sc = e_scale[e];
+                    int* row = acc + (int)e_slot[e] * SB_TD - ilo;
+#pragma unroll
+                    for (int j = 0; j < SB_CHUNK / 32; ++j)
+                        atomicAdd(dl[j] >= 0 ? row + dl[j] : dummy, __float2int_rn(pv[j] * sc));
+                }
+                i = segend;
+                ++k;
+            }
+        }
+    };
+    // ---- selection: warp (slot, half) scans its 1024 scores, 4 per lane and step, clearing them for the
+    // next tile as it goes; survivors of the integer threshold test are rare ----
+    auto scan_clear = [&](long long lo, long long hi) {
+        constexpr int HALF = SB_TD / 2;
+        int4* row4 = reinterpret_cast<int4*>(acc + my_slot * SB_TD + my_half * HALF);
+        const long long base = lo + my_half * HALF;
+#pragma unroll 2
+        for (int it = 0; it < HALF / 128; ++it) {
+            const int i4 = it * 32 + lane;
+            const int4 v = row4[i4];
+            row4[i4] = make_int4(0, 0, 0, 0);
+            if (!my_valid) continue;
+            const int tv = cthr ? (int)((uint32_t)(cthr >> 32) ^ 0x80000000u) : (int)0x80000000;
+            const bool any = v.x >= tv || v.y >= tv || v.z >= tv || v.w >= tv;
+            if (__ballot_sync(0xffffffffu, any) == 0u) continue;
+            const int vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const long long doc = base + (long long)i4 * 4 + j;
+                const u64 key = ((u64)((uint32_t)vv[j] ^ 0x80000000u) << 32) | (u64)(uint32_t)doc;
+                const bool pred = doc < hi && key > cthr;
                 const unsigned m = __ballot_sync(0xffffffffu, pred);
                 if (m) {
                     if (pred) myc[ccount + __popc(m & ((1u << lane) - 1u))] = key;
@@ -588,11 +625,65 @@ __global__ void __launch_bounds__(SB_THREADS, 2) sparse_score_batched_kernel(con
                 }
             }
         }
+    };
+
+    {
+        int4* z = reinterpret_cast<int4*>(acc);
+        for (int i = tid; i < SB_QG * SB_TD / 4; i += SB_THREADS) z[i] = make_int4(0, 0, 0, 0);
+    }
+    if (tid == 0) { misc[0] = 0; *s_P = 0; *s_chunk = 0; *s_K = 0; }
+    if (tid < 32) s_dummy[tid] = 0;
+    __syncthreads();
+    auto tile_lo = [&](long long tile) { return tile * SB_TD; };
+    auto tile_hi = [&](long long tile) { const long long h = tile * SB_TD + SB_TD; return h < p.n_docs ? h : p.n_docs; };
+    if (rounds == 1) {
+        build_table(0);
+        const int U = misc[0];
+        if (tid < U && u_row[tid] < 0) u_end[tid] = lower_bound_rel(tid, tile1 * SB_TD, 0u, u_len[tid]);
+        __syncthreads();
+        if (tile1 > tile0) {
+            uint32_t c, e;
+            range_load(tile1 - 1, tile_lo(tile1 - 1), tile_hi(tile1 - 1), c, e);
+            range_store(c, e);
+        }
         __syncthreads();
     }
-    if (warp < SB_QG && q0 + warp < p.nq) {
+
+    // Tiles are visited in DESCENDING doc order: a later doc then has a lower id and loses every tie
+    // (score desc, id DESC), so floods of equal scores (all-zero queries) stop entering the lists once
+    // they hold kk entries.
+    for (long long tile = tile1 - 1; tile >= tile0; --tile) {
+        const long long lo = tile_lo(tile), hi = tile_hi(tile);
+        if (persistent) {
+            // ranges of this tile are already in shared memory (published during the previous tile)
+            uint32_t nc = 0u, ne = 0u;
+            prefix();
+            __syncthreads();
+            if (rounds == 1) {
+                if (tile > tile0) range_load(tile - 1, tile_lo(tile - 1), tile_hi(tile - 1), nc, ne);   // in flight during the posting phase
+                postings(lo);
+            }
+            __syncthreads();
+            if (rounds == 1 && tile > tile0) range_store(nc, ne);
+        } else {
+            for (int r = 0; r < rounds; ++r) {
+                build_table(r);
+                uint32_t c, e;
+                range_load(tile, lo, hi, c, e);
+                range_store(c, e);
+                __syncthreads();
+                prefix();
+                __syncthreads();
+                postings(lo);
+                __syncthreads();
+            }
+        }
+        scan_clear(lo, hi);
+        __syncthreads();
+    }
+    if (my_valid) {
         compact();
-        const size_t o = (size_t)part * p.nq + (q0 + warp);
+        const size_t o = (size_t)(part * 2 + my_half) * p.nq + (q0 + my_slot);
         for (int j = lane; j < p.kk; j += 32) p.cand[o * p.kk + j] = j < ccount ? myc[j] : 0ull;
         if (lane == 0) p.cand_cnt[o] = ccount;
     }
@@ -740,8 +831,9 @@ static int sparse_search_core(prs_sparse* sp, const long long* d_qptr, const int
         long long want = ((long long)sp->sm_count * 3 * 4 + nq - 1) / nq;              // ~4 waves of 3 CTAs per SM
         parts = (int)std::max<long long>(1, std::min<long long>(n_tiles, want));
     }
-    if ((rc = sp->cand.ensure((size_t)parts * nq * kk * 8))) return rc;
-    if ((rc = sp->cand_cnt.ensure((size_t)parts * nq * 4))) return rc;
+    const int lists = fast ? parts * 2 : parts;          // the batched kernel keeps one list per (part, tile half)
+    if ((rc = sp->cand.ensure((size_t)lists * nq * kk * 8))) return rc;
+    if ((rc = sp->cand_cnt.ensure((size_t)lists * nq * 4))) return rc;
     if ((rc = sp->dI.ensure((size_t)nq * kk * 8))) return rc;
     if (fast) {
         SbParams p;
@@ -770,7 +862,7 @@ static int sparse_search_core(prs_sparse* sp, const long long* d_qptr, const int
     {
         const size_t msmem = (size_t)sortn * 8 + 16;
         PRS_CUDA(cudaFuncSetAttribute(sparse_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem));
-        sparse_merge_kernel<<<(unsigned)nq, SP_THREADS, msmem, st>>>((const u64*)sp->cand.p, (const int*)sp->cand_cnt.p, parts, (int)nq, kk,
+        sparse_merge_kernel<<<(unsigned)nq, SP_THREADS, msmem, st>>>((const u64*)sp->cand.p, (const int*)sp->cand_cnt.p, lists, (int)nq, kk,
                                                                      sortn, (long long*)sp->dI.p);
         PRS_LAUNCH_CHECK();
     }
