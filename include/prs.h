@@ -117,6 +117,17 @@ int prs_index_reconstruct_host(prs_index* idx, int64_t i0, int64_t n, float* out
 int prs_index_write(prs_index* idx, const char* path);
 int prs_index_read(const char* path, int storage, int device, prs_index** out);
 
+/* Sharded container: one file per shard = [128-byte header | corpus exactly as it sits in HBM
+ * (16-bit: T64 blocks; fp32: row-major) | float32 squared norms], page-aligned sections (mmap-able).  Loading is a
+ * straight double-buffered copy through page-locked staging (one cudaMemcpyAsync per 64 MB chunk, file reads
+ * overlapping the copies): no conversion kernel, no norm recomputation.  The reference's anchor is the single
+ * faiss file at src/create_embeddings.py:136 / src/retrieval.py:55; this is what a 307 GB corpus needs instead.
+ * prs_index_read_shard: *out == NULL -> new index; otherwise the shard is APPENDED to *out (consecutive shards of
+ * one rank; 16-bit images concatenate at 64-row boundaries only).  The manifest (which shard goes to which rank,
+ * global ids) is kept by the host layer (container.py). */
+int prs_index_write_shard(prs_index* idx, const char* path);
+int prs_index_read_shard(const char* path, int device, prs_index** out);
+
 /* ---------------------------------------------------------------------------------------
  * Row-sharded search: merge step.  Each of `nparts` shards contributes its local
  * top-k for the same nq queries, concatenated as D_parts/I_parts [nparts, nq, k] on the device
@@ -126,6 +137,11 @@ int prs_index_read(const char* path, int storage, int device, prs_index** out);
  * ------------------------------------------------------------------------------------- */
 int prs_merge_topk_device(const float* D_parts, const int64_t* I_parts, int nparts, int64_t nq, int k,
                           int largest, int tie_high_id, float* D, int64_t* I, int device, void* stream);
+
+/* same for the sparse path ("shard by doc range the same way"): float64 scores, always largest
+ * first; tie_high_id = 1 reproduces the unsharded order (score desc, id desc). */
+int prs_merge_topk_f64_device(const double* S_parts, const int64_t* I_parts, int nparts, int64_t nq, int k,
+                              int tie_high_id, double* S, int64_t* I, int device, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * Row-sharded search with the exchange fused into the merge kernel (one process per GPU).

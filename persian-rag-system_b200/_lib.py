@@ -43,7 +43,10 @@ SIGNATURES = {
     "prs_index_reconstruct_host": (c_int, [c_void_p, c_i64, c_i64, c_void_p]),
     "prs_index_write": (c_int, [c_void_p, c_char_p]),
     "prs_index_read": (c_int, [c_char_p, c_int, c_int, ctypes.POINTER(c_void_p)]),
+    "prs_index_write_shard": (c_int, [c_void_p, c_char_p]),
+    "prs_index_read_shard": (c_int, [c_char_p, c_int, ctypes.POINTER(c_void_p)]),
     "prs_merge_topk_device": (c_int, [c_void_p, c_void_p, c_int, c_i64, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p]),
+    "prs_merge_topk_f64_device": (c_int, [c_void_p, c_void_p, c_int, c_i64, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p]),
     "prs_xchg_create": (c_int, [c_int, c_int, c_int, c_i64, c_int, ctypes.POINTER(c_void_p)]),
     "prs_xchg_handle_bytes": (c_int, []),
     "prs_xchg_get_handle": (c_int, [c_void_p, c_void_p]),

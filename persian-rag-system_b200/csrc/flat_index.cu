@@ -901,3 +901,173 @@ int prs_index_read(const char* path, int storage, int device, prs_index** out) {
 }
 
 }  // extern "C"
+
+// ---- sharded container (second half): one file per shard holding the HBM image itself ----
+// A shard file is [128-byte header][pad to 4096][payload][pad to 4096][norms]:
+//   payload = the corpus exactly as it sits in HBM (16-bit storage: T64 blocks, rows padded to a multiple of 64;
+//             fp32: row-major [rows, pitch]), norms = float32 ||x||^2 of the stored rows.
+// Loading is therefore a straight copy -- no conversion kernel, no re-computation of the norms -- streamed through
+// two page-locked staging buffers with one cudaMemcpyAsync per 64 MB chunk, the file read of chunk i+1 overlapping
+// the copy of chunk i.  Offsets are page aligned, so the payload can also be mmap'ed as is.  Which shard belongs to
+// which rank is the manifest's business (container.py); every rank loads its own file(s) in parallel.
+#pragma pack(push, 1)
+struct ShardHeader {
+    char fourcc[4];                  // "PRST"
+    int32_t version, d, pitch, metric, storage;
+    int64_t rows, rows_padded, id_offset;
+    int64_t payload_offset, payload_bytes, norms_offset, norms_bytes;
+    char pad[128 - 4 - 5 * 4 - 7 * 8];
+};
+#pragma pack(pop)
+static_assert(sizeof(ShardHeader) == 128, "shard header is 128 bytes");
+constexpr size_t SHARD_CHUNK = (size_t)64 << 20;
+
+struct PinnedPair {
+    void* buf[2] = {nullptr, nullptr};
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    cudaStream_t st = nullptr;
+    int init() {
+        for (int i = 0; i < 2; ++i) {
+            if (cudaHostAlloc(&buf[i], SHARD_CHUNK, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); set_error("shard I/O: cannot allocate page-locked staging buffers"); return PRS_ENOMEM; }
+            if (cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); set_error("shard I/O: cudaEventCreate failed"); return PRS_ECUDA; }
+        }
+        if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); set_error("shard I/O: cudaStreamCreate failed"); return PRS_ECUDA; }
+        return 0;
+    }
+    ~PinnedPair() {
+        if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
+        for (int i = 0; i < 2; ++i) { if (ev[i]) cudaEventDestroy(ev[i]); if (buf[i]) cudaFreeHost(buf[i]); }
+    }
+};
+
+// file[off, off+bytes) -> device, double buffered
+static int file_to_device(FILE* f, long long off, void* dptr, size_t bytes, PinnedPair& pp, const char* path) {
+    if (fseeko(f, (off_t)off, SEEK_SET) != 0) { set_error("read_shard: seek failed in %s", path); return PRS_EIO; }
+    int b = 0;
+    bool used[2] = {false, false};
+    for (size_t o = 0; o < bytes; o += SHARD_CHUNK, b ^= 1) {
+        const size_t c = std::min(SHARD_CHUNK, bytes - o);
+        if (used[b]) PRS_CUDA(cudaEventSynchronize(pp.ev[b]));             // the copy that last used this buffer is done
+        if (fread(pp.buf[b], 1, c, f) != c) { set_error("read_shard: %s is truncated", path); return PRS_EIO; }
+        PRS_CUDA(cudaMemcpyAsync((unsigned char*)dptr + o, pp.buf[b], c, cudaMemcpyHostToDevice, pp.st));
+        PRS_CUDA(cudaEventRecord(pp.ev[b], pp.st));
+        used[b] = true;
+    }
+    PRS_CUDA(cudaStreamSynchronize(pp.st));
+    return 0;
+}
+// device -> file (appended at the current position), double buffered
+static int device_to_file(FILE* f, const void* dptr, size_t bytes, PinnedPair& pp, const char* path) {
+    int b = 0;
+    size_t pending[2] = {0, 0};
+    for (size_t o = 0; o < bytes || pending[0] || pending[1]; o += SHARD_CHUNK, b ^= 1) {
+        if (pending[b]) {                                                   // flush what this buffer received two steps ago
+            PRS_CUDA(cudaEventSynchronize(pp.ev[b]));
+            if (fwrite(pp.buf[b], 1, pending[b], f) != pending[b]) { set_error("write_shard: short write to %s", path); return PRS_EIO; }
+            pending[b] = 0;
+        }
+        if (o < bytes) {
+            const size_t c = std::min(SHARD_CHUNK, bytes - o);
+            PRS_CUDA(cudaMemcpyAsync(pp.buf[b], (const unsigned char*)dptr + o, c, cudaMemcpyDeviceToHost, pp.st));
+            PRS_CUDA(cudaEventRecord(pp.ev[b], pp.st));
+            pending[b] = c;
+        }
+        if (o >= bytes && !pending[b ^ 1]) break;
+    }
+    return 0;
+}
+static int pad_file_to(FILE* f, long long target, const char* path) {
+    static const char zeros[4096] = {0};
+    long long pos = (long long)ftello(f);
+    while (pos < target) {
+        const size_t c = (size_t)std::min<long long>(4096, target - pos);
+        if (fwrite(zeros, 1, c, f) != c) { set_error("write_shard: short write to %s", path); return PRS_EIO; }
+        pos += (long long)c;
+    }
+    return 0;
+}
+static inline long long align4k(long long v) { return (v + 4095) & ~4095ll; }
+
+extern "C" {
+
+int prs_index_write_shard(prs_index* idx, const char* path) {
+    if (!idx || !path) { set_error("write_shard: bad arguments"); return PRS_EINVAL; }
+    DeviceGuard g(idx->device);
+    std::lock_guard<std::mutex> lock(idx->mu);
+    PRS_CUDA(cudaDeviceSynchronize());
+    const size_t es = elem_size(idx->storage);
+    ShardHeader h;
+    memset(&h, 0, sizeof(h));
+    memcpy(h.fourcc, "PRST", 4);
+    h.version = 1; h.d = idx->d; h.pitch = idx->pitch; h.metric = idx->metric; h.storage = idx->storage;
+    h.rows = idx->n;
+    h.rows_padded = idx->storage != PRS_F32 ? (idx->n + BLK_ROWS - 1) / BLK_ROWS * BLK_ROWS : idx->n;
+    h.id_offset = idx->id_offset;
+    h.payload_offset = 4096;
+    h.payload_bytes = (int64_t)((size_t)h.rows_padded * idx->pitch * es);
+    h.norms_offset = align4k(h.payload_offset + h.payload_bytes);
+    h.norms_bytes = (int64_t)idx->n * 4;
+    PinnedPair pp;
+    int rc = pp.init();
+    if (rc) return rc;
+    FILE* f = fopen(path, "wb");
+    if (!f) { set_error("write_shard: cannot open %s: %s", path, strerror(errno)); return PRS_EIO; }
+    rc = fwrite(&h, sizeof(h), 1, f) == 1 ? 0 : PRS_EIO;
+    if (rc) set_error("write_shard: short write to %s", path);
+    if (!rc) rc = pad_file_to(f, h.payload_offset, path);
+    if (!rc && h.payload_bytes) rc = device_to_file(f, idx->x, (size_t)h.payload_bytes, pp, path);
+    if (!rc) rc = pad_file_to(f, h.norms_offset, path);
+    if (!rc && h.norms_bytes) rc = device_to_file(f, idx->xnorm, (size_t)h.norms_bytes, pp, path);
+    if (fclose(f) != 0 && !rc) { set_error("write_shard: close failed for %s", path); rc = PRS_EIO; }
+    return rc;
+}
+
+// Loads a shard file into a new index, or -- when *out already holds an index -- appends it (consecutive shards of
+// one rank); 16-bit images concatenate only at 64-row block boundaries.
+int prs_index_read_shard(const char* path, int device, prs_index** out) {
+    if (!path || !out) { set_error("read_shard: bad arguments"); return PRS_EINVAL; }
+    FILE* f = fopen(path, "rb");
+    if (!f) { set_error("read_shard: cannot open %s: %s", path, strerror(errno)); return PRS_EIO; }
+    ShardHeader h;
+    if (fread(&h, sizeof(h), 1, f) != 1 || memcmp(h.fourcc, "PRST", 4) != 0 || h.version != 1) {
+        fclose(f); set_error("read_shard: %s is not a version-1 PRST shard file", path); return PRS_EIO;
+    }
+    const size_t es = (size_t)elem_size(h.storage);
+    const bool t64 = h.storage != PRS_F32;
+    if (h.d < 1 || h.pitch != (h.d + 63) / 64 * 64 || h.rows < 0 || (h.storage != PRS_F32 && h.storage != PRS_F16 && h.storage != PRS_BF16) ||
+        h.rows_padded != (t64 ? (h.rows + BLK_ROWS - 1) / BLK_ROWS * BLK_ROWS : h.rows) ||
+        h.payload_bytes != (int64_t)((size_t)h.rows_padded * h.pitch * es) || h.norms_bytes != h.rows * 4 ||
+        h.payload_offset < (int64_t)sizeof(h) || h.norms_offset < h.payload_offset + h.payload_bytes) {
+        fclose(f); set_error("read_shard: %s has an inconsistent header", path); return PRS_EIO;
+    }
+    prs_index* idx = *out;
+    const bool fresh = idx == nullptr;
+    int rc = 0;
+    if (fresh) {
+        rc = prs_index_create(h.d, h.metric, h.storage, device, &idx);
+        if (rc) { fclose(f); return rc; }
+        idx->id_offset = h.id_offset;
+    } else if (idx->d != h.d || idx->storage != h.storage || idx->metric != h.metric || idx->device != device) {
+        fclose(f); set_error("read_shard: %s does not match the index it is appended to", path); return PRS_EINVAL;
+    } else if (t64 && idx->n % BLK_ROWS != 0) {
+        fclose(f); set_error("read_shard: cannot append %s: the index holds %lld rows, not a multiple of %d", path, idx->n, BLK_ROWS); return PRS_EINVAL;
+    }
+    DeviceGuard g(device);
+    {
+        std::lock_guard<std::mutex> lock(idx->mu);
+        PRS_CUDA(cudaDeviceSynchronize());
+        PinnedPair pp;
+        rc = pp.init();
+        if (!rc) rc = index_grow(idx, idx->n + h.rows);
+        if (!rc && h.payload_bytes)
+            rc = file_to_device(f, h.payload_offset, (unsigned char*)idx->x + (size_t)idx->n * idx->pitch * es, (size_t)h.payload_bytes, pp, path);
+        if (!rc && h.norms_bytes) rc = file_to_device(f, h.norms_offset, idx->xnorm + idx->n, (size_t)h.norms_bytes, pp, path);
+        if (!rc) idx->n += h.rows;
+    }
+    fclose(f);
+    if (rc) { if (fresh) prs_index_free(idx); return rc; }
+    *out = idx;
+    return 0;
+}
+
+}  // extern "C"

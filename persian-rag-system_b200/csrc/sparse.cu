@@ -882,6 +882,45 @@ static int sparse_search_core(prs_sparse* sp, const long long* d_qptr, const int
     return 0;
 }
 
+// doc-range shards: [nparts, nq, k] float64 (score, global id) lists -> [nq, k], ordered (score desc, then id
+// DESC when tie_high, ASC otherwise).  One CTA per query, rank counting over the nparts*k candidates.
+__global__ void __launch_bounds__(256) merge_parts_f64_kernel(const double* __restrict__ Sp, const long long* __restrict__ Ip, int nparts,
+                                                              long long nq, int k, int tie_high, double* __restrict__ S, long long* __restrict__ I) {
+    extern __shared__ __align__(16) unsigned char fsm[];
+    const int n = nparts * k;
+    double* sc = reinterpret_cast<double*>(fsm);                 // [n] when it fits, else the lists are re-read from L2
+    long long* id = reinterpret_cast<long long*>(sc + n);
+    __shared__ int s_valid;
+    const long long q = blockIdx.x;
+    const int tid = threadIdx.x;
+    const bool staged = n <= 4096;
+    auto at = [&](int i, double& s, long long& d) {
+        const int part = i / k, j = i - part * k;
+        const size_t o = ((size_t)part * nq + q) * k + j;
+        s = Sp[o]; d = Ip[o];
+    };
+    if (tid == 0) s_valid = 0;
+    if (staged) for (int i = tid; i < n; i += 256) at(i, sc[i], id[i]);
+    __syncthreads();
+    int mine = 0;
+    for (int i = tid; i < n; i += 256) {
+        double s; long long d;
+        if (staged) { s = sc[i]; d = id[i]; } else at(i, s, d);
+        if (d < 0) continue;
+        ++mine;
+        int rank = 0;
+        for (int j = 0; j < n; ++j) {
+            double sj; long long dj;
+            if (staged) { sj = sc[j]; dj = id[j]; } else at(j, sj, dj);
+            rank += dj >= 0 && (sj > s || (sj == s && (tie_high ? dj > d : dj < d)));
+        }
+        if (rank < k) { S[q * k + rank] = s; I[q * k + rank] = d; }
+    }
+    if (mine) atomicAdd(&s_valid, mine);
+    __syncthreads();
+    for (int j = s_valid + tid; j < k; j += 256) { S[q * k + j] = 0.0; I[q * k + j] = -1; }
+}
+
 __global__ void sparse_fill_empty_kernel(double* S, long long* I, long long n) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) { S[i] = 0.0; I[i] = -1; }
@@ -1051,6 +1090,21 @@ int prs_sparse_search_device(prs_sparse* sp, const int64_t* q_indptr, const int3
     PRS_LAUNCH_CHECK();
     sp->count_on_device = true;
     return sparse_search_core(sp, (const long long*)q_indptr, q_terms, q_weights, nq, k, S, (long long*)I, st);
+}
+
+int prs_merge_topk_f64_device(const double* S_parts, const int64_t* I_parts, int nparts, int64_t nq, int k, int tie_high_id,
+                              double* S, int64_t* I, int device, void* stream) {
+    if (nparts < 1 || nparts > 64 || nq < 0 || k < 1 || k > PRS_MAX_K) { set_error("merge_f64: bad arguments"); return PRS_EINVAL; }
+    if (nq == 0) return 0;
+    if (!S_parts || !I_parts || !S || !I) { set_error("merge_f64: null pointer"); return PRS_EINVAL; }
+    DeviceGuard g(device);
+    const int n = nparts * k;
+    const size_t smem = n <= 4096 ? (size_t)n * 16 : 16;
+    PRS_CUDA(cudaFuncSetAttribute(merge_parts_f64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    merge_parts_f64_kernel<<<(unsigned)nq, 256, smem, (cudaStream_t)stream>>>(S_parts, (const long long*)I_parts, nparts, nq, k, tie_high_id,
+                                                                             S, (long long*)I);
+    PRS_LAUNCH_CHECK();
+    return 0;
 }
 
 int prs_sparse_search_host(prs_sparse* sp, const int64_t* q_indptr, const int32_t* q_terms, const double* q_weights,

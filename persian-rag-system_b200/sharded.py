@@ -42,6 +42,79 @@ def merge_topk(D_parts, I_parts, largest: bool, tie_high_id: bool = False):
     return D, I
 
 
+def merge_topk_f64(S_parts, I_parts, tie_high_id: bool = True):
+    """[G, nq, k] float64 scores + int64 global ids (CUDA tensors) -> merged ([nq, k], [nq, k]), largest
+    first; ties by id descending (the sparse path's order) unless `tie_high_id` is False."""
+    import torch
+    G, nq, k = (int(s) for s in S_parts.shape)
+    S_parts = S_parts.to(torch.float64).contiguous()
+    I_parts = I_parts.to(torch.int64).contiguous()
+    S = torch.empty((nq, k), dtype=torch.float64, device=S_parts.device)
+    I = torch.empty((nq, k), dtype=torch.int64, device=S_parts.device)
+    st = torch.cuda.current_stream(S_parts.device).cuda_stream
+    check(_lib.lib().prs_merge_topk_f64_device(ctypes.c_void_p(S_parts.data_ptr()), ctypes.c_void_p(I_parts.data_ptr()), G, nq, k,
+                                               1 if tie_high_id else 0, ctypes.c_void_p(S.data_ptr()), ctypes.c_void_p(I.data_ptr()),
+                                               int(S_parts.device.index or 0), ctypes.c_void_p(st)))
+    return S, I
+
+
+class ShardedSparseIndex:
+    """Sparse (BM25 / TF-IDF) index split by DOC RANGE across the ranks of a process group:
+    rank g holds the postings of docs [lo_g, hi_g) -- the rows of the global doc-by-term weight matrix that
+    belong to its block; idf / avgdl / vocabulary are global quantities baked into those weights by whoever
+    built the matrix (e.g. `sparse.build_bm25_csr` over the whole corpus, then sliced by rows).  A search
+    scores the local block, all-gathers the [nq, k] (score, global id) lists over NCCL and merges them on
+    the device with ties on GLOBAL ids, so the result equals the unsharded index's."""
+
+    def __init__(self, indptr, indices, values, n_terms: int, doc_offset: int, n_docs_global: int, group=None,
+                 device: int | None = None, mode: str = "exact"):
+        import torch.distributed as dist
+        from .sparse import SparseIndex
+        self.dist, self.group = dist, group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.local = SparseIndex(indptr, indices, values, n_terms, device, mode)
+        self.local.set_id_offset(int(doc_offset))
+        self.offset, self.ndocs_global = int(doc_offset), int(n_docs_global)
+        if self.world > 1:
+            dist.barrier(group=group)
+
+    @classmethod
+    def from_global_csr(cls, indptr, indices, values, n_terms: int, group=None, device: int | None = None, mode: str = "exact"):
+        """Every rank holds (or can read) the global CSR: keep only this rank's contiguous row block."""
+        import torch.distributed as dist
+        rank = dist.get_rank(group) if dist.is_initialized() else 0
+        world = dist.get_world_size(group) if dist.is_initialized() else 1
+        indptr = np.asarray(indptr, dtype=np.int64)
+        n = int(indptr.shape[0] - 1)
+        lo, hi = shard_bounds(n, world, rank)
+        a, b = int(indptr[lo]), int(indptr[hi])
+        return cls(indptr[lo:hi + 1] - indptr[lo], np.asarray(indices)[a:b], np.asarray(values)[a:b], n_terms, lo, n, group, device, mode)
+
+    def search_device(self, q_indptr, q_terms, q_weights, k: int):
+        """Query CSR as CUDA tensors (replicated on every rank) -> (S float64 [nq, k], I int64 [nq, k]) CUDA
+        tensors with global doc ids, identical on every rank."""
+        import torch
+        S, I = self.local.search_device(q_indptr, q_terms, q_weights, k)
+        if self.world == 1:
+            return S, I
+        nq = int(S.shape[0])
+        Sg = torch.empty((self.world * nq, k), dtype=S.dtype, device=S.device)
+        Ig = torch.empty((self.world * nq, k), dtype=I.dtype, device=I.device)
+        self.dist.all_gather_into_tensor(Sg, S, group=self.group)
+        self.dist.all_gather_into_tensor(Ig, I, group=self.group)
+        return merge_topk_f64(Sg.view(self.world, nq, k), Ig.view(self.world, nq, k), tie_high_id=True)
+
+    def search(self, q_indptr, q_terms, q_weights, k: int):
+        """numpy in / numpy out convenience around `search_device`."""
+        import torch
+        dev = torch.device("cuda", self.local.device)
+        S, I = self.search_device(torch.from_numpy(np.ascontiguousarray(q_indptr, dtype=np.int64)).to(dev),
+                                  torch.from_numpy(np.ascontiguousarray(q_terms, dtype=np.int32)).to(dev),
+                                  torch.from_numpy(np.ascontiguousarray(q_weights, dtype=np.float64)).to(dev), k)
+        return S.cpu().numpy(), I.cpu().numpy()
+
+
 class ShardedFlatIndex:
     """FlatIndex whose rows are split across the ranks of a torch.distributed process group."""
 
@@ -118,6 +191,28 @@ class ShardedFlatIndex:
             self._xs = []
         except Exception:
             pass
+
+    def write(self, dirpath: str) -> None:
+        """Persist the sharded corpus: every rank writes its block as one shard file (the HBM image + norms),
+        rank 0 the manifest (container.py)."""
+        from .container import write_sharded
+        write_sharded(self, dirpath)
+
+    def load(self, dirpath: str) -> None:
+        """Load this rank's shard file(s) of a container written by `write` (any number of files >= ranks),
+        in parallel with the other ranks: a straight disk -> pinned -> HBM copy."""
+        from .container import read_manifest, read_sharded
+        man = read_manifest(dirpath)
+        idx = read_sharded(dirpath, self.local.device, self.rank, self.world)
+        if idx.d != self.d or idx.metric_type != self.metric or idx.storage != self.local.storage:
+            raise _lib.PrsError(_lib.EINVAL, "container does not match this index (d / metric / storage)")
+        self.local = idx
+        from .container import shards_for_rank
+        mine = list(shards_for_rank(len(man["shards"]), self.world, self.rank))
+        self.offset = int(man["shards"][mine[0]]["id_offset"])
+        self.ntotal_global = int(man["ntotal"])
+        if self.world > 1:
+            self.dist.barrier(group=self.group)
 
     def add_local(self, x, global_offset: int, n_total_global: int) -> None:
         """Add this rank's row block; `global_offset` is the global id of its first row."""

@@ -376,6 +376,72 @@ def test_16bit_container_roundtrip(P, storage, tmp_path):
     assert np.array_equal(back.search(q, 5)[1], idx.search(q, 5)[1])
 
 
+@pytest.mark.parametrize("storage", ["fp16", "bf16", "fp32"])
+def test_sharded_container_roundtrip_and_mmap(P, storage, tmp_path):
+    """f-2: shard files hold the HBM image (T64 for 16-bit) + norms, page aligned; a load is a straight copy."""
+    import json
+    import struct
+    from persian_rag_system_b200 import container as C
+    rng = np.random.default_rng(8)
+    n, d = 1000, 200                                         # d not a multiple of 64, rows not a multiple of 64
+    x = rng.standard_normal((n, d)).astype(np.float32)
+    q = rng.standard_normal((9, d)).astype(np.float32)
+    whole = P.FlatIndex(d, P.METRIC_L2, storage)
+    whole.add(x)
+    Dw, Iw = whole.search(q, 7)
+    # one shard
+    C.write_sharded(whole, str(tmp_path / "one"))
+    man = json.load(open(tmp_path / "one" / "manifest.json"))
+    assert man["ntotal"] == n and man["storage"] == storage and len(man["shards"]) == 1
+    back = C.read_sharded(str(tmp_path / "one"))
+    assert back.ntotal == n and back.d == d and back.storage == storage and back.metric_type == P.METRIC_L2
+    D, I = back.search(q, 7)
+    assert np.array_equal(I, Iw) and np.array_equal(D, Dw)
+    assert np.array_equal(back.reconstruct_n(0, n), whole.reconstruct_n(0, n))
+    # the file layout: 128-byte header, page-aligned payload and norms; norms are those of the STORED rows
+    raw = open(tmp_path / "one" / man["shards"][0]["file"], "rb").read()
+    assert raw[:4] == b"PRST"
+    ver, dd, pitch, metric, st = struct.unpack_from("<5i", raw, 4)
+    rows, rows_pad, id_off, p_off, p_bytes, n_off, n_bytes = struct.unpack_from("<7q", raw, 24)
+    es = 4 if storage == "fp32" else 2
+    assert (ver, dd, pitch, rows, id_off) == (1, d, 256, n, 0) and p_off % 4096 == 0 and n_off % 4096 == 0
+    assert rows_pad == (n if storage == "fp32" else 1024) and p_bytes == rows_pad * pitch * es and n_bytes == 4 * n
+    norms = np.memmap(tmp_path / "one" / man["shards"][0]["file"], dtype="<f4", mode="r", offset=n_off, shape=(n,))
+    xs = whole.reconstruct_n(0, n).astype(np.float64)
+    np.testing.assert_allclose(norms, (xs * xs).sum(1), rtol=1e-5)
+    # three shards with global ids (what three ranks would write), loaded by 1 rank (appended) and by rank 1 of 3
+    bounds = [(0, 384), (384, 768), (768, n)]                  # non-final shards end on 64-row block boundaries
+    os.makedirs(tmp_path / "three")
+    for i, (lo, hi) in enumerate(bounds):
+        part = P.FlatIndex(d, P.METRIC_L2, storage)
+        part.add(x[lo:hi])
+        part.set_id_offset(lo)
+        C.write_shard(part, str(tmp_path / "three" / f"shard_{i:05d}.prst"))
+    json.dump({"format": C.FORMAT, "d": d, "metric": P.METRIC_L2, "storage": storage, "ntotal": n,
+               "shards": [{"file": f"shard_{i:05d}.prst", "rows": hi - lo, "id_offset": lo} for i, (lo, hi) in enumerate(bounds)]},
+              open(tmp_path / "three" / "manifest.json", "w"))
+    allin = C.read_sharded(str(tmp_path / "three"))
+    D, I = allin.search(q, 7)
+    assert allin.ntotal == n and np.array_equal(I, Iw) and np.array_equal(D, Dw)
+    mid = C.read_sharded(str(tmp_path / "three"), rank=1, world=3)
+    Dm, Im = mid.search(q, 7)
+    ref = P.FlatIndex(d, P.METRIC_L2, storage)
+    ref.add(x[384:768])
+    Dr, Ir = ref.search(q, 7)
+    assert mid.ntotal == 384 and np.array_equal(Im, Ir + 384) and np.array_equal(Dm, Dr)
+    # errors: truncated file, append at a non-block boundary, foreign file
+    open(tmp_path / "trunc.prst", "wb").write(raw[: len(raw) // 2])
+    with pytest.raises(P.PrsError):
+        C.read_shard(str(tmp_path / "trunc.prst"))
+    if storage != "fp32":
+        odd = P.FlatIndex(d, P.METRIC_L2, storage)
+        odd.add(x[:100])
+        with pytest.raises(P.PrsError):
+            C.read_shard(str(tmp_path / "three" / "shard_00001.prst"), into=odd)
+    with pytest.raises(P.PrsError):
+        C.read_shard(os.path.join(os.path.dirname(__file__), "golden", "indices", "drugs_sentence_chunks.index"))
+
+
 def test_auto_path_selection(P):
     rng = np.random.default_rng(6)
     x = rng.standard_normal((2048, 256)).astype(np.float32)

@@ -74,6 +74,51 @@ def _worker(rank, world, port, out_dir):
             if not flag.item():
                 bad.append((exchange, n, d, nq, k, storage, metric))
             del sh, whole
+    # container: every rank writes its block in parallel, a fresh sharded index loads it back (f-2)
+    n, d = 20000, 128
+    base = np.random.default_rng(n + d).standard_normal((n, d)).astype(np.float32)
+    sh = ShardedFlatIndex(d, 1, "fp16", device=rank, exchange="p2p", nq_cap=64, k_cap=16)
+    lo, hi = shard_bounds(n, world, rank)
+    sh.add_local(base[lo:hi], lo, n)
+    qd = torch.from_numpy(base[:33]).to(dev)
+    D0, I0 = sh.search(qd, 10)
+    cdir = os.path.join(out_dir, "container")
+    sh.write(cdir)
+    sh2 = ShardedFlatIndex(d, 1, "fp16", device=rank, exchange="p2p", nq_cap=64, k_cap=16)
+    sh2.load(cdir)
+    D1, I1 = sh2.search(qd, 10)
+    ok = sh2.ntotal == n and bool(torch.equal(I1, I0)) and bool(torch.equal(D1, D0))
+    flag = torch.tensor([1 if ok else 0], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if not flag.item():
+        bad.append(("container",))
+    del sh, sh2
+    # sparse path, doc-range shards on real GPUs: NCCL all-gather of the [nq, k] float64 lists + device merge
+    from persian_rag_system_b200.sharded import ShardedSparseIndex
+    from persian_rag_system_b200.sparse import build_bm25_csr
+    rng = np.random.default_rng(5)
+    vocab = [f"w{i}" for i in range(300)]
+    docs = [[vocab[j] for j in rng.integers(0, 300, size=int(rng.integers(1, 30)))] for _ in range(4000)]
+    docs = docs + docs[:500]
+    b = build_bm25_csr(docs)
+    qs = [docs[i][:5] for i in range(20)] + [["nope"]]
+    helper = P.BM25Index(docs[:8], device=rank)
+    helper.vocab = b["vocab"]
+    ip, qt, qw = helper.encode_queries(qs)
+    dip, dqt, dqw = (torch.from_numpy(v).to(dev) for v in (ip, qt, qw))
+    sparse_bad = 0
+    for mode in ("exact", "throughput"):
+        whole = P.SparseIndex(b["indptr"], b["indices"], b["weights"], len(b["vocab"]), device=rank, mode=mode)
+        Sw, Iw = whole.search_device(dip, dqt, dqw, 10)
+        shs = ShardedSparseIndex.from_global_csr(b["indptr"], b["indices"], b["weights"], len(b["vocab"]), device=rank, mode=mode)
+        S, I = shs.search_device(dip, dqt, dqw, 10)
+        ok = bool(torch.equal(S, Sw)) and bool(torch.equal(I, Iw))
+        flag = torch.tensor([1 if ok else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        sparse_bad += 0 if flag.item() else 1
+        del shs, whole
+    if sparse_bad:
+        bad.append(("sparse", sparse_bad))
     # a peer that never searches: the fused exchange gives up after the timeout, answers -1 and reports
     sh = ShardedFlatIndex(32, 1, "fp16", device=rank, exchange="p2p", nq_cap=8, k_cap=16, lanes=1)
     x = np.random.default_rng(1).standard_normal((256, 32)).astype(np.float32)

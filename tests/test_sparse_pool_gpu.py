@@ -214,6 +214,46 @@ def test_throughput_mode_raw_csr_many_tiles_negative_weights_and_shared_terms(P)
                 assert np.array_equal(S[r], sc[I[r]])
 
 
+# ------------------------------------------------------------------ doc-range shards (emulated on one device)
+@pytest.mark.parametrize("G", [2, 5])
+@pytest.mark.parametrize("mode", ["exact", "throughput"])
+def test_doc_range_sharded_sparse_equals_unsharded(P, G, mode):
+    """SURVEY 8e: every shard holds the postings of its doc block (global idf / avgdl baked into the weights);
+    local top-k with global ids -> float64 merge kernel with ties on global ids (id DESC) == unsharded."""
+    import torch
+    from persian_rag_system_b200.sharded import merge_topk_f64, shard_bounds
+    from persian_rag_system_b200.sparse import build_bm25_csr
+    rng = np.random.default_rng(G)
+    vocab = [f"w{i}" for i in range(400)]
+    base = [[vocab[j] for j in rng.integers(0, 400, size=int(rng.integers(1, 40)))] for _ in range(3000)]
+    docs = base + base[:700] + base[:50]                      # duplicate docs across shards: exact score ties
+    qs = [base[i][:4] for i in range(12)] + [["nope"], [vocab[3], vocab[3], vocab[7]]]
+    b = build_bm25_csr(docs)
+    whole = P.SparseIndex(b["indptr"], b["indices"], b["weights"], len(b["vocab"]), mode=mode)
+    bm = P.BM25Index(docs)                                    # only for encode_queries
+    ip, qt, qw = bm.encode_queries(qs)
+    dev = torch.device("cuda", 0)
+    dip, dqt, dqw = (torch.from_numpy(v).to(dev) for v in (ip, qt, qw))
+    k = 10
+    Sw, Iw = whole.search_device(dip, dqt, dqw, k)
+    Sp, Ip = [], []
+    n = len(docs)
+    for g in range(G):
+        lo, hi = shard_bounds(n, G, g)
+        a, e = int(b["indptr"][lo]), int(b["indptr"][hi])
+        sh = P.SparseIndex(b["indptr"][lo:hi + 1] - b["indptr"][lo], b["indices"][a:e], b["weights"][a:e], len(b["vocab"]), mode=mode)
+        sh.set_id_offset(lo)
+        S, I = sh.search_device(dip, dqt, dqw, k)
+        Sp.append(S)
+        Ip.append(I)
+    S, I = merge_topk_f64(torch.stack(Sp), torch.stack(Ip))
+    assert torch.equal(S, Sw) and torch.equal(I, Iw)
+    ob = O.BM25OkapiOracle(docs)
+    for r, q in enumerate(qs):
+        sc = ob.get_scores(q)
+        assert I[r].tolist() == O.argsort_topk_canonical(sc, k).tolist() and np.array_equal(S[r].cpu().numpy(), sc[I[r].cpu().numpy()])
+
+
 # ------------------------------------------------------------------ pooling epilogue
 def test_pool_golden(P, gold_dir):
     import torch
