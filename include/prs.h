@@ -151,7 +151,7 @@ int prs_merge_topk_f64_device(const double* S_parts, const int64_t* I_parts, int
  * the local scan followed by ONE kernel that merges the local per-CTA lists, stores the local
  * top-k into every peer's buffer, waits for the peers' lists and merges them: no collective
  * launch, 12*nq*k bytes per rank pair.  It is a collective: every rank must call it the same
- * number of times with the same nq and k, and must hold at least one row.  Results are identical
+ * number of times with the same nq and k (a rank whose shard is empty contributes empty lists).  Results are identical
  * on every rank and identical to the unsharded index (ties on global ids).
  * nq_cap / k_cap bound the nq*k of one search (buffer = 2*n_ranks*nq_cap*k_cap*12 bytes).
  * ------------------------------------------------------------------------------------- */
@@ -171,6 +171,36 @@ int prs_xchg_set_timeout_ms(prs_xchg* x, int64_t ms);
 void prs_xchg_free(prs_xchg* x);
 int prs_index_search_sharded_device(prs_index* idx, prs_xchg* x, const void* q, int qdtype, int64_t nq, int k,
                                     float* D, int64_t* I, void* stream);
+
+/* link exchange buffers created by ONE process on different devices (peer access enabled between them): the
+ * in-process alternative to prs_xchg_get_handle / prs_xchg_open_peers.  xs[i] must have rank i of n. */
+int prs_xchg_link_local(prs_xchg** xs, int n);
+
+/* ---------------------------------------------------------------------------------------
+ * One process, several GPUs (`devices=[...]`).  The reference's retriever is a single Python
+ * process (src/retrieval.py:13; scripts/gradio_luncher.py:354-362 shares one instance between threads); a
+ * prs_group lets that process use every GPU of the box: one shard index, one exchange buffer and one host
+ * worker thread per device, peer access between all pairs, the same fused merge + NVLink exchange kernel as
+ * the one-process-per-GPU layout.  Rows are dealt in contiguous ascending blocks of ceil(n_total / ndev) rows
+ * (call prs_group_reserve first; the first add fixes the block size otherwise), results are identical to the
+ * single index.  nq_cap / k_cap bound one exchange (larger batches are chunked).  q / D / I of the device entry
+ * point live on devs[0] (or in page-locked host memory); `stream` is a stream of devs[0].
+ * ------------------------------------------------------------------------------------- */
+typedef struct prs_group prs_group;
+int prs_group_create(int d, int metric, int storage, const int* devs, int ndev, int64_t nq_cap, int k_cap, prs_group** out);
+void prs_group_free(prs_group* g);
+int prs_group_ndev(const prs_group* g);
+int64_t prs_group_ntotal(const prs_group* g);
+int prs_group_d(const prs_group* g);
+int prs_group_metric(const prs_group* g);
+int prs_group_storage(const prs_group* g);
+int64_t prs_group_shard_rows(const prs_group* g, int i);
+int prs_group_reserve(prs_group* g, int64_t n_total);
+int prs_group_add_host(prs_group* g, const float* x, int64_t n);
+int prs_group_add_device(prs_group* g, const void* x, int dtype, int64_t n, void* stream);
+int prs_group_search_host(prs_group* g, const float* q, int64_t nq, int k, float* D, int64_t* I);
+int prs_group_search_device(prs_group* g, const void* q, int qdtype, int64_t nq, int k, float* D, int64_t* I, void* stream);
+int prs_group_reconstruct_host(prs_group* g, int64_t i0, int64_t n, float* out);
 
 /* ---------------------------------------------------------------------------------------
  * Sparse scoring (BM25 / TF-IDF) over an inverted index.

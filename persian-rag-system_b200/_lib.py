@@ -55,6 +55,21 @@ SIGNATURES = {
     "prs_xchg_set_timeout_ms": (c_int, [c_void_p, c_i64]),
     "prs_xchg_free": (None, [c_void_p]),
     "prs_index_search_sharded_device": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_i64, c_int, c_void_p, c_void_p, c_void_p]),
+    "prs_xchg_link_local": (c_int, [c_void_p, c_int]),
+    "prs_group_create": (c_int, [c_int, c_int, c_int, c_void_p, c_int, c_i64, c_int, ctypes.POINTER(c_void_p)]),
+    "prs_group_free": (None, [c_void_p]),
+    "prs_group_ndev": (c_int, [c_void_p]),
+    "prs_group_ntotal": (c_i64, [c_void_p]),
+    "prs_group_d": (c_int, [c_void_p]),
+    "prs_group_metric": (c_int, [c_void_p]),
+    "prs_group_storage": (c_int, [c_void_p]),
+    "prs_group_shard_rows": (c_i64, [c_void_p, c_int]),
+    "prs_group_reserve": (c_int, [c_void_p, c_i64]),
+    "prs_group_add_host": (c_int, [c_void_p, c_void_p, c_i64]),
+    "prs_group_add_device": (c_int, [c_void_p, c_void_p, c_int, c_i64, c_void_p]),
+    "prs_group_search_host": (c_int, [c_void_p, c_void_p, c_i64, c_int, c_void_p, c_void_p]),
+    "prs_group_search_device": (c_int, [c_void_p, c_void_p, c_int, c_i64, c_int, c_void_p, c_void_p, c_void_p]),
+    "prs_group_reconstruct_host": (c_int, [c_void_p, c_i64, c_i64, c_void_p]),
     "prs_sparse_build": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_i64, ctypes.c_int32, c_int, ctypes.POINTER(c_void_p)]),
     "prs_sparse_free": (None, [c_void_p]),
     "prs_sparse_ndocs": (c_i64, [c_void_p]),

@@ -404,6 +404,10 @@ static int search_device_impl(prs_index* idx, const void* q, int qdtype, long lo
     if (!ws->event) PRS_CUDA(cudaEventCreateWithFlags(&ws->event, cudaEventDisableTiming));
     if (ws->used && ws->stream != st) PRS_CUDA(cudaStreamWaitEvent(st, ws->event, 0));
     struct Rec { prs_index::Workspace* w; cudaStream_t s; ~Rec() { cudaEventRecord(w->event, s); w->stream = s; w->used = true; } } rec{ws, st};
+    if (idx->n == 0 && t_xchg) {
+        // an empty shard of a row-sharded corpus still takes part in the exchange: it contributes empty lists
+        return launch_merge(idx, 0, nq, k, idx->metric == PRS_METRIC_L2 ? 1 : 0, nullptr, D, I, st);
+    }
     if (idx->n == 0) {
         const long long tot = nq * k;
         fill_empty_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(D, (long long*)I, tot,
@@ -760,6 +764,18 @@ static int xchg_take_status(prs_xchg* x) {
     return PRS_ECUDA;
 }
 
+// exchange buffers of ONE process on different devices (group.cu): peer access is enabled, so the peers' buffers
+// are addressed directly instead of through CUDA IPC handles
+int prs_xchg_link_local(prs_xchg** xs, int n) {
+    if (!xs || n < 1 || n > XCHG_MAX_RANKS) { set_error("xchg_link_local: bad arguments"); return PRS_EINVAL; }
+    for (int i = 0; i < n; ++i) if (!xs[i] || xs[i]->G != n || xs[i]->rank != i) { set_error("xchg_link_local: buffer %d does not belong to a group of %d", i, n); return PRS_EINVAL; }
+    for (int i = 0; i < n; ++i) {
+        for (int p = 0; p < n; ++p) xs[i]->peer_base[p] = xs[p]->base;
+        xchg_fill_view(xs[i]);
+    }
+    return 0;
+}
+
 int prs_xchg_status(prs_xchg* x) {
     if (!x) { set_error("null exchange"); return PRS_EINVAL; }
     DeviceGuard g(x->device);
@@ -794,7 +810,6 @@ int prs_index_search_sharded_device(prs_index* idx, prs_xchg* x, const void* q, 
     }
     for (int p = 0; p < x->G; ++p) if (!x->peer_base[p]) { set_error("sharded search: peer %d not opened", p); return PRS_EINVAL; }
     DeviceGuard g(idx->device);
-    if (idx->n == 0) { set_error("sharded search: every rank must hold at least one row"); return PRS_EINVAL; }
     // a timeout reported by an EARLIER search on this context surfaces here (cheap: mapped host word)
     if (int rc = xchg_take_status(x)) return rc;
     struct Scope { ~Scope() { t_xchg = nullptr; } } scope;

@@ -53,9 +53,26 @@ def _default_device() -> int:
 class FlatIndex:
     """Exact (brute-force) dense index resident in HBM."""
 
-    def __init__(self, d: int, metric: int = METRIC_L2, storage="fp32", device: int | None = None, _handle=None):
+    def __init__(self, d: int, metric: int = METRIC_L2, storage="fp32", device: int | None = None, _handle=None,
+                 devices=None, nq_cap: int = 1024, k_cap: int = 128):
         self._h = ctypes.c_void_p()
+        self._g = None                      # prs_group handle when the rows are split over several devices
         self._L = _lib.lib()
+        if devices is not None and len(devices) > 1:
+            # one process, several GPUs (SURVEY 8b `devices=[...]`): contiguous row blocks per device, fused
+            # merge + NVLink exchange kernel, results identical to the single index (csrc/group.cu)
+            if storage not in _STORAGE:
+                raise PrsError(_lib.EINVAL, f"unknown storage {storage!r}")
+            devs = (ctypes.c_int * len(devices))(*[int(v) for v in devices])
+            self._g = ctypes.c_void_p()
+            check(self._L.prs_group_create(int(d), int(metric), _STORAGE[storage], devs, len(devices), int(nq_cap), int(k_cap),
+                                           ctypes.byref(self._g)))
+            self.devices = [int(v) for v in devices]
+            self.device = self.devices[0]
+            self.is_trained = True
+            return
+        if devices is not None and len(devices) == 1:
+            device = int(devices[0])
         if _handle is not None:
             self._h = _handle
         else:
@@ -69,31 +86,46 @@ class FlatIndex:
     # ---- faiss attributes ----
     @property
     def d(self) -> int:
-        return int(self._L.prs_index_d(self._h))
+        return int(self._L.prs_group_d(self._g) if self._g else self._L.prs_index_d(self._h))
 
     @property
     def ntotal(self) -> int:
-        return int(self._L.prs_index_ntotal(self._h))
+        return int(self._L.prs_group_ntotal(self._g) if self._g else self._L.prs_index_ntotal(self._h))
 
     @property
     def metric_type(self) -> int:
-        return int(self._L.prs_index_metric(self._h))
+        return int(self._L.prs_group_metric(self._g) if self._g else self._L.prs_index_metric(self._h))
 
     @property
     def storage(self) -> str:
-        return _STORAGE_NAME[int(self._L.prs_index_storage(self._h))]
+        return _STORAGE_NAME[int(self._L.prs_group_storage(self._g) if self._g else self._L.prs_index_storage(self._h))]
+
+    @property
+    def shard_rows(self):
+        """Rows held by each device (one entry for a single-device index)."""
+        if not self._g:
+            return [self.ntotal]
+        return [int(self._L.prs_group_shard_rows(self._g, i)) for i in range(len(self.devices))]
+
+    def _single_only(self, what: str) -> None:
+        if self._g:
+            raise PrsError(_lib.EUNSUP, f"{what} is not available on a multi-device index")
 
     @property
     def last_path(self) -> str:
+        if self._g:
+            return "group"
         return {0: "none", 1: "cuda-core", 2: "tcgen05"}[int(self._L.prs_index_last_path(self._h))]
 
     def set_path(self, path) -> None:
         """'auto' | 'cuda-core' | 'tcgen05' (tests and benchmarks)."""
+        self._single_only("set_path")
         code = {"auto": 0, "cuda-core": 1, "tcgen05": 2, 0: 0, 1: 1, 2: 2}[path]
         check(self._L.prs_index_set_path(self._h, code))
 
     def set_timing(self, enable: bool) -> None:
         """Bracket every scan-kernel launch with CUDA events on its stream (bench instrumentation)."""
+        self._single_only("set_timing")
         check(self._L.prs_index_set_timing(self._h, 1 if enable else 0))
 
     def scan_time(self):
@@ -109,9 +141,12 @@ class FlatIndex:
         return float(a.value), float(b.value)
 
     def set_id_offset(self, offset: int) -> None:
+        self._single_only("set_id_offset")
         check(self._L.prs_index_set_id_offset(self._h, int(offset)))
 
     def reserve(self, n_total: int) -> None:
+        if self._g:
+            return check(self._L.prs_group_reserve(self._g, int(n_total)))
         check(self._L.prs_index_reserve(self._h, int(n_total)))
 
     # ---- faiss methods ----
@@ -124,13 +159,14 @@ class FlatIndex:
                 raise PrsError(_lib.EINVAL, f"add: expected [n, {self.d}], got {tuple(x.shape)}")
             x = x.contiguous()
             st = torch.cuda.current_stream(x.device).cuda_stream
-            check(self._L.prs_index_add_device(self._h, ctypes.c_void_p(x.data_ptr()), _torch_dtype_code(x),
-                                               int(x.shape[0]), ctypes.c_void_p(st)))
+            fn, h = (self._L.prs_group_add_device, self._g) if self._g else (self._L.prs_index_add_device, self._h)
+            check(fn(h, ctypes.c_void_p(x.data_ptr()), _torch_dtype_code(x), int(x.shape[0]), ctypes.c_void_p(st)))
             return
         x = np.ascontiguousarray(x, dtype=np.float32)
         if x.ndim != 2 or x.shape[1] != self.d:
             raise PrsError(_lib.EINVAL, f"add: expected [n, {self.d}], got {x.shape}")
-        check(self._L.prs_index_add_host(self._h, x.ctypes.data_as(ctypes.c_void_p), int(x.shape[0])))
+        fn, h = (self._L.prs_group_add_host, self._g) if self._g else (self._L.prs_index_add_host, self._h)
+        check(fn(h, x.ctypes.data_as(ctypes.c_void_p), int(x.shape[0])))
 
     def search(self, x, k: int):
         """numpy in -> (D float32 [nq,k], I int64 [nq,k]) numpy out (faiss contract);
@@ -145,6 +181,12 @@ class FlatIndex:
             D = torch.empty((nq, k), dtype=torch.float32, device=x.device)
             I = torch.empty((nq, k), dtype=torch.int64, device=x.device)
             st = torch.cuda.current_stream(x.device).cuda_stream
+            if self._g:
+                if int(x.device.index or 0) != self.device:
+                    raise PrsError(_lib.EINVAL, f"search: queries must live on the group's first device (cuda:{self.device})")
+                check(self._L.prs_group_search_device(self._g, ctypes.c_void_p(x.data_ptr()), _torch_dtype_code(x), nq, k,
+                                                      ctypes.c_void_p(D.data_ptr()), ctypes.c_void_p(I.data_ptr()), ctypes.c_void_p(st)))
+                return D, I
             check(self._L.prs_index_search_device(self._h, ctypes.c_void_p(x.data_ptr()), _torch_dtype_code(x), nq, k,
                                                   ctypes.c_void_p(D.data_ptr()), ctypes.c_void_p(I.data_ptr()),
                                                   ctypes.c_void_p(st)))
@@ -157,23 +199,28 @@ class FlatIndex:
         nq = int(x.shape[0])
         D = np.empty((nq, k), dtype=np.float32)
         I = np.empty((nq, k), dtype=np.int64)
-        check(self._L.prs_index_search_host(self._h, x.ctypes.data_as(ctypes.c_void_p), nq, k,
-                                            D.ctypes.data_as(ctypes.c_void_p), I.ctypes.data_as(ctypes.c_void_p)))
+        fn, h = (self._L.prs_group_search_host, self._g) if self._g else (self._L.prs_index_search_host, self._h)
+        check(fn(h, x.ctypes.data_as(ctypes.c_void_p), nq, k, D.ctypes.data_as(ctypes.c_void_p), I.ctypes.data_as(ctypes.c_void_p)))
         return D, I
 
     def search_into(self, q_ptr: int, nq: int, k: int, D_ptr: int, I_ptr: int) -> None:
         """Raw host-pointer search (pinned buffers in benchmarks): no allocation per call."""
+        self._single_only("search_into")
         check(self._L.prs_index_search_host(self._h, ctypes.c_void_p(q_ptr), int(nq), int(k),
                                             ctypes.c_void_p(D_ptr), ctypes.c_void_p(I_ptr)))
 
     def reconstruct_n(self, i0: int = 0, n: int | None = None) -> np.ndarray:
         n = self.ntotal - i0 if n is None else n
         out = np.empty((n, self.d), dtype=np.float32)
-        check(self._L.prs_index_reconstruct_host(self._h, int(i0), int(n), out.ctypes.data_as(ctypes.c_void_p)))
+        fn, h = (self._L.prs_group_reconstruct_host, self._g) if self._g else (self._L.prs_index_reconstruct_host, self._h)
+        check(fn(h, int(i0), int(n), out.ctypes.data_as(ctypes.c_void_p)))
         return out
 
     def __del__(self):
         try:
+            if getattr(self, "_g", None) is not None and self._g.value:
+                self._L.prs_group_free(self._g)
+                self._g = None
             if getattr(self, "_h", None) is not None and self._h.value:
                 self._L.prs_index_free(self._h)
                 self._h = ctypes.c_void_p()
@@ -181,28 +228,44 @@ class FlatIndex:
             pass
 
 
-def IndexFlatL2(d: int, storage="fp32", device: int | None = None) -> FlatIndex:
+def IndexFlatL2(d: int, storage="fp32", device: int | None = None, devices=None) -> FlatIndex:
     """faiss.IndexFlatL2(d) -- src/create_embeddings.py:130"""
-    return FlatIndex(d, METRIC_L2, storage, device)
+    return FlatIndex(d, METRIC_L2, storage, device, devices=devices)
 
 
-def IndexFlatIP(d: int, storage="fp32", device: int | None = None) -> FlatIndex:
+def IndexFlatIP(d: int, storage="fp32", device: int | None = None, devices=None) -> FlatIndex:
     """faiss.IndexFlatIP(d)"""
-    return FlatIndex(d, METRIC_INNER_PRODUCT, storage, device)
+    return FlatIndex(d, METRIC_INNER_PRODUCT, storage, device, devices=devices)
 
 
 def write_index(index: FlatIndex, path: str) -> None:
     """faiss.write_index(index, path) -- src/create_embeddings.py:136.  fp32 storage writes faiss's
     byte-exact IndexFlat file."""
+    if index._g:
+        # gather the row blocks of all devices into a single-device index of the same storage, then write that
+        tmp = FlatIndex(index.d, index.metric_type, index.storage, index.device)
+        tmp.reserve(index.ntotal)
+        step = max(1, (64 << 20) // (4 * index.d))
+        for i0 in range(0, index.ntotal, step):
+            tmp.add(index.reconstruct_n(i0, min(step, index.ntotal - i0)))
+        index = tmp
     check(index._L.prs_index_write(index._h, os.fsencode(path)))
 
 
-def read_index(path: str, storage="fp32", device: int | None = None) -> FlatIndex:
-    """faiss.read_index(path) -- src/retrieval.py:55"""
+def read_index(path: str, storage="fp32", device: int | None = None, devices=None) -> FlatIndex:
+    """faiss.read_index(path) -- src/retrieval.py:55.  `devices=[...]`: the rows are split over those GPUs."""
     if storage not in _STORAGE:
         raise PrsError(_lib.EINVAL, f"unknown storage {storage!r}")
     L = _lib.lib()
     h = ctypes.c_void_p()
-    dev = _default_device() if device is None else int(device)
+    dev = (_default_device() if device is None else int(device)) if not devices else int(devices[0])
     check(L.prs_index_read(os.fsencode(path), _STORAGE[storage], dev, ctypes.byref(h)))
-    return FlatIndex(0, _handle=h, device=dev)
+    one = FlatIndex(0, _handle=h, device=dev)
+    if not devices or len(devices) < 2:
+        return one
+    grp = FlatIndex(one.d, one.metric_type, storage, devices=devices)
+    grp.reserve(one.ntotal)
+    step = max(1, (64 << 20) // (4 * one.d))
+    for i0 in range(0, one.ntotal, step):
+        grp.add(one.reconstruct_n(i0, min(step, one.ntotal - i0)))      # values are exactly representable in `storage`
+    return grp

@@ -64,11 +64,13 @@ class RetrievalSystem:
 
     encoder -- any object with `.encode(list[str], device=...) -> ndarray`; used instead of loading
                `SentenceTransformer(model_path)` (the encoders themselves are unchanged, north-star);
-    storage -- how the dense corpus is held in HBM: "fp32" (reference parity), "fp16", "bf16".
+    storage -- how the dense corpus is held in HBM: "fp32" (reference parity), "fp16", "bf16";
+    devices -- GPUs the dense corpus is split over inside this ONE process (the reference and its
+               Gradio app are single-process): contiguous row blocks, results identical to one device.
     """
 
-    def __init__(self, method="dense", model_path=None, device=None, encoder=None, storage="fp32"):
-        self.method, self.storage = method, storage
+    def __init__(self, method="dense", model_path=None, device=None, encoder=None, storage="fp32", devices=None):
+        self.method, self.storage, self.devices = method, storage, devices
         self.device = device or ("cuda" if _cuda_available() else "cpu")
         self.embedding_model = encoder
         if encoder is None and method in ("dense", "hybrid") and model_path:
@@ -114,8 +116,9 @@ class RetrievalSystem:
         return True
 
     def _open_dense(self, path):
-        self.faiss_index = read_index(path, storage=self.storage)
-        print(f"✓ Loaded FAISS index with {self.faiss_index.ntotal} vectors into HBM ({self.storage})")
+        self.faiss_index = read_index(path, storage=self.storage, devices=self.devices)
+        where = f"{len(self.devices)} GPUs" if self.devices and len(self.devices) > 1 else "HBM"
+        print(f"✓ Loaded FAISS index with {self.faiss_index.ntotal} vectors into {where} ({self.storage})")
 
     def _build_bm25(self):
         # whitespace tokens, no lower-casing, no stop words: src/retrieval.py:66

@@ -152,3 +152,45 @@ def test_sharded_search_on_real_gpus_equals_unsharded(tmp_path):
         res = np.load(tmp_path / f"r{r}.npy")
         assert res[0] == 0, f"rank {r}: {res[0]} sharded cases differ from the unsharded index"
         assert res[1] == 1, f"rank {r}: timeout handling"
+
+
+@pytest.mark.skipif(_ngpu() < 2, reason="needs >= 2 GPUs on one box (gpurun --gpus 2)")
+@pytest.mark.timeout(600)
+def test_single_process_multi_device_index_equals_single_device(tmp_path):
+    """SURVEY 8b `devices=[...]`: ONE process (like the reference's RetrievalSystem / Gradio app) splits the rows
+    over the GPUs of the box -- worker thread per device, peer access, the fused merge + exchange kernel -- and
+    returns exactly what the single-device index returns."""
+    import torch
+    import persian_rag_system_b200 as P
+    from oracle import oracle as O
+    devs = list(range(min(_ngpu(), 8)))
+    for (n, d, nq, k, storage, metric) in CASES + [(125, 384, 9, 5, "fp32", 1), (125, 384, 9, 5, "fp16", 1), (3, 32, 2, 5, "fp32", 0)]:
+        rng = np.random.default_rng(n + d)
+        base = rng.standard_normal((n, d)).astype(np.float32)
+        if n > 200:
+            base[n // 2: n // 2 + 50] = base[:50]              # ties on global ids across the device blocks
+        q = rng.standard_normal((nq, d)).astype(np.float32)
+        q[:2] = base[:2]
+        whole = P.FlatIndex(d, metric, storage, device=0)
+        whole.add(base)
+        grp = P.FlatIndex(d, metric, storage, devices=devs, nq_cap=128, k_cap=128)
+        grp.reserve(n)
+        a, b = n // 3, 2 * n // 3
+        grp.add(base[:a])                                       # host rows
+        grp.add(torch.from_numpy(base[a:b]).to(f"cuda:{devs[-1]}"))   # rows produced on another device of the group
+        grp.add(base[b:])
+        assert grp.ntotal == n and sum(grp.shard_rows) == n and grp.d == d and grp.storage == storage
+        Dw, Iw = whole.search(q, k)
+        D, I = grp.search(q, k)                                 # nq > nq_cap is chunked
+        assert np.array_equal(I, Iw) and np.array_equal(D, Dw), (n, d, nq, k, storage, metric)
+        Dt, It = grp.search(torch.from_numpy(q).to(f"cuda:{devs[0]}"), k)
+        assert np.array_equal(It.cpu().numpy(), Iw) and np.array_equal(Dt.cpu().numpy(), Dw)
+        assert np.array_equal(grp.reconstruct_n(0, n), whole.reconstruct_n(0, n))
+    # the drop-in surface: read_index / RetrievalSystem over several devices, byte-exact write-back
+    gold = os.path.join(ROOT, "tests", "golden", "indices", "drugs_sentence_chunks.index")
+    idx = P.read_index(gold, devices=devs)
+    x, _ = O.read_faiss_flat(gold)
+    D, I = idx.search(x[:7], 1)
+    assert I[:, 0].tolist() == list(range(7)) and (D[:, 0] == 0).all()
+    P.write_index(idx, str(tmp_path / "back.index"))
+    assert open(tmp_path / "back.index", "rb").read() == open(gold, "rb").read()
