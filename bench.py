@@ -58,6 +58,10 @@ def parse():
                     help="searches in flight in the extra `pipelined` measurement (alternating CUDA streams / index workspaces); 1 = skip it")
     ap.add_argument("--capacity-rows", type=int, default=50_000_000,
                     help="rows per GPU of the secondary weak-scaling measurement (configs[4] share: 400M x 384 over 8 GPUs); 0 = skip")
+    ap.add_argument("--extras", default="c0,c2,c3,c4",
+                    help="secondary north-star configs measured after the headline (extra JSON keys): c0 = the reference's own call shape "
+                         "(125 x 384 fp32, nq=1, k=5, latency), c2 = 50M x 512 fp16 k=100, c3 = BM25 on 10M docs x 4096 queries, "
+                         "c4 = batch x k sweep on the 50M x 384 per-GPU share; 'none' skips them")
     ap.add_argument("--no-sweep", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sweep-out", default="")
@@ -160,18 +164,39 @@ def use_all_host_threads():
 # ------------------------------------------------------------------------------------------------
 # CPU leg: the oracle port (faiss IndexFlat restated: sgemm blocks + threshold/heap), all host cores
 # ------------------------------------------------------------------------------------------------
-def cpu_search_timed(x32, q, k, metric_code, budget_s, min_reps=1):
+def cpu_flat_search():
+    """(callable(x32, q, k, metric) -> (D, I), kind, note): real faiss-cpu when it is importable (site-packages or
+    baseline/_ref), else the numpy/OpenBLAS restatement of faiss IndexFlat.search (the oracle "port")."""
     from oracle import oracle as O
-    O.flat_search_np_threshold(x32[: min(len(x32), 131072)], q, k, metric_code)       # warm BLAS threads
+    faiss = O.reference_library("faiss")
+    if faiss is not None:
+        cache = {}
+
+        def run(x32, q, k, metric):
+            key = (id(x32), metric)
+            if key not in cache:                             # index.add is not part of a search step
+                cache.clear()
+                idx = faiss.IndexFlatL2(x32.shape[1]) if metric == O.METRIC_L2 else faiss.IndexFlatIP(x32.shape[1])
+                idx.add(np.ascontiguousarray(x32, dtype=np.float32))
+                cache[key] = idx
+            return cache[key].search(np.ascontiguousarray(q, dtype=np.float32), k)
+        return run, "reference", f"faiss {getattr(faiss, '__version__', '?')} IndexFlat.search (the reference's own library)"
+    return (lambda x32, q, k, metric: O.flat_search_np_threshold(x32, q, k, metric)), "port", \
+        "faiss-cpu/rank_bm25 wheels absent; numpy+OpenBLAS restatement of faiss IndexFlat.search"
+
+
+def cpu_search_timed(x32, q, k, metric_code, budget_s, min_reps=1):
+    search, kind, note = cpu_flat_search()
+    search(x32[: min(len(x32), 131072)], q, k, metric_code)       # warm BLAS threads
     times, res = [], None
     t_all = time.perf_counter()
     while len(times) < min_reps or (time.perf_counter() - t_all) < budget_s:
         t0 = time.perf_counter()
-        res = O.flat_search_np_threshold(x32, q, k, metric_code)
+        res = search(x32, q, k, metric_code)
         times.append(time.perf_counter() - t0)
         if len(times) >= 50:
             break
-    return times, res
+    return times, res, kind, note
 
 
 def run_reference(a):
@@ -194,11 +219,12 @@ def run_reference(a):
     Q = torch.randn(a.warmup + a.steps, a.batch, a.d, generator=gq)
     Q /= Q.norm(dim=2, keepdim=True)
     Q = Q.numpy()
+    search, kind, note = cpu_flat_search()
     for w in range(a.warmup):
-        O.flat_search_np_threshold(x32, Q[w], a.k, metric_code)
+        search(x32, Q[w], a.k, metric_code)
     t0 = time.perf_counter()
     for s in range(a.steps):
-        O.flat_search_np_threshold(x32, Q[a.warmup + s], a.k, metric_code)
+        search(x32, Q[a.warmup + s], a.k, metric_code)
     dt = time.perf_counter() - t0
     qps = a.steps * a.batch / dt
     sample = f"full workload per step: {a.batch} queries x {a.rows} x {a.d} fp32 rows, k={a.k}"
@@ -207,8 +233,7 @@ def run_reference(a):
         "steps": a.steps, "warmup": a.warmup, "ms_per_step": dt / a.steps * 1e3, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(a, a.gpus),
-        "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port", "sample": sample,
-                         "note": "faiss-cpu/rank_bm25 wheels absent; numpy+OpenBLAS restatement of faiss IndexFlat.search"},
+        "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": cores, "kind": kind, "sample": sample, "note": note},
         "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -343,8 +368,15 @@ def run_b200(a):
         dev_ms = e0.elapsed_time(e1)
     else:
         evs = []
+        tok = torch.zeros(1, device=dev)
         for s in range(a.steps):
             l2_flush(s)
+            # every rank starts the timed step together: a one-element NCCL all-reduce ENQUEUED on the stream (no
+            # host synchronisation, so the launches of the step stay queued behind it) releases all GPUs within
+            # microseconds of each other; without it the ranks drift out of phase through the flush kernels and the
+            # fused exchange would measure that skew
+            if world > 1:
+                dist.all_reduce(tok)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             step_device(a.warmup + s)
@@ -512,12 +544,11 @@ def run_b200(a):
         blas_threads = use_all_host_threads()
         x32 = idx.reconstruct_n(0, n_local)                       # the stored (rounded) rows, as fp32
         qlast = Qh[nbatches - 1].numpy()
-        times, (Dc, Ic) = cpu_search_timed(x32, qlast, a.k, O.METRIC_IP if a.metric == "ip" else O.METRIC_L2, budget_s=12.0)
+        times, (Dc, Ic), cpu_kind, cpu_note = cpu_search_timed(x32, qlast, a.k, O.METRIC_IP if a.metric == "ip" else O.METRIC_L2, budget_s=12.0)
         cpu_qps = a.batch / float(np.median(times))
-        out["cpu_baseline"] = {"value": cpu_qps, "unit": "queries/s", "cores": blas_threads, "kind": "port",
+        out["cpu_baseline"] = {"value": cpu_qps, "unit": "queries/s", "cores": blas_threads, "kind": cpu_kind,
                                "sample": f"{len(times)} x (1 batch of {a.batch} queries over all {n_local} rows, fp32), median",
-                               "ms_per_batch": float(np.median(times)) * 1e3,
-                               "note": "faiss-cpu wheel absent: numpy/OpenBLAS restatement of faiss IndexFlat.search"}
+                               "ms_per_batch": float(np.median(times)) * 1e3, "note": cpu_note}
         # parity of the timed GPU result (last e2e step) against the CPU port: ids identical except ties within 1e-3
         try:
             qh = torch.from_numpy(qlast).to(tdt).float().numpy() if last_path == "tcgen05" else qlast
@@ -534,26 +565,288 @@ def run_b200(a):
     # time per batch should stay flat.  Not the headline (the headline keeps the 1M x 768 corpus).
     if world > 1:
         sh.check_exchange()
+    extras = set() if a.extras == "none" else set(a.extras.split(","))
+    del sh, idx, Qd
+    torch.cuda.empty_cache()
+    if "c0" in extras and world == 1:
+        try:
+            out["configs0_reference_call_shape"] = measure_configs0(local, dev)
+        except Exception as e:                                    # never lose the headline line
+            out["configs0_reference_call_shape"] = {"error": repr(e)[:300]}
     if a.capacity_rows > 0:
         try:
-            del sh, idx, Qd
-            torch.cuda.empty_cache()
-            out["capacity_scaling"] = measure_capacity(a, world, rank, local, dev, peak)
-        except Exception as e:                                    # never lose the headline line
+            out["capacity_scaling"] = measure_capacity(a, world, rank, local, dev, peak, sweep="c4" in extras)
+        except Exception as e:
             out["capacity_scaling"] = {"error": repr(e)[:300]}
+        torch.cuda.empty_cache()
+    if "c2" in extras:
+        try:
+            out["configs2_50M_x_512_k100"] = measure_configs2(a, world, rank, local, dev, peak)
+        except Exception as e:
+            out["configs2_50M_x_512_k100"] = {"error": repr(e)[:300]}
+        torch.cuda.empty_cache()
+    if "c3" in extras and world == 1:
+        try:
+            out["configs3_bm25_10M_docs"] = measure_configs3(dev, peak)
+        except Exception as e:
+            out["configs3_bm25_10M_docs"] = {"error": repr(e)[:300]}
     if rank == 0:
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
 
 
-def measure_capacity(a, world, rank, local, dev, peak):
+def _timed_search(sh, idx, q, k, iters, world):
+    """(ms per batch, scan-kernel ms per batch) of `iters` back-to-back searches, max over ranks."""
+    import torch
+    import torch.distributed as dist
+    sh.search(q, k)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    idx.set_timing(True); idx.scan_time()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        sh.search(q, k)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    scan_ms, _n = idx.scan_time()
+    idx.set_timing(False)
+    t = torch.tensor([ms, scan_ms / iters], dtype=torch.float64, device=q.device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t[0].item()), float(t[1].item())
+
+
+def measure_configs0(local, dev):
+    """BASELINE configs[0] -- the only shape the reference itself ever runs: its shipped MiniLM index (125 x 384 fp32,
+    IndexFlatL2), ONE query per call, k = 5, through `RetrievalSystem.retrieve` (src/retrieval.py:222 -> :92-115), 1 000
+    queries (seeded perturbations of cyclic rows), latency per call.  Encoder = a table lookup (the
+    transformer is out of scope): numpy output (the reference's call, pageable host buffers) and CUDA-tensor output (no
+    host hop).  The CPU path beside it is the scalar C restatement of faiss's nq < 20 direct-form search on the same
+    queries.  At 125 rows the search is pure launch latency: the GPU is EXPECTED to lose to a CPU here."""
+    import torch
+    import persian_rag_system_b200 as P
+    from oracle import oracle as O
+    path = os.path.join(ROOT, "tests", "golden", "indices", "paraphrase-multilingual-MiniLM-L12-v2_finetuned_drugs_word_chunks.index")
+    x, _ = O.read_faiss_flat(path)
+    n, d = x.shape
+    rng = np.random.default_rng(100)
+    rows = x[np.arange(1000) % n]
+    q = (rows + 0.1 * np.linalg.norm(rows, axis=1, keepdims=True) / np.sqrt(d) * rng.standard_normal((1000, d))).astype(np.float32)
+    texts = [f"q{i}" for i in range(1000)]
+    table = {t: q[i:i + 1] for i, t in enumerate(texts)}
+    qdev = torch.from_numpy(q).to(dev)
+    dtable = {t: qdev[i:i + 1] for i, t in enumerate(texts)}
+
+    class HostEnc:
+        def encode(self, s, device=None):
+            return table[s[0]]
+
+    class DevEnc:
+        def encode(self, s, device=None, convert_to_tensor=False):
+            return dtable[s[0]]
+
+    chunks = [{"id": f"word_chunk_{i}", "text": "x", "chunk_type": "word_based"} for i in range(n)]
+    res = {"workload": f"configs[0]: reference MiniLM index {n} x {d} fp32 (IndexFlatL2), nq=1, k=5, 1000 queries, latency per RetrievalSystem.retrieve call"}
+    got = {}
+    for name, enc in (("numpy_embeddings_pageable_host_path", HostEnc()), ("cuda_tensor_embeddings_no_host_hop", DevEnc())):
+        r = P.RetrievalSystem(method="dense", encoder=enc, device=f"cuda:{local}")
+        import contextlib
+        import io
+        with contextlib.redirect_stdout(io.StringIO()):
+            assert r.load_chunks(chunks, path)
+        for t in texts[:50]:
+            r.retrieve(t, 5)
+        lat, ids = [], []
+        for t in texts:
+            t0 = time.perf_counter()
+            hits = r.retrieve(t, 5)
+            lat.append(time.perf_counter() - t0)
+            ids.append([int(c["id"].rsplit("_", 1)[1]) for c, _ in hits])
+        lat = np.array(lat) * 1e6
+        got[name] = np.array(ids)
+        res[name] = {"p50_us": float(np.percentile(lat, 50)), "p99_us": float(np.percentile(lat, 99)), "mean_us": float(lat.mean()),
+                     "qps_single_caller": float(1e6 / lat.mean())}
+    # raw index call (no Python retriever around it): FlatIndex.search(numpy [1, d], 5)
+    idx = P.read_index(path, device=local)
+    lat = []
+    for i in range(1000):
+        t0 = time.perf_counter()
+        idx.search(q[i:i + 1], 5)
+        lat.append(time.perf_counter() - t0)
+    lat = np.array(lat) * 1e6
+    res["flat_index_search_numpy"] = {"p50_us": float(np.percentile(lat, 50)), "p99_us": float(np.percentile(lat, 99))}
+    # CPU beside it: faiss when importable, else the scalar C restatement (nq = 1 -> direct form), one query per call
+    faiss = O.reference_library("faiss")
+    if faiss is not None:
+        fi = faiss.IndexFlatL2(d)
+        fi.add(x)
+        cpu_call, kind = (lambda qq: fi.search(qq, 5)), "reference"
+    else:
+        cpu_call, kind = (lambda qq: O.flat_search_c(x, qq, 5, O.METRIC_L2, form=1)), "port"
+    lat, Ic = [], []
+    for i in range(1000):
+        t0 = time.perf_counter()
+        _D, I1 = cpu_call(q[i:i + 1])
+        lat.append(time.perf_counter() - t0)
+        Ic.append(I1[0])
+    lat = np.array(lat) * 1e6
+    res["cpu_baseline"] = {"p50_us": float(np.percentile(lat, 50)), "p99_us": float(np.percentile(lat, 99)), "cores": 1, "kind": kind,
+                           "sample": "the same 1000 single-query searches (search call only, no retriever around it)"}
+    Ic = np.array(Ic)
+    res["parity"] = {name: {"identical_id_lists": int((g == Ic).all(axis=1).sum()), "of": 1000} for name, g in got.items()}
+    return res
+
+
+def measure_configs2(a, world, rank, local, dev, peak):
+    """BASELINE configs[2]: distiluse shape d = 512, 50 M synthetic unit-norm chunks fp16 (51.2 GB), row-sharded over the N
+    GPUs of the run, k = 100 (the wide-k path: sampled threshold -> collecting scan -> select, fully asynchronous) with
+    the top-k merged across GPUs (fused exchange / NCCL), batches of 1, 64 and 1024 queries."""
+    import torch
+    import torch.distributed as dist
+    import persian_rag_system_b200 as P
+    from persian_rag_system_b200.sharded import ShardedFlatIndex, shard_bounds
+    d, rows_total, k = 512, 50_000_000, 100
+    lo, hi = shard_bounds(rows_total, world, rank)
+    rows = hi - lo
+    sh = ShardedFlatIndex(d, P.METRIC_INNER_PRODUCT, "fp16", device=local, exchange=a.exchange, nq_cap=1024, k_cap=128, lanes=1)
+    idx = sh.local
+    idx.reserve(rows)
+    gen = torch.Generator(device=dev).manual_seed(512 + rank)
+    slab = (512 << 20) // (d * 4)
+    done = 0
+    while done < rows:
+        c = min(slab, rows - done)
+        xb = torch.randn(c, d, generator=gen, device=dev)
+        xb /= xb.norm(dim=1, keepdim=True)
+        idx.add(xb.half())
+        done += c
+    del xb
+    sh.offset, sh.ntotal_global = lo, rows_total
+    idx.set_id_offset(lo)
+    if world > 1:
+        dist.barrier()
+    gq = torch.Generator(device=dev).manual_seed(78)
+    cases = []
+    shard_bytes = rows * d * 2
+    for B in (1, 64, 1024):
+        q = torch.randn(B, d, generator=gq, device=dev)
+        q /= q.norm(dim=1, keepdim=True)
+        ms, scan = _timed_search(sh, idx, q, k, 8 if B <= 64 else 3, world)
+        passes = (B + 127) // 128
+        cases.append({"batch": B, "ms_per_batch": ms, "qps": B / (ms * 1e-3), "collect_scan_ms": scan,
+                      "collect_scan_gbs_per_gpu": passes * shard_bytes / (scan * 1e-3) / 1e9,
+                      "frac_hbm_collect_scan": passes * shard_bytes / (scan * 1e-3) / 1e9 / peak,
+                      "whole_search_gbs_per_gpu": passes * shard_bytes / (ms * 1e-3) / 1e9})
+    D, I = sh.search(q[:4], k)
+    ok = bool((I >= 0).all().item() and (I < rows_total).all().item() and (D[:, :-1] >= D[:, 1:]).all().item())
+    res = {"workload": f"configs[2]: {rows_total} x {d} fp16 rows over {world} GPU(s) ({rows} per GPU), inner product, k={k}",
+           "cases": cases, "results_valid": ok, "exchange": a.exchange if world > 1 else "none"}
+    if world > 1:
+        sh.check_exchange()
+    # CPU beside it (rank 0, N = 1): the corpus (102 GB as fp32) exceeds what a host arm should hold, so the CPU path is
+    # timed on the first 1 M rows and extrapolated linearly in N (a flat scan is linear), as SURVEY 8d prescribes
+    if world == 1 and rank == 0 and not a.no_cpu_baseline:
+        from oracle import oracle as O
+        threads = use_all_host_threads()
+        x32 = idx.reconstruct_n(0, 1_000_000)
+        qh = q[:64].cpu().numpy()
+        search, kind, note = cpu_flat_search()
+        search(x32[:65536], qh, k, O.METRIC_IP)
+        t0 = time.perf_counter()
+        search(x32, qh, k, O.METRIC_IP)
+        dt = time.perf_counter() - t0
+        res["cpu_baseline"] = {"value": 64 / (dt * rows_total / 1_000_000), "unit": "queries/s", "cores": threads, "kind": kind,
+                               "sample": "64 queries over the first 1M rows (fp32), time scaled x50 to the 50M-row corpus", "note": note}
+    return res
+
+
+def measure_configs3(dev, peak):
+    """BASELINE configs[3]: BM25 over a synthetic Persian-vocabulary CSR matrix -- 10 M docs, 200 k terms, ~100 draws per
+    doc (Zipf 1.07; ~73 distinct terms), 4 096 queries of 1 + Poisson(6) Zipf tokens, k = 10.  Both scoring
+    kernels through prs_sparse_search_device (query CSR and results on the device), CUDA events around the call.
+    Roofline: HBM, algorithmic bytes = 8 x sum of df over the query tokens (one doc id + one fp32 weight per posting)."""
+    import torch
+    import scipy.sparse as sp
+    import persian_rag_system_b200 as P
+    from oracle import oracle as O
+    from tools.bench_aux import gen_sparse
+    docs, terms, nq, k = 10_000_000, 200_000, 4096, 10
+    t0 = time.time()
+    indptr, indices, values, cdf, _df = gen_sparse(docs, terms, 7, dev)
+    t_gen = time.time() - t0
+    t0 = time.time()
+    idx = P.SparseIndex(indptr, indices, values, terms, device=int(dev.index or 0))
+    t_build = time.time() - t0
+    rng = np.random.default_rng(11)
+    qlen = 1 + rng.poisson(6, size=nq)
+    q_indptr = np.zeros(nq + 1, np.int64)
+    q_indptr[1:] = np.cumsum(qlen)
+    u = torch.from_numpy(rng.random(int(q_indptr[-1]))).to(dev)
+    q_terms = torch.searchsorted(cdf, u).clamp_(max=terms - 1).to(torch.int32)
+    d_ip = torch.from_numpy(q_indptr).to(dev)
+    d_qw = torch.ones(q_terms.shape[0], dtype=torch.float64, device=dev)
+    res = {"workload": f"configs[3]: BM25, {docs} docs x {terms} terms, nnz {int(indices.shape[0])} (~{indices.shape[0] / docs:.0f}/doc), {nq} queries, k={k}",
+           "build": {"generate_s": t_gen, "index_build_s": t_build}, "modes": {}}
+    out = {}
+    for mode in ("exact", "throughput"):
+        t0 = time.time()
+        idx.set_mode(mode)
+        torch.cuda.synchronize()
+        t_prep = time.time() - t0
+        idx.search_device(d_ip, q_terms, d_qw, k)
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(3):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            S, I = idx.search_device(d_ip, q_terms, d_qw, k)
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        postings = idx.last_postings
+        ms = float(np.median(ts))
+        out[mode] = (S.cpu().numpy(), I.cpu().numpy())
+        res["modes"][mode] = {"ms_per_batch": ms, "qps": nq / (ms * 1e-3), "algorithmic_gbs": 8.0 * postings / (ms * 1e-3) / 1e9,
+                              "frac_hbm": 8.0 * postings / (ms * 1e-3) / 1e9 / peak, "prepare_s": t_prep}
+    res["postings_touched"] = int(postings)
+    res["modes_agree"] = {"scores_identical": bool(np.array_equal(out["exact"][0], out["throughput"][0])),
+                          "id_positions_identical": float((out["exact"][1] == out["throughput"][1]).mean())}
+    res["roofline"] = {"bound": "hbm", "achieved": res["modes"]["throughput"]["algorithmic_gbs"], "peak": peak, "unit": "GB/s",
+                       "frac": res["modes"]["throughput"]["frac_hbm"], "kernel": "sparse_score_batched_kernel (+ merge + exact re-score)",
+                       "note": "algorithmic bytes assume every query streams its own postings; the throughput kernel shares a posting between "
+                               "the queries of a CTA and the L2 between CTAs, so its DRAM traffic is far below this figure"}
+    # CPU beside it: vectorised scipy CSC column adds + canonical top-k (faster than rank_bm25's pure-Python loop), 4 queries
+    M = sp.csr_matrix((values.astype(np.float64), indices, indptr), shape=(docs, terms)).tocsc()
+    qt = q_terms.cpu().numpy()
+    t0 = time.perf_counter()
+    bad = 0
+    for qi in range(4):
+        sc = np.zeros(docs, np.float64)
+        for t in qt[q_indptr[qi]:q_indptr[qi + 1]]:
+            a0, a1 = M.indptr[t], M.indptr[t + 1]
+            sc[M.indices[a0:a1]] += M.data[a0:a1]
+        try:
+            O.check_topk_against_scores(out["throughput"][1][qi], out["throughput"][0][qi], sc, k, True, rtol=1e-5, atol=1e-9)
+        except AssertionError:
+            bad += 1
+    res["cpu_baseline"] = {"value": 4 / (time.perf_counter() - t0), "unit": "queries/s", "cores": 1, "kind": "port",
+                           "sample": "first 4 queries, scipy CSC column adds + stable top-k (rank_bm25 itself is absent; this is faster than its Python loop)"}
+    res["parity"] = {"queries_checked_against_cpu": 4, "mismatch": bad}
+    return res
+
+
+def measure_capacity(a, world, rank, local, dev, peak, sweep=False):
     import torch
     import torch.distributed as dist
     import persian_rag_system_b200 as P
     from persian_rag_system_b200.sharded import ShardedFlatIndex
     d, rows, B, k = 384, a.capacity_rows, 64, 10
-    sh = ShardedFlatIndex(d, P.METRIC_INNER_PRODUCT, "fp16", device=local, exchange=a.exchange, nq_cap=64, k_cap=16)
+    sh = ShardedFlatIndex(d, P.METRIC_INNER_PRODUCT, "fp16", device=local, exchange=a.exchange, nq_cap=1024 if sweep else 64,
+                          k_cap=128 if sweep else 16, lanes=1)
     idx = sh.local
     idx.reserve(rows)
     gen = torch.Generator(device=dev).manual_seed(99 + rank)
@@ -597,7 +890,21 @@ def measure_capacity(a, world, rank, local, dev, peak):
     shard_bytes = rows * d * 2
     # sanity: the best hit of query 0 must be a valid global id
     ok = bool((I[:, 0] >= 0).all().item() and (I[:, 0] < rows * world).all().item())
-    return {"workload": f"configs[4] share: {rows} x {d} fp16 rows per GPU, global corpus {rows * world} rows, batch {B}, k={k}",
+    sweep_rows = None
+    if sweep:
+        # BASELINE configs[4]: batch x k sweep on the same per-GPU share (B in {1,16,256,4096} x k in {1,10,100,1024})
+        sweep_rows = []
+        for Bs in (1, 16, 256, 4096):
+            qs = torch.randn(Bs, d, generator=gq, device=dev)
+            qs /= qs.norm(dim=1, keepdim=True)
+            for ks in (1, 10, 100, 1024):
+                m, sc = _timed_search(sh, idx, qs, ks, 6 if Bs <= 256 else 2, world)
+                sweep_rows.append({"batch": Bs, "k": ks, "ms_per_batch": round(m, 4), "qps": round(Bs / (m * 1e-3), 1),
+                                   "scan_ms": round(sc, 4), "tflops": round(2.0 * rows * world * d * Bs / (m * 1e-3) / 1e12, 1)})
+        if world > 1:
+            sh.check_exchange()
+    return {"batch_k_sweep": sweep_rows,
+            "workload": f"configs[4] share: {rows} x {d} fp16 rows per GPU, global corpus {rows * world} rows, batch {B}, k={k}",
             "scaling": "weak (corpus grows with N)", "ms_per_batch": ms, "qps": B / (ms * 1e-3), "scan_ms": scan,
             "scan_gbs_per_gpu": shard_bytes / (scan * 1e-3) / 1e9, "frac_hbm": shard_bytes / (scan * 1e-3) / 1e9 / peak,
             "aggregate_scan_gbs": world * shard_bytes / (scan * 1e-3) / 1e9, "ids_valid": ok}
