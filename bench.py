@@ -62,6 +62,7 @@ def parse():
                     help="secondary north-star configs measured after the headline (extra JSON keys): c0 = the reference's own call shape "
                          "(125 x 384 fp32, nq=1, k=5, latency), c2 = 50M x 512 fp16 k=100, c3 = BM25 on 10M docs x 4096 queries, "
                          "c4 = batch x k sweep on the 50M x 384 per-GPU share; 'none' skips them")
+    ap.add_argument("--no-fuse", action="store_true", help="three-kernel search (prep, scan, merge) instead of the one-launch search (A/B)")
     ap.add_argument("--no-sweep", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sweep-out", default="")
@@ -287,6 +288,8 @@ def run_b200(a):
     sh.offset, sh.ntotal_global = lo, a.rows
     idx.set_id_offset(lo)
     idx.set_path(a.path)
+    if a.no_fuse:
+        idx.set_fused(False)
     torch.cuda.synchronize()
 
     gq = torch.Generator(device=dev).manual_seed(4321)              # same queries on every rank

@@ -95,6 +95,12 @@ int prs_index_set_id_offset(prs_index* idx, int64_t id_offset);
 int prs_index_set_path(prs_index* idx, int path);
 /* which family the last search on this index used (1 or 2), and its main kernel's name */
 int prs_index_last_path(const prs_index* idx);
+/* One-launch search (default on): on the tcgen05 path with nq <= 128 and k <= 16 the query preparation, the scan
+ * and the merge (or merge + NVLink exchange) run as ONE cooperative kernel -- the epilogue threads convert their
+ * own query rows, a grid barrier replaces the kernel boundary, and the CTAs merge the queries among themselves.
+ * 0 restores the three-kernel sequence (A/B measurements).  prs_index_last_fused: 1 if the last search was one launch. */
+int prs_index_set_fused(prs_index* idx, int enable);
+int prs_index_last_fused(const prs_index* idx);
 
 /* bench instrumentation (bench.py's roofline): while enabled, every launch of the scan kernel
  * (the dominant kernel of a search) is bracketed by CUDA events on the launching stream.

@@ -37,6 +37,8 @@ SIGNATURES = {
     "prs_index_set_id_offset": (c_int, [c_void_p, c_i64]),
     "prs_index_set_path": (c_int, [c_void_p, c_int]),
     "prs_index_last_path": (c_int, [c_void_p]),
+    "prs_index_set_fused": (c_int, [c_void_p, c_int]),
+    "prs_index_last_fused": (c_int, [c_void_p]),
     "prs_index_set_timing": (c_int, [c_void_p, c_int]),
     "prs_index_scan_time": (c_int, [c_void_p, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(c_i64)]),
     "prs_index_phase_times": (c_int, [c_void_p, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]),

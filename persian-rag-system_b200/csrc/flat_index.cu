@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_parts_kernel(
         const uint32_t lo = tie_high ? (uint32_t)(part * k + (k - 1 - j)) : ~(uint32_t)(part * k + j);
         return ((u64)f2ord(s) << 32) | lo;
     };
-    const int n = block_topk_lists(fetch, nparts, k, k, buf, sortn, heads, s_n, tid);
+    const int n = block_topk_lists<MERGE_THREADS>(fetch, nparts, k, k, buf, sortn, heads, s_n, tid);
     for (int j = tid; j < k; j += MERGE_THREADS) {
         if (j < n) {
             const uint32_t lo = (uint32_t)buf[j];
@@ -168,6 +168,7 @@ struct prs_index {
     long long id_offset = 0;
     int path_force = 0, last_path = 0;
     int l2_rerank = 1;                   // 16-bit storage, L2: direct-form distances for the selected rows (see topk_merge.cuh)
+    int fuse = 1, last_fused = 0;        // one-launch search (prep + scan + merge in one cooperative kernel) when the shape allows
     std::mutex mu, host_mu;
     // Search workspaces.  Two slots used round-robin so that two searches can be IN FLIGHT on two
     // streams (the merge / exchange kernel of one overlaps the scan of the next); a slot is reused
@@ -187,40 +188,6 @@ struct prs_index {
     ScanTimer timer, timer_prep, timer_merge;
 };
 static thread_local struct prs_xchg* t_xchg = nullptr;   // set by the calling thread for the duration of a sharded search
-
-// peer-memory exchange buffer of one rank (see xchg.cuh)
-struct prs_xchg {
-    int device = 0, G = 1, rank = 0, nq_cap = 0;
-    long long cap = 0;
-    void* base = nullptr;                 // local allocation: vals | ids | flags | status
-    size_t bytes = 0;
-    void* peer_base[XCHG_MAX_RANKS] = {};
-    bool opened[XCHG_MAX_RANKS] = {};
-    uint32_t gen = 0;
-    XchgView view{};
-    int* h_status = nullptr;              // page-locked, device-mapped: the kernel's timeout report, readable without a sync
-    int* d_status = nullptr;              // device alias of h_status
-    unsigned long long timeout_ns = 2000000000ull;
-    // consecutive searches on ONE exchange context must be stream-ordered on every rank (a peer may
-    // only overwrite a slot after this rank's read of it has finished): each search waits for the
-    // previous one's merge kernel through this event, whatever streams the caller uses
-    cudaEvent_t event = nullptr;
-    bool used = false;
-};
-
-static inline size_t xchg_vals_bytes(const prs_xchg* x) { return (size_t)2 * x->G * x->cap * 4; }
-static inline size_t xchg_ids_bytes(const prs_xchg* x) { return (size_t)2 * x->G * x->cap * 8; }
-static inline size_t xchg_flags_bytes(const prs_xchg* x) { return (((size_t)2 * x->G * x->nq_cap * 4) + 255) & ~(size_t)255; }
-static void xchg_fill_view(prs_xchg* x) {
-    x->view.cap = x->cap; x->view.nq_cap = x->nq_cap; x->view.G = x->G; x->view.rank = x->rank;
-    for (int p = 0; p < x->G; ++p) {
-        unsigned char* b = (unsigned char*)x->peer_base[p];
-        x->view.ids[p] = (long long*)b;                                  // 8-byte aligned first
-        x->view.vals[p] = (float*)(b + xchg_ids_bytes(x));
-        x->view.vals2[p] = (float*)(b + xchg_ids_bytes(x) + xchg_vals_bytes(x));
-        x->view.flags[p] = (uint32_t*)(b + xchg_ids_bytes(x) + 2 * xchg_vals_bytes(x));
-    }
-}
 
 static int index_grow(prs_index* idx, long long n_total) {
     if (idx->storage != PRS_F32) n_total = (n_total + BLK_ROWS - 1) / BLK_ROWS * BLK_ROWS;   // whole T64 blocks
@@ -302,11 +269,11 @@ static inline int merge_sortn(long long total, int k) {
 static int launch_merge(prs_index* idx, int parts, long long nq, int k, int out_mode, const float* qnorm,
                         float* D, int64_t* I, cudaStream_t st) {
     const int sortn = merge_sortn((long long)parts * k, k);
-    const size_t smem = (size_t)sortn * 8 + MERGE_THREADS * 8 + 16 + (size_t)(k + 2) * 12;
+    const size_t smem = merge_smem_bytes(sortn, MERGE_THREADS, k);
     struct T { ScanTimer& t; cudaStream_t s; T(ScanTimer& t_, cudaStream_t s_) : t(t_), s(s_) { t.begin(s); } ~T() { t.end(s); } } tm(idx->timer_merge, st);
     // 16-bit storage + L2 (tcgen05 scan, expanded form): the merge recomputes the selected rows' distances in
     // the direct form from the stored rows and the 16-bit queries the prep kernel left behind
-    Rerank rr{nullptr, nullptr, idx->pitch, idx->storage == PRS_BF16 ? 1 : 0};
+    Rerank rr{nullptr, nullptr, nullptr, 0, idx->d, idx->pitch, idx->storage == PRS_BF16 ? 1 : 0};
     if (out_mode == 2 && idx->l2_rerank) { rr.x = (const unsigned char*)idx->x; rr.qlow = (const uint16_t*)idx->cur->umma.qlow.p; }
     if (t_xchg) {
         prs_xchg* x = t_xchg;
@@ -444,9 +411,20 @@ static int search_device_impl(prs_index* idx, const void* q, int qdtype, long lo
         idx->last_path = 2;
         if ((rc = idx->cur->qnorm.ensure((size_t)nq * 4))) return rc;
         int parts = 0;
+        const int out_mode = idx->metric == PRS_METRIC_L2 ? 2 : 0;
+        UmmaTail tail;
+        tail.enable = idx->fuse != 0;
+        tail.out_mode = out_mode; tail.largest = idx->metric == PRS_METRIC_IP ? 1 : 0; tail.id_offset = idx->id_offset;
+        tail.D = D; tail.I = (long long*)I; tail.device = idx->device;
+        tail.rerank_x = (out_mode == 2 && idx->l2_rerank) ? (const unsigned char*)idx->x : nullptr;
+        tail.xchg = t_xchg;
+        bool fused = false;
         if ((rc = search_umma(idx->cur->umma, idx->x, idx->xnorm, idx->n, idx->d, idx->pitch, idx->storage, idx->metric, idx->sm_count,
-                              q, qdtype, nq, k, (float*)idx->cur->qnorm.p, idx->cur->cand, idx->cur->cand_cnt, &parts, st, &idx->timer, &idx->timer_prep))) return rc;
-        return launch_merge(idx, parts, nq, k, idx->metric == PRS_METRIC_L2 ? 2 : 0, (const float*)idx->cur->qnorm.p, D, I, st);
+                              q, qdtype, nq, k, (float*)idx->cur->qnorm.p, idx->cur->cand, idx->cur->cand_cnt, &parts, st, &idx->timer, &idx->timer_prep,
+                              &tail, &fused))) return rc;
+        idx->last_fused = fused ? 1 : 0;
+        if (fused) return 0;                       // the scan kernel merged (and exchanged) the lists itself
+        return launch_merge(idx, parts, nq, k, out_mode, (const float*)idx->cur->qnorm.p, D, I, st);
     }
     const float* qf = (const float*)q;
     if (qdtype != PRS_F32) {
@@ -570,6 +548,13 @@ int prs_index_set_path(prs_index* idx, int path) {
     idx->path_force = path;
     return 0;
 }
+
+int prs_index_set_fused(prs_index* idx, int enable) {
+    if (!idx) { set_error("null index"); return PRS_EINVAL; }
+    idx->fuse = enable != 0;
+    return 0;
+}
+int prs_index_last_fused(const prs_index* idx) { return idx ? idx->last_fused : -1; }
 
 int prs_index_set_timing(prs_index* idx, int enable) {
     if (!idx) { set_error("null index"); return PRS_EINVAL; }
@@ -1074,6 +1059,9 @@ int prs_index_read_shard(const char* path, int device, prs_index** out) {
         PinnedPair pp;
         rc = pp.init();
         if (!rc) rc = index_grow(idx, idx->n + h.rows);
+        // index_grow zeroes / copies on the legacy stream (asynchronous to the host); the shard copies below run on
+        // their own non-blocking stream and must not overtake them
+        if (!rc && cudaDeviceSynchronize() != cudaSuccess) { cudaGetLastError(); set_error("read_shard: device synchronisation failed"); rc = PRS_ECUDA; }
         if (!rc && h.payload_bytes)
             rc = file_to_device(f, h.payload_offset, (unsigned char*)idx->x + (size_t)idx->n * idx->pitch * es, (size_t)h.payload_bytes, pp, path);
         if (!rc && h.norms_bytes) rc = file_to_device(f, h.norms_offset, idx->xnorm + idx->n, (size_t)h.norms_bytes, pp, path);

@@ -32,6 +32,7 @@
 #include "common.cuh"
 #include "host_common.h"
 #include "topk_merge.cuh"
+#include "xchg.cuh"
 
 // Timing experiments (profiles/r1_umma_variant_experiments.log) change what the kernel computes, so they
 // exist only in builds made with -DPRS_EXPERIMENTS; the shipped library has no such switches.
@@ -48,6 +49,7 @@ constexpr int UMMA_THREADS = 192;
 constexpr int UMMA_M = 128;            // queries per pass
 constexpr int UMMA_MAX_STAGES = 24;
 constexpr int UMMA_TMEM_COLS = 512;
+constexpr int UMMA_FUSED_ONESHOT = 160 * UMMA_MAX_K;   // candidate keys one merge of the one-launch search can meet (<= 160 CTAs x k <= 16)
 
 struct UmmaParams {
     const unsigned char* x; // corpus, T64 layout
@@ -71,6 +73,20 @@ struct UmmaParams {
     int coll_cap;           // mode 1: entries per (part, query) slice, >= 2k (a full slice is compacted to its k best)
     uint32_t* boot;         // per query block: [parts][128] ord(best score of the first tile) + 1 counter; zeroed per search
     long long boot_stride;  // words between the bootstrap arrays of consecutive query blocks
+    // ---- one-launch search (nq <= 128, k <= 16): the query preparation and the merge live in this kernel ----
+    const void* q;          // fuse_prep: ORIGINAL queries [nq, d] (qdtype), converted by the epilogue threads themselves
+    int qdtype, d, fuse_prep, fuse_merge;
+    float* qnorm;           // fuse_prep: [nq] ||q~||^2 out (written by part 0)
+    unsigned int* gbar;     // fuse_merge: [0] arrivals, [1] generation of the grid barrier (self-resetting)
+    int sortn, out_mode, largest, use_xchg;
+    long long id_offset;
+    float* D;
+    long long* I;
+    Rerank rr;
+    XchgView xv;
+    uint32_t xgen;
+    unsigned long long timeout_ns;
+    int* status;            // host-mapped report word (exchange timeout / barrier timeout), may be null
 };
 
 // ---------------- PTX wrappers (tcgen05 / TMA) ----------------
@@ -158,6 +174,169 @@ __device__ __noinline__ u64 slice_kth_largest(const u64* s, int n, int k) {
     return prefix;
 }
 
+// One-launch search, prologue: an epilogue thread converts ITS query row (fp32 / fp16 / bf16, d a multiple of 8) to
+// the storage type on the way into its TMEM lane and returns ||q~||^2 of the rounded row.  Out of line on purpose, and
+// with scalar arguments: taking the address of the kernel's parameter block (or indexing its arrays dynamically) makes
+// the compiler copy it to local memory and drop the uniform-datapath branches of the hot loops (measured: +15 % scan time).
+__device__ __noinline__ float stage_query_row(const void* q, int qdtype, int d, int is_bf16, uint32_t a_addr, int ncol, bool qvalid, size_t qoff) {
+    float qn = 0.f;
+    auto pack2 = [&](float a, float b) -> uint32_t {
+        if (is_bf16) {
+            const __nv_bfloat16 x0 = __float2bfloat16_rn(a), x1 = __float2bfloat16_rn(b);
+            const float f0 = __bfloat162float(x0), f1 = __bfloat162float(x1);
+            qn = fmaf(f0, f0, qn); qn = fmaf(f1, f1, qn);
+            return (uint32_t)__bfloat16_as_ushort(x0) | ((uint32_t)__bfloat16_as_ushort(x1) << 16);
+        }
+        const __half x0 = __float2half_rn(a), x1 = __float2half_rn(b);
+        const float f0 = __half2float(x0), f1 = __half2float(x1);
+        qn = fmaf(f0, f0, qn); qn = fmaf(f1, f1, qn);
+        return (uint32_t)__half_as_ushort(x0) | ((uint32_t)__half_as_ushort(x1) << 16);
+    };
+    const int nch = d >> 3;                           // 16-byte chunks (8 elements) that hold data
+    if (qdtype == PRS_F32) {
+        const float4* src = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(q) + qoff);
+        for (int c0 = 0; c0 < ncol; c0 += 64) {         // 64 columns = 128 elements = 32 float4 loads in flight
+            float4 t[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const int ch = (c0 >> 2) + (i >> 1);
+                t[i] = (qvalid && ch < nch) ? __ldg(src + (size_t)ch * 2 + (i & 1)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+                if (c0 + g * 32 >= ncol) break;
+                uint32_t v[32];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    v[2 * i] = pack2(t[g * 16 + i].x, t[g * 16 + i].y);
+                    v[2 * i + 1] = pack2(t[g * 16 + i].z, t[g * 16 + i].w);
+                }
+                tmem_st32(a_addr + (uint32_t)(c0 + g * 32), v);
+            }
+        }
+    } else {
+        const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(q) + qoff);
+        const int src_bf16 = qdtype == PRS_BF16;
+        for (int c0 = 0; c0 < ncol; c0 += 96) {         // 24 loads of 16 bytes in flight
+            uint4 t[24];
+#pragma unroll
+            for (int i = 0; i < 24; ++i) {
+                const int ch = (c0 >> 2) + i;
+                t[i] = (qvalid && ch < nch && c0 + 4 * i < ncol) ? __ldg(src + ch) : make_uint4(0u, 0u, 0u, 0u);
+            }
+#pragma unroll
+            for (int g = 0; g < 3; ++g) {
+                if (c0 + g * 32 >= ncol) break;
+                uint32_t v[32];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    float f[8];
+                    cvt8(t[g * 8 + i], src_bf16, f);
+                    v[4 * i] = pack2(f[0], f[1]); v[4 * i + 1] = pack2(f[2], f[3]);
+                    v[4 * i + 2] = pack2(f[4], f[5]); v[4 * i + 3] = pack2(f[6], f[7]);
+                }
+                tmem_st32(a_addr + (uint32_t)(c0 + g * 32), v);
+            }
+        }
+    }
+    return qn;
+}
+
+// The two merges of the one-launch search, out of line with scalar arguments (see stage_query_row): inlined, they
+// triple the size of the scan kernel and ptxas then stops using uniform-datapath branches in its hot loops.
+__device__ __noinline__ void fused_merge_plain(const u64* cand, int parts, int nq, int k, int sortn, int out_mode, const float* qnorm,
+                                               long long id_offset, Rerank rr, float* D, long long* I, int q, int tid, unsigned char* smem) {
+    merge_query<UMMA_THREADS, false, UMMA_FUSED_ONESHOT>(cand, parts, nq, k, sortn, out_mode, qnorm, id_offset, rr, D, I, q, tid, smem);
+}
+// everything the exchanging merge needs, staged in shared memory by the tail (few arguments, no parameter-block addresses)
+struct FusedXchgArgs {
+    XchgView xv;
+    Rerank rr;
+    const u64* cand;
+    const float* qnorm;
+    float* D;
+    long long* I;
+    int* status;
+    long long id_offset;
+    unsigned long long timeout_ns;
+    uint32_t gen;
+    int parts, nq, k, sortn, out_mode, largest;
+};
+__device__ __noinline__ void fused_merge_xchg(const FusedXchgArgs* a, int q, int tid, unsigned char* smem) {
+    merge_xchg_query<UMMA_THREADS, false, UMMA_FUSED_ONESHOT, XCHG_MAX_RANKS * UMMA_MAX_K>(a->cand, a->parts, a->nq, a->k, a->sortn, a->out_mode, a->qnorm, a->id_offset, a->largest, a->rr, a->xv,
+                                   a->gen, a->timeout_ns, a->D, a->I, a->status, q, tid, smem);
+}
+
+// One-launch search, tail: grid barrier, then the CTAs merge the queries among themselves.  XCHG = 1 is the row-sharded
+// variant (merge + NVLink exchange); it is a separate kernel instantiation because the exchange code pushes the kernel over
+// the size at which ptxas stops emitting uniform-datapath branches in the hot loops.
+template <int XCHG>
+__device__ __forceinline__ void fused_tail(const UmmaParams& p, int part, int nparts, int tid, unsigned char* base, int* s_flag) {
+    // ---------------- one-launch search: grid barrier, then the CTAs merge the queries among themselves ----------------
+    // The launch is cooperative (all CTAs co-resident).  Every CTA's lists are written (the __syncthreads above);
+    // thread 0 publishes them with a fence + arrival and waits for the generation to move.  The barrier resets
+    // itself (the last arriver zeroes the count), so nothing has to be prepared per search.  The wait is bounded.
+    if (tid == 0) {
+        const unsigned g0 = ld_relaxed_gpu(p.gbar + 1);
+        __threadfence();
+        const unsigned arrived = atomicAdd(p.gbar, 1u);
+        int ok = 1;
+        if (arrived == gridDim.x - 1) {
+            p.gbar[0] = 0u;
+            __threadfence();
+            atomicAdd(p.gbar + 1, 1u);
+        } else {
+            unsigned long long t0 = 0;
+            int spins = 0;
+            while (ld_relaxed_gpu(p.gbar + 1) == g0) {
+                __nanosleep(20);
+                if ((++spins & 4095) == 0) {
+                    const unsigned long long now = global_timer_ns();
+                    if (!t0) t0 = now;
+                    else if (now - t0 > 4000000000ull) { ok = 0; break; }
+                }
+            }
+        }
+        __threadfence();
+        *s_flag = ok;
+    }
+    __syncthreads();
+    const bool ok = *s_flag != 0;
+    // the bootstrap words this CTA used are cleared for the next search on this workspace
+    for (int i = tid; i < UMMA_M; i += UMMA_THREADS) p.boot[(size_t)part * UMMA_M + i] = 0u;
+    if (part == 0 && tid == 0) p.boot[(size_t)nparts * UMMA_M] = 0u;
+    // the exchanging merge reads its arguments (the peers' buffer pointers are indexed by rank at run time) from shared
+    // memory: they get there through constant indices -- dynamic indexing of the parameter block would send the whole
+    // block to local memory, see stage_query_row
+    FusedXchgArgs* xa = reinterpret_cast<FusedXchgArgs*>(base + 96 * 1024);
+    if (XCHG && tid == 0) {
+#pragma unroll
+        for (int r = 0; r < XCHG_MAX_RANKS; ++r) {
+            xa->xv.vals[r] = p.xv.vals[r]; xa->xv.vals2[r] = p.xv.vals2[r]; xa->xv.ids[r] = p.xv.ids[r]; xa->xv.flags[r] = p.xv.flags[r];
+        }
+        xa->xv.cap = p.xv.cap; xa->xv.nq_cap = p.xv.nq_cap; xa->xv.G = p.xv.G; xa->xv.rank = p.xv.rank;
+        xa->rr = p.rr; xa->cand = p.cand; xa->qnorm = p.qnorm; xa->D = p.D; xa->I = p.I; xa->status = p.status;
+        xa->id_offset = p.id_offset; xa->timeout_ns = p.timeout_ns; xa->gen = p.xgen;
+        xa->parts = nparts; xa->nq = p.nq_total; xa->k = p.k; xa->sortn = p.sortn; xa->out_mode = p.out_mode; xa->largest = p.largest;
+    }
+    __syncthreads();
+    for (int q = part; q < p.nq; q += nparts) {
+        if (!ok) {
+            for (int j = tid; j < p.k; j += UMMA_THREADS) {
+                p.D[(size_t)q * p.k + j] = p.largest ? -3.402823466e+38f : 3.402823466e+38f;
+                p.I[(size_t)q * p.k + j] = -1;
+            }
+            if (tid == 0 && p.status) { *(volatile int*)p.status = 2; __threadfence_system(); }
+            continue;
+        }
+        if (XCHG)
+            fused_merge_xchg(xa, q, tid, base);
+        else
+            fused_merge_plain(p.cand, nparts, p.nq_total, p.k, p.sortn, p.out_mode, p.qnorm, p.id_offset, p.rr, p.D, p.I, q, tid, base);
+        __syncthreads();
+    }
+}
+
 // CL = thread-block cluster size.  CL == 1: one CTA per SM streams its own tiles (bandwidth-bound
 // batches, nq <= 128).  CL = 2 / 4 (nq > 128): the CTAs of a cluster hold DIFFERENT 128-query blocks
 // in tensor memory and share every corpus stage -- the stage's bulk copies are dealt round-robin to
@@ -173,7 +352,7 @@ __device__ __noinline__ u64 slice_kth_largest(const u64* s, int n, int k) {
 // leaves room in tensor memory for two 128-column accumulator buffers (pitch <= 512: d = 384 went
 // from 74 % to 86 % of the HBM roofline); pitch 768 keeps NB = 1 with double buffering (a single
 // 128-column buffer serialises MMA and epilogue: 93.7 % vs 95.3 %).
-template <int CL, int NB>
+template <int CL, int NB, int XCHG = 0>
 __global__ void __launch_bounds__(UMMA_THREADS, 1) flat_scan_umma_kernel(const UmmaParams p) {
     constexpr int TILE_N = NB * BLK_ROWS;
     constexpr int UMMA_KB_STAGE_BYTES = NB * KBLOCK_BYTES;   // one k-block of a tile: NB adjacent 8 KB block pieces
@@ -197,6 +376,7 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) flat_scan_umma_kernel(const U
     uint64_t* tmem_full = empty + UMMA_MAX_STAGES;
     uint64_t* tmem_empty = tmem_full + 2;
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    int* s_flag = reinterpret_cast<int*>(tmem_ptr + 1);
 
     const int kblocks = p.pitch >> 6;
     const int kstages = kblocks / p.kbs;           // pipeline stages per tile
@@ -302,28 +482,36 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) flat_scan_umma_kernel(const U
             // stage this thread's query row into TMEM: lane m, columns [0, pitch/2).  The MMA warp waits
             // for this, so the row is fetched with 24 independent 16-byte loads in flight per round
             // (three TMEM stores per round) instead of 8; empty slots store zeros without reading.
-            const uint4* qrow = reinterpret_cast<const uint4*>(p.qlow + ((size_t)crank * UMMA_M + m) * p.pitch);
             const uint32_t a_addr = tmem_base + ((uint32_t)(qd * 32) << 16);
             const int ncol = p.pitch >> 1;                     // 32-bit TMEM columns of the A operand
-            auto stage = [&](auto NG, int c0) {                 // NG x 32 columns starting at c0
-                constexpr int G_ = decltype(NG)::value;
-                uint32_t v[G_][32];
+            if (!p.fuse_prep) {
+                const uint4* qrow = reinterpret_cast<const uint4*>(p.qlow + ((size_t)crank * UMMA_M + m) * p.pitch);
+                auto stage = [&](auto NG, int c0) {                 // NG x 32 columns starting at c0
+                    constexpr int G_ = decltype(NG)::value;
+                    uint32_t v[G_][32];
 #pragma unroll
-                for (int g = 0; g < G_; ++g) {
+                    for (int g = 0; g < G_; ++g) {
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        uint4 t4 = make_uint4(0u, 0u, 0u, 0u);
-                        if (qvalid) t4 = __ldg(&qrow[((c0 + g * 32) >> 2) + i]);
-                        v[g][4 * i] = t4.x; v[g][4 * i + 1] = t4.y; v[g][4 * i + 2] = t4.z; v[g][4 * i + 3] = t4.w;
+                        for (int i = 0; i < 8; ++i) {
+                            uint4 t4 = make_uint4(0u, 0u, 0u, 0u);
+                            if (qvalid) t4 = __ldg(&qrow[((c0 + g * 32) >> 2) + i]);
+                            v[g][4 * i] = t4.x; v[g][4 * i + 1] = t4.y; v[g][4 * i + 2] = t4.z; v[g][4 * i + 3] = t4.w;
+                        }
                     }
-                }
 #pragma unroll
-                for (int g = 0; g < G_; ++g) tmem_st32(a_addr + (uint32_t)(c0 + g * 32), v[g]);
-            };
-            int c0 = 0;
-            for (; c0 + 96 <= ncol; c0 += 96) stage(std::integral_constant<int, 3>{}, c0);
-            if (ncol - c0 == 64) stage(std::integral_constant<int, 2>{}, c0);
-            else if (ncol - c0 == 32) stage(std::integral_constant<int, 1>{}, c0);
+                    for (int g = 0; g < G_; ++g) tmem_st32(a_addr + (uint32_t)(c0 + g * 32), v[g]);
+                };
+                int c0 = 0;
+                for (; c0 + 96 <= ncol; c0 += 96) stage(std::integral_constant<int, 3>{}, c0);
+                if (ncol - c0 == 64) stage(std::integral_constant<int, 2>{}, c0);
+                else if (ncol - c0 == 32) stage(std::integral_constant<int, 1>{}, c0);
+            } else {
+                // one-launch search: this thread converts ITS query row on the way into tensor memory (out of line:
+                // the conversion code is large and must not sit between the hot loops of the three warp roles)
+                const size_t qg = (size_t)p.q0 + (size_t)crank * UMMA_M + qi;
+                const float qn = stage_query_row(p.q, p.qdtype, p.d, p.is_bf16, a_addr, ncol, qvalid, qg * (size_t)p.d);
+                if (part == 0 && qvalid && p.qnorm) p.qnorm[qg] = qn;
+            }
             tmem_st_wait();
             tc_fence_before();
             named_bar_sync(2, 160);
@@ -554,6 +742,8 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) flat_scan_umma_kernel(const U
     if (CL > 1) cluster_sync_all();          // no CTA leaves while a peer's commits can still arrive on its barriers
     tc_fence_after();
     if (warp == 0) tmem_dealloc(tmem_base, UMMA_TMEM_COLS);
+
+    if (CL == 1 && p.fuse_merge) fused_tail<XCHG>(p, part, nparts, tid, base, s_flag);
 }
 
 // One launch per search: queries (fp32 / fp16 / bf16) -> [128-padded, pitch] 16-bit rows in TMEM-slot
@@ -601,9 +791,22 @@ __global__ void __launch_bounds__(128) prep_queries_kernel(const TQ* __restrict_
 
 // ---------------- host side ----------------
 struct UmmaState {
-    DevBuf qlow, boot, tau, gmax, coll, coll_cnt;
+    DevBuf qlow, boot, tau, gmax, coll, coll_cnt, gbar;
+    bool boot_clean = false;      // the bootstrap words are all zero (left so by the one-launch search's tail)
     void invalidate() {}
-    void release() { qlow.release(); boot.release(); tau.release(); gmax.release(); coll.release(); coll_cnt.release(); }
+    void release() { qlow.release(); boot.release(); tau.release(); gmax.release(); coll.release(); coll_cnt.release(); gbar.release(); }
+};
+
+// what the one-launch search needs to know about the merge it absorbs (filled by flat_index.cu)
+struct UmmaTail {
+    bool enable = false;
+    int out_mode = 0, largest = 1;
+    long long id_offset = 0;
+    float* D = nullptr;
+    long long* I = nullptr;
+    const unsigned char* rerank_x = nullptr;      // corpus pointer when the 16-bit L2 re-rank is on
+    prs_xchg* xchg = nullptr;                      // row-sharded search: exchange context of this rank
+    int device = 0;
 };
 
 static inline bool umma_eligible(int storage, int d, int pitch, long long nq, int k) {
@@ -611,7 +814,7 @@ static inline bool umma_eligible(int storage, int d, int pitch, long long nq, in
     return (storage == PRS_F16 || storage == PRS_BF16) && pitch <= 768 && k <= UMMA_MAX_K && nq >= 1;
 }
 
-template <int CL, int NB>
+template <int CL, int NB, int XCHG = 0>
 static inline int umma_launch(const UmmaParams& p, int n_clusters, size_t smem, cudaStream_t stream) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(n_clusters * CL), 1, 1);
@@ -619,10 +822,16 @@ static inline int umma_launch(const UmmaParams& p, int n_clusters, size_t smem, 
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = CL > 1 ? 1 : 0;
-    PRS_CUDA(cudaLaunchKernelEx(&cfg, flat_scan_umma_kernel<CL, NB>, p));
+    if (CL > 1) {
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    } else {
+        attr[0].id = cudaLaunchAttributeCooperative;      // the one-launch search has a grid barrier: all CTAs co-resident
+        attr[0].val.cooperative = 1;
+    }
+    static const int x_nocoop = getenv("PRS_X_NOCOOP") ? atoi(getenv("PRS_X_NOCOOP")) : 0;      // TEMP experiment
+    cfg.attrs = attr; cfg.numAttrs = (CL > 1 || (p.fuse_merge && !x_nocoop)) ? 1 : 0;
+    PRS_CUDA(cudaLaunchKernelEx(&cfg, flat_scan_umma_kernel<CL, NB, XCHG>, p));
     return 0;
 }
 
@@ -639,6 +848,7 @@ static inline int umma_max_clusters(size_t smem, int sm_count) {
     auto it = cache.find({device, smem});
     if (it != cache.end()) return it->second;
     if (cudaFuncSetAttribute(flat_scan_umma_kernel<CL, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return 0; }
+    if (CL == 1 && cudaFuncSetAttribute(flat_scan_umma_kernel<1, NB, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return 0; }
     int n = sm_count / CL;
     if (CL > 1) {
         cudaLaunchConfig_t cfg = {};
@@ -738,9 +948,13 @@ static inline int umma_prep(UmmaState& st, const UmmaPlan& pl, const void* q, in
 static inline int umma_scan(UmmaState& st, const UmmaPlan& pl, const void* x, const float* xnorm, long long n, int pitch, int storage,
                             int metric, long long nq, int k, int tile_step, int mode, u64* cand, int* cand_cnt, const float* tau,
                             u64* coll, int* coll_cnt, int coll_cap, cudaStream_t stream, ScanTimer* timer,
-                            float* gmax = nullptr, long long gmax_stride = 0) {
+                            float* gmax = nullptr, long long gmax_stride = 0, const UmmaParams* fused = nullptr) {
     for (long long q0 = 0; q0 < nq; q0 += pl.qblock) {
         UmmaParams p;
+        if (fused) p = *fused;                                  // one-launch search: prologue / tail fields (single pass)
+        else { p.q = nullptr; p.qdtype = 0; p.d = 0; p.fuse_prep = 0; p.fuse_merge = 0; p.qnorm = nullptr; p.gbar = nullptr; p.sortn = 0;
+               p.out_mode = 0; p.largest = 1; p.use_xchg = 0; p.id_offset = 0; p.D = nullptr; p.I = nullptr; p.rr = Rerank{};
+               p.xgen = 0; p.timeout_ns = 0; p.status = nullptr; }
         p.x = (const unsigned char*)x;
         p.qlow = (const uint16_t*)st.qlow.p + (size_t)q0 * pitch;
         p.xnorm = xnorm; p.n_rows = n; p.pitch = pitch;
@@ -756,7 +970,8 @@ static inline int umma_scan(UmmaState& st, const UmmaPlan& pl, const void* x, co
         if (timer) timer->begin(stream);
         int rc;
         const int CL = pl.CL, nc = pl.n_clusters;
-        if (pl.NB == 2) rc = CL == 4 ? umma_launch<4, 2>(p, nc, pl.smem, stream) : (CL == 2 ? umma_launch<2, 2>(p, nc, pl.smem, stream) : umma_launch<1, 2>(p, nc, pl.smem, stream));
+        if (CL == 1 && p.fuse_merge && p.use_xchg) rc = pl.NB == 2 ? umma_launch<1, 2, 1>(p, nc, pl.smem, stream) : umma_launch<1, 1, 1>(p, nc, pl.smem, stream);
+        else if (pl.NB == 2) rc = CL == 4 ? umma_launch<4, 2>(p, nc, pl.smem, stream) : (CL == 2 ? umma_launch<2, 2>(p, nc, pl.smem, stream) : umma_launch<1, 2>(p, nc, pl.smem, stream));
         else rc = CL == 4 ? umma_launch<4, 1>(p, nc, pl.smem, stream) : (CL == 2 ? umma_launch<2, 1>(p, nc, pl.smem, stream) : umma_launch<1, 1>(p, nc, pl.smem, stream));
         if (rc) return rc;
         if (timer) timer->end(stream);
@@ -765,18 +980,65 @@ static inline int umma_scan(UmmaState& st, const UmmaPlan& pl, const void* x, co
     return 0;
 }
 
+static inline bool umma_local_device_ptr(const void* ptr, int device) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, ptr) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeDevice && a.device == device;
+}
+
 // k <= 16.  q: [nq, d] device, dtype qdtype.  qnorm: [nq] device out.  cand: per-part lists out.
+// With `tail` (and nq <= 128: one pass, no clusters) the whole search is ONE cooperative launch: the epilogue
+// threads convert their own query rows (when q is local device memory and d % 8 == 0; otherwise the preparation
+// kernel still runs -- it reads host-mapped or peer queries exactly once), and after a grid barrier the CTAs merge
+// the queries among themselves (merge / merge + NVLink exchange of topk_merge.cuh / xchg.cuh).  *fused tells the
+// caller that D / I are already on their way.
 static inline int search_umma(UmmaState& st, const void* x, const float* xnorm, long long n, int d, int pitch, int storage,
                               int metric, int sm_count, const void* q, int qdtype, long long nq, int k, float* qnorm,
-                              DevBuf& cand, DevBuf& cand_cnt, int* parts_out, cudaStream_t stream, ScanTimer* timer = nullptr, ScanTimer* timer_prep = nullptr) {
+                              DevBuf& cand, DevBuf& cand_cnt, int* parts_out, cudaStream_t stream, ScanTimer* timer = nullptr, ScanTimer* timer_prep = nullptr,
+                              const UmmaTail* tail = nullptr, bool* fused_out = nullptr) {
     UmmaPlan pl;
     int rc;
+    if (fused_out) *fused_out = false;
     if ((rc = umma_plan(n, pitch, nq, sm_count, pl))) return rc;
-    if ((rc = umma_prep(st, pl, q, qdtype, nq, d, pitch, storage, qnorm, stream, timer_prep))) return rc;
+    static const int x_noprep = getenv("PRS_X_NOPREP") ? atoi(getenv("PRS_X_NOPREP")) : 0;      // TEMP experiment
+    const bool fuse_merge = tail && tail->enable && pl.CL == 1 && nq <= pl.qblock;
+    const bool fuse_prep = !x_noprep && fuse_merge && d % 8 == 0 && ((uintptr_t)q & 15u) == 0 && umma_local_device_ptr(q, tail->device);
+    if (!fuse_prep) {
+        if ((rc = umma_prep(st, pl, q, qdtype, nq, d, pitch, storage, qnorm, stream, timer_prep))) return rc;
+    } else {
+        const void* before = st.boot.p;
+        if ((rc = st.boot.ensure((size_t)pl.boot_words * pl.nblocks * 4))) return rc;
+        if (st.boot.p != before) st.boot_clean = false;
+        if (!st.boot_clean) PRS_CUDA(cudaMemsetAsync(st.boot.p, 0, st.boot.bytes, stream));
+    }
     if ((rc = cand.ensure((size_t)pl.n_clusters * nq * k * 8))) return rc;
     if ((rc = cand_cnt.ensure((size_t)pl.n_clusters * nq * 4))) return rc;
+    UmmaParams fp;
+    const UmmaParams* fpp = nullptr;
+    prs_xchg* xc = fuse_merge ? tail->xchg : nullptr;
+    if (fuse_merge) {
+        if (!st.gbar.p) {
+            if ((rc = st.gbar.ensure(256))) return rc;
+            PRS_CUDA(cudaMemsetAsync(st.gbar.p, 0, 256, stream));
+        }
+        fp.q = q; fp.qdtype = qdtype; fp.d = d; fp.fuse_prep = fuse_prep ? 1 : 0; fp.fuse_merge = 1; fp.qnorm = qnorm;
+        fp.gbar = (unsigned int*)st.gbar.p;
+        fp.sortn = next_pow2((int)std::max<long long>(k + UMMA_THREADS, (long long)pl.n_clusters * k));
+        fp.out_mode = tail->out_mode; fp.largest = tail->largest; fp.id_offset = tail->id_offset; fp.D = tail->D; fp.I = tail->I;
+        fp.rr = Rerank{tail->rerank_x, fuse_prep ? nullptr : (const uint16_t*)st.qlow.p, q, qdtype, d, pitch, storage == PRS_BF16 ? 1 : 0};
+        fp.use_xchg = xc ? 1 : 0; fp.xgen = 0; fp.timeout_ns = 0; fp.status = nullptr;
+        if (xc) {
+            ++xc->gen;
+            if (xc->used) PRS_CUDA(cudaStreamWaitEvent(stream, xc->event, 0));
+            fp.xv = xc->view; fp.xgen = xc->gen; fp.timeout_ns = xc->timeout_ns; fp.status = xc->d_status;
+        }
+        fpp = &fp;
+    }
     if ((rc = umma_scan(st, pl, x, xnorm, n, pitch, storage, metric, nq, k, 1, 0, (u64*)cand.p, (int*)cand_cnt.p, nullptr, nullptr, nullptr, 0,
-                        stream, timer))) return rc;
+                        stream, timer, nullptr, 0, fpp))) return rc;
+    st.boot_clean = fuse_merge;                                  // the fused tail leaves the bootstrap words zeroed
+    if (xc) { PRS_CUDA(cudaEventRecord(xc->event, stream)); xc->used = true; }
+    if (fused_out) *fused_out = fuse_merge;
     *parts_out = pl.n_clusters;
     return 0;
 }

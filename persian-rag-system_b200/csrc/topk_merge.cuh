@@ -13,7 +13,7 @@ constexpr int MERGE_ONESHOT = 4096;     // inputs up to this many keys are sorte
 
 // CTA-level top-k over `parts` lists of L keys each (list p = keys [p*L, (p+1)*L), sorted
 // descending, 0 = empty).  buf: sortn keys of shared memory (power of two, >= k + MERGE_THREADS);
-// heads: MERGE_THREADS keys of shared memory; s_n: two ints.
+// heads: NT keys of shared memory; s_n: two ints.
 // Inputs that fit (parts*k <= sortn) are done in one memory round trip:
 //   1. every thread fetches its keys (independent loads) and the list heads go to `heads`;
 //   2. bound = k-th largest head (rank counting, no sort): k distinct candidates are >= bound, so
@@ -23,18 +23,22 @@ constexpr int MERGE_ONESHOT = 4096;     // inputs up to this many keys are sorte
 // Measured on B200 (148 lists x 10): 28 us for the full in-smem sort -> see profiles/.
 // Larger inputs stream through block_topk_stream.  On return buf[0..k) holds the result
 // (descending, 0 = empty); returns the number of valid entries.
-template <class Fetch>
+// NT = threads of the calling CTA (all of them call): 256 in the merge kernels, 192 in the fused tail of the scan kernel.
+// STREAM = false drops the streaming fall-back (callers that guarantee parts * L <= min(sortn, MERGE_ONESHOT): the fused
+// tail of the scan kernel, whose code size must stay small).
+// ONESHOT bounds parts * L of such a caller (fewer unrolled fetches).
+template <int NT, bool STREAM = true, int ONESHOT = MERGE_ONESHOT, class Fetch>
 __device__ __forceinline__ int block_topk_lists(Fetch fetch, int parts, int L, int k, u64* buf, int sortn, u64* heads, int* s_n, int tid) {
     const long long total = (long long)parts * L;
-    if (total > sortn) return block_topk_stream(fetch, total, k, buf, sortn, s_n, tid, MERGE_THREADS, 1);
-    constexpr int NREG = MERGE_ONESHOT / MERGE_THREADS;        // 16
+    if (STREAM) { if (total > sortn || total > ONESHOT) return block_topk_stream(fetch, total, k, buf, sortn, s_n, tid, NT, 1); }
+    constexpr int NREG = (ONESHOT + NT - 1) / NT;              // 16 in the merge kernels
     u64 v[NREG];
 #pragma unroll
     for (int i = 0; i < NREG; ++i) {
-        const int idx = i * MERGE_THREADS + tid;
+        const int idx = i * NT + tid;
         v[i] = idx < (int)total ? fetch((long long)idx) : 0ull;
     }
-    const int nheads = parts < MERGE_THREADS ? parts : MERGE_THREADS;
+    const int nheads = parts < NT ? parts : NT;
     const u64 myhead = tid < nheads ? fetch((long long)tid * L) : 0ull;
     heads[tid] = myhead;
     if (tid == 0) { s_n[0] = 0; s_n[1] = 0; }
@@ -55,10 +59,10 @@ __device__ __forceinline__ int block_topk_lists(Fetch fetch, int parts, int L, i
     const int cnt = s_n[0];
     int n2 = 2;
     while (n2 < cnt) n2 <<= 1;
-    for (int i = cnt + tid; i < n2; i += MERGE_THREADS) buf[i] = 0ull;
-    if (n2 < k) for (int i = n2 + tid; i < k; i += MERGE_THREADS) buf[i] = 0ull;
-    named_bar_sync(1, MERGE_THREADS);
-    block_sort_desc(buf, n2, tid, MERGE_THREADS, 1);
+    for (int i = cnt + tid; i < n2; i += NT) buf[i] = 0ull;
+    if (n2 < k) for (int i = n2 + tid; i < k; i += NT) buf[i] = 0ull;
+    named_bar_sync(1, NT);
+    block_sort_desc(buf, n2, tid, NT, 1);
     return cnt < k ? cnt : k;
 }
 
@@ -73,7 +77,9 @@ __device__ __forceinline__ int block_topk_lists(Fetch fetch, int parts, int L, i
 // ---------------------------------------------------------------------------------------------
 struct Rerank {
     const unsigned char* x;   // corpus, T64 layout (nullptr = no re-rank)
-    const uint16_t* qlow;     // [nq padded][pitch] 16-bit queries in TMEM-slot order (prep kernel)
+    const uint16_t* qlow;     // [nq padded][pitch] 16-bit queries in TMEM-slot order (prep kernel), or nullptr:
+    const void* q;            // ... then the ORIGINAL queries [nq, d] of type qdtype, rounded to the storage type on the fly
+    int qdtype, d;
     int pitch, is_bf16;
 };
 
@@ -91,20 +97,38 @@ __device__ __forceinline__ void cvt8(const uint4& v, int is_bf16, float (&f)[8])
         else { const float2 t = __half22float2(*reinterpret_cast<const __half2*>(&w[i])); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
     }
 }
+// one query element as the scan kernel sees it: rounded to the storage type, back in fp32
+__device__ __forceinline__ float round_to_storage(float v, int is_bf16) {
+    return is_bf16 ? __bfloat162float(__float2bfloat16_rn(v)) : __half2float(__float2half_rn(v));
+}
+__device__ __forceinline__ float load_query_elem(const void* q, int qdtype, size_t i) {
+    if (qdtype == PRS_F32) return reinterpret_cast<const float*>(q)[i];
+    if (qdtype == PRS_F16) return __half2float(reinterpret_cast<const __half*>(q)[i]);
+    return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(q)[i]);
+}
 
 // dd[j] = sum (q~ - x_row(j))^2 for the n keys in buf (one warp per key, 16-byte pieces per lane)
+template <int NT>
 __device__ __forceinline__ void direct_l2_of_keys(const u64* buf, int n, const Rerank& rr, int q, float* dd, int tid) {
     const int warp = tid >> 5, lane = tid & 31;
-    const uint16_t* qrow = rr.qlow + (size_t)qlow_row(q) * rr.pitch;
-    for (int j = warp; j < n; j += MERGE_THREADS / 32) {
+    const uint16_t* qrow = rr.qlow ? rr.qlow + (size_t)qlow_row(q) * rr.pitch : nullptr;
+    for (int j = warp; j < n; j += NT / 32) {
         const long long row = (long long)key_id<PRS_TIE_LOW_ID>(buf[j]);
         float acc = 0.f;
         for (int ch = lane; ch < (rr.pitch >> 3); ch += 32) {
             const uint4 xv = __ldg(reinterpret_cast<const uint4*>(rr.x + t64_offset(row, ch, rr.pitch)));
-            const uint4 qv = __ldg(reinterpret_cast<const uint4*>(qrow + ch * 8));
             float xf[8], qf[8];
             cvt8(xv, rr.is_bf16, xf);
-            cvt8(qv, rr.is_bf16, qf);
+            if (qrow) {
+                const uint4 qv = __ldg(reinterpret_cast<const uint4*>(qrow + ch * 8));
+                cvt8(qv, rr.is_bf16, qf);
+            } else {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const int c = ch * 8 + e;
+                    qf[e] = c < rr.d ? round_to_storage(load_query_elem(rr.q, rr.qdtype, (size_t)q * rr.d + c), rr.is_bf16) : 0.f;
+                }
+            }
 #pragma unroll
             for (int e = 0; e < 8; ++e) { const float t = qf[e] - xf[e]; acc = fmaf(t, t, acc); }
         }
@@ -114,28 +138,30 @@ __device__ __forceinline__ void direct_l2_of_keys(const u64* buf, int n, const R
     }
 }
 
-__global__ void __launch_bounds__(MERGE_THREADS) merge_cand_kernel(
-    const u64* __restrict__ cand, int parts, int nq, int k, int sortn,
-    int out_mode, const float* __restrict__ qnorm, long long id_offset, const Rerank rr, float* __restrict__ D,
-    long long* __restrict__ I) {
-    extern __shared__ __align__(16) unsigned char msm[];
+// shared memory one merge needs (buf | heads | s_n | dd | ids)
+__host__ __device__ inline size_t merge_smem_bytes(int sortn, int nt, int k) { return (size_t)sortn * 8 + (size_t)nt * 8 + 16 + (size_t)(k + 2) * 12; }
+
+// Merge of ONE query (all NT threads of the CTA call it): per-part candidate lists -> D / I rows of query q.
+template <int NT, bool STREAM = true, int ONESHOT = MERGE_ONESHOT>
+__device__ __forceinline__ void merge_query(const u64* __restrict__ cand, int parts, int nq, int k, int sortn, int out_mode,
+                                            const float* __restrict__ qnorm, long long id_offset, const Rerank& rr,
+                                            float* __restrict__ D, long long* __restrict__ I, int q, int tid, unsigned char* msm) {
     u64* buf = reinterpret_cast<u64*>(msm);
     u64* heads = buf + sortn;
-    int* s_n = reinterpret_cast<int*>(heads + MERGE_THREADS);
+    int* s_n = reinterpret_cast<int*>(heads + NT);
     float* dd = reinterpret_cast<float*>(s_n + 4);               // [k] direct-form distances (re-rank only)
-    const int q = blockIdx.x, tid = threadIdx.x;
     // every (part, query) list has all k slots written, empty ones as key 0 (scan kernels' contract)
     auto fetch = [&](long long i) -> u64 {
         const int part = (int)((unsigned)i / (unsigned)k), j = (int)i - part * k;
         return __ldcg(cand + ((size_t)part * nq + q) * k + j);
     };
-    const int n = block_topk_lists(fetch, parts, k, k, buf, sortn, heads, s_n, tid);
+    const int n = block_topk_lists<NT, STREAM, ONESHOT>(fetch, parts, k, k, buf, sortn, heads, s_n, tid);
     if (out_mode == 2 && rr.x) {
         __syncthreads();
-        direct_l2_of_keys(buf, n, rr, q, dd, tid);
+        direct_l2_of_keys<NT>(buf, n, rr, q, dd, tid);
         __syncthreads();
         // order by (distance asc, id asc): rank counting (n <= 1024; ids are unique)
-        for (int j = tid; j < k; j += MERGE_THREADS) {
+        for (int j = tid; j < k; j += NT) {
             if (j < n) {
                 const float dj = dd[j];
                 const uint32_t idj = key_id<PRS_TIE_LOW_ID>(buf[j]);
@@ -153,7 +179,7 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_cand_kernel(
         }
         return;
     }
-    for (int j = tid; j < k; j += MERGE_THREADS) {
+    for (int j = tid; j < k; j += NT) {
         float dv;
         long long iv;
         if (j < n) {
@@ -168,6 +194,14 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_cand_kernel(
         D[(size_t)q * k + j] = dv;
         I[(size_t)q * k + j] = iv;
     }
+}
+
+__global__ void __launch_bounds__(MERGE_THREADS) merge_cand_kernel(
+    const u64* __restrict__ cand, int parts, int nq, int k, int sortn,
+    int out_mode, const float* __restrict__ qnorm, long long id_offset, const Rerank rr, float* __restrict__ D,
+    long long* __restrict__ I) {
+    extern __shared__ __align__(16) unsigned char msm[];
+    merge_query<MERGE_THREADS>(cand, parts, nq, k, sortn, out_mode, qnorm, id_offset, rr, D, I, (int)blockIdx.x, (int)threadIdx.x, msm);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -42,6 +42,11 @@ __device__ __forceinline__ uint32_t ld_relaxed_sys(const uint32_t* p) {
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+__device__ __forceinline__ unsigned ld_relaxed_gpu(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
 __device__ __forceinline__ unsigned long long global_timer_ns() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -54,18 +59,18 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
 // carries its direct-form distance (vals2), which becomes the output value and the final order.
 // status: host-mapped word; set to 1 when a peer's lists did not arrive within timeout_ns -- the
 // query's output is then the empty-result sentinel (ids -1), never a merge of stale lists.
-__global__ void __launch_bounds__(MERGE_THREADS) merge_xchg_kernel(
+// One query (all NT threads of the CTA call it).
+template <int NT, bool STREAM = true, int ONESHOT = MERGE_ONESHOT, int ONESHOT2 = MERGE_ONESHOT>
+__device__ __forceinline__ void merge_xchg_query(
     const u64* __restrict__ cand, int parts, int nq, int k, int sortn,
-    int out_mode, const float* __restrict__ qnorm, long long id_offset, int largest, const Rerank rr,
-    const XchgView xv, uint32_t gen, unsigned long long timeout_ns, float* __restrict__ D, long long* __restrict__ I,
-    volatile int* status) {
-    extern __shared__ __align__(16) unsigned char msm[];
+    int out_mode, const float* __restrict__ qnorm, long long id_offset, int largest, const Rerank& rr,
+    const XchgView& xv, uint32_t gen, unsigned long long timeout_ns, float* __restrict__ D, long long* __restrict__ I,
+    volatile int* status, int q, int tid, unsigned char* msm) {
     u64* buf = reinterpret_cast<u64*>(msm);
     u64* heads = buf + sortn;
-    int* s_n = reinterpret_cast<int*>(heads + MERGE_THREADS);      // [0..1] block_topk_lists, [2] timeout flag
+    int* s_n = reinterpret_cast<int*>(heads + NT);                 // [0..1] block_topk_lists, [2] timeout flag
     float* dd = reinterpret_cast<float*>(s_n + 4);                 // [k]
     long long* ids_s = reinterpret_cast<long long*>(dd + ((k + 1) & ~1));   // [k]
-    const int q = blockIdx.x, tid = threadIdx.x;
     const int G = xv.G, slot = (int)(gen & 1u);
     const bool rerank = out_mode == 2 && rr.x != nullptr;
 
@@ -74,19 +79,19 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_xchg_kernel(
         const int part = (int)((unsigned)i / (unsigned)k), j = (int)i - part * k;
         return __ldcg(cand + ((size_t)part * nq + q) * k + j);
     };
-    const int n = block_topk_lists(fetch, parts, k, k, buf, sortn, heads, s_n, tid);
+    const int n = block_topk_lists<NT, STREAM, ONESHOT>(fetch, parts, k, k, buf, sortn, heads, s_n, tid);
     if (tid == 0) s_n[2] = 0;
     if (rerank) {
         __syncthreads();
-        direct_l2_of_keys(buf, n, rr, q, dd, tid);
+        direct_l2_of_keys<NT>(buf, n, rr, q, dd, tid);
     }
     __syncthreads();
     // keep the local list in registers: buf is reused by the second merge
-    u64 mine[(PRS_MAX_K + MERGE_THREADS - 1) / MERGE_THREADS];
-    float mine_dd[(PRS_MAX_K + MERGE_THREADS - 1) / MERGE_THREADS];
+    u64 mine[(PRS_MAX_K + NT - 1) / NT];
+    float mine_dd[(PRS_MAX_K + NT - 1) / NT];
 #pragma unroll
-    for (int r = 0; r < (PRS_MAX_K + MERGE_THREADS - 1) / MERGE_THREADS; ++r) {
-        const int j = tid + r * MERGE_THREADS;
+    for (int r = 0; r < (PRS_MAX_K + NT - 1) / NT; ++r) {
+        const int j = tid + r * NT;
         mine[r] = (j < n) ? buf[j] : 0ull;
         mine_dd[r] = (rerank && j < n) ? dd[j] : 0.f;
     }
@@ -94,8 +99,8 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_xchg_kernel(
     // ---- 2. push the local list into every rank's buffer (slot, my rank, query q) ----
     const size_t ebase = ((size_t)slot * G + xv.rank) * (size_t)xv.cap + (size_t)q * k;
 #pragma unroll
-    for (int r = 0; r < (PRS_MAX_K + MERGE_THREADS - 1) / MERGE_THREADS; ++r) {
-        const int j = tid + r * MERGE_THREADS;
+    for (int r = 0; r < (PRS_MAX_K + NT - 1) / NT; ++r) {
+        const int j = tid + r * NT;
         if (j >= k) break;
         float dv;
         long long iv;
@@ -136,7 +141,7 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_xchg_kernel(
     __syncthreads();
     if (s_n[2]) {
         // never merge stale or partial lists: this query answers "nothing found" and the host is told
-        for (int j = tid; j < k; j += MERGE_THREADS) {
+        for (int j = tid; j < k; j += NT) {
             D[(size_t)q * k + j] = largest ? -3.402823466e+38f : 3.402823466e+38f;
             I[(size_t)q * k + j] = -1;
         }
@@ -156,11 +161,11 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_xchg_kernel(
         const float s = sanitize(largest ? v : -v);
         return ((u64)f2ord(s) << 32) | (u64)(~(uint32_t)(part * k + j));
     };
-    const int n2 = block_topk_lists(fetch2, G, k, k, buf, sortn, heads, s_n, tid);
+    const int n2 = block_topk_lists<NT, STREAM, ONESHOT2>(fetch2, G, k, k, buf, sortn, heads, s_n, tid);
     if (rerank) {
         // selected by the expanded form; output the direct-form distances ordered by (distance, global id)
         __syncthreads();
-        for (int j = tid; j < n2; j += MERGE_THREADS) {
+        for (int j = tid; j < n2; j += NT) {
             const uint32_t pos = ~(uint32_t)buf[j];
             const int part = (int)(pos / k), jj = (int)(pos - (uint32_t)part * k);
             const size_t o = (size_t)part * (size_t)xv.cap + (size_t)q * k + jj;
@@ -168,7 +173,7 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_xchg_kernel(
             ids_s[j] = __ldcg(Ip + o);
         }
         __syncthreads();
-        for (int j = tid; j < k; j += MERGE_THREADS) {
+        for (int j = tid; j < k; j += NT) {
             if (j < n2) {
                 const float dj = dd[j];
                 const long long idj = ids_s[j];
@@ -183,7 +188,7 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_xchg_kernel(
         }
         return;
     }
-    for (int j = tid; j < k; j += MERGE_THREADS) {
+    for (int j = tid; j < k; j += NT) {
         if (j < n2) {
             const uint32_t pos = ~(uint32_t)buf[j];
             const int part = (int)(pos / k), jj = (int)(pos - (uint32_t)part * k);
@@ -197,4 +202,51 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_xchg_kernel(
     }
 }
 
+__global__ void __launch_bounds__(MERGE_THREADS) merge_xchg_kernel(
+    const u64* __restrict__ cand, int parts, int nq, int k, int sortn,
+    int out_mode, const float* __restrict__ qnorm, long long id_offset, int largest, const Rerank rr,
+    const XchgView xv, uint32_t gen, unsigned long long timeout_ns, float* __restrict__ D, long long* __restrict__ I,
+    volatile int* status) {
+    extern __shared__ __align__(16) unsigned char msm[];
+    merge_xchg_query<MERGE_THREADS>(cand, parts, nq, k, sortn, out_mode, qnorm, id_offset, largest, rr, xv, gen, timeout_ns, D, I, status,
+                                    (int)blockIdx.x, (int)threadIdx.x, msm);
+}
+
 }  // namespace prs
+
+// ---- host side of one rank's exchange buffer (used by flat_index.cu and by the one-launch search in flat_umma.cuh) ----
+// peer-memory exchange buffer of one rank (see xchg.cuh)
+struct prs_xchg {
+    int device = 0, G = 1, rank = 0, nq_cap = 0;
+    long long cap = 0;
+    void* base = nullptr;                 // local allocation: vals | ids | flags | status
+    size_t bytes = 0;
+    void* peer_base[prs::XCHG_MAX_RANKS] = {};
+    bool opened[prs::XCHG_MAX_RANKS] = {};
+    uint32_t gen = 0;
+    prs::XchgView view{};
+    int* h_status = nullptr;              // page-locked, device-mapped: the kernel's timeout report, readable without a sync
+    int* d_status = nullptr;              // device alias of h_status
+    unsigned long long timeout_ns = 2000000000ull;
+    // consecutive searches on ONE exchange context must be stream-ordered on every rank (a peer may
+    // only overwrite a slot after this rank's read of it has finished): each search waits for the
+    // previous one's merge kernel through this event, whatever streams the caller uses
+    cudaEvent_t event = nullptr;
+    bool used = false;
+};
+
+static inline size_t xchg_vals_bytes(const prs_xchg* x) { return (size_t)2 * x->G * x->cap * 4; }
+static inline size_t xchg_ids_bytes(const prs_xchg* x) { return (size_t)2 * x->G * x->cap * 8; }
+static inline size_t xchg_flags_bytes(const prs_xchg* x) { return (((size_t)2 * x->G * x->nq_cap * 4) + 255) & ~(size_t)255; }
+static inline void xchg_fill_view(prs_xchg* x) {
+    x->view.cap = x->cap; x->view.nq_cap = x->nq_cap; x->view.G = x->G; x->view.rank = x->rank;
+    for (int p = 0; p < x->G; ++p) {
+        unsigned char* b = (unsigned char*)x->peer_base[p];
+        x->view.ids[p] = (long long*)b;                                  // 8-byte aligned first
+        x->view.vals[p] = (float*)(b + xchg_ids_bytes(x));
+        x->view.vals2[p] = (float*)(b + xchg_ids_bytes(x) + xchg_vals_bytes(x));
+        x->view.flags[p] = (uint32_t*)(b + xchg_ids_bytes(x) + 2 * xchg_vals_bytes(x));
+    }
+}
+
+

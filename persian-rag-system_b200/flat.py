@@ -123,6 +123,15 @@ class FlatIndex:
         code = {"auto": 0, "cuda-core": 1, "tcgen05": 2, 0: 0, 1: 1, 2: 2}[path]
         check(self._L.prs_index_set_path(self._h, code))
 
+    def set_fused(self, enable: bool) -> None:
+        """One-launch search (prep + scan + merge in one cooperative kernel, default on) vs the three-kernel sequence."""
+        self._single_only("set_fused")
+        check(self._L.prs_index_set_fused(self._h, 1 if enable else 0))
+
+    @property
+    def last_fused(self) -> bool:
+        return (not self._g) and int(self._L.prs_index_last_fused(self._h)) == 1
+
     def set_timing(self, enable: bool) -> None:
         """Bracket every scan-kernel launch with CUDA events on its stream (bench instrumentation)."""
         self._single_only("set_timing")
