@@ -96,9 +96,11 @@ int prs_index_set_path(prs_index* idx, int path);
 /* which family the last search on this index used (1 or 2), and its main kernel's name */
 int prs_index_last_path(const prs_index* idx);
 /* One-launch search (default on): on the tcgen05 path with nq <= 128 and k <= 16 the query preparation, the scan
- * and the merge (or merge + NVLink exchange) run as ONE cooperative kernel -- the epilogue threads convert their
- * own query rows, a grid barrier replaces the kernel boundary, and the CTAs merge the queries among themselves.
- * 0 restores the three-kernel sequence (A/B measurements).  prs_index_last_fused: 1 if the last search was one launch. */
+ * and the merge run as ONE cooperative kernel -- the epilogue threads convert their own query rows, a grid barrier
+ * replaces the kernel boundaries, and the CTAs merge the queries among themselves.  (Host-mapped or peer-resident
+ * queries keep the preparation kernel, which reads them exactly once; row-sharded searches keep the separate
+ * merge + exchange kernel.)  0 restores the three-kernel sequence (A/B measurements).
+ * prs_index_last_fused: 1 if the last search was one launch. */
 int prs_index_set_fused(prs_index* idx, int enable);
 int prs_index_last_fused(const prs_index* idx);
 

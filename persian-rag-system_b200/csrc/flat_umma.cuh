@@ -78,15 +78,12 @@ struct UmmaParams {
     int qdtype, d, fuse_prep, fuse_merge;
     float* qnorm;           // fuse_prep: [nq] ||q~||^2 out (written by part 0)
     unsigned int* gbar;     // fuse_merge: [0] arrivals, [1] generation of the grid barrier (self-resetting)
-    int sortn, out_mode, largest, use_xchg;
+    int sortn, out_mode, largest;
     long long id_offset;
     float* D;
     long long* I;
     Rerank rr;
-    XchgView xv;
-    uint32_t xgen;
-    unsigned long long timeout_ns;
-    int* status;            // host-mapped report word (exchange timeout / barrier timeout), may be null
+    int* status;            // host-mapped report word (grid-barrier timeout), may be null
 };
 
 // ---------------- PTX wrappers (tcgen05 / TMA) ----------------
@@ -248,29 +245,9 @@ __device__ __noinline__ void fused_merge_plain(const u64* cand, int parts, int n
                                                long long id_offset, Rerank rr, float* D, long long* I, int q, int tid, unsigned char* smem) {
     merge_query<UMMA_THREADS, false, UMMA_FUSED_ONESHOT>(cand, parts, nq, k, sortn, out_mode, qnorm, id_offset, rr, D, I, q, tid, smem);
 }
-// everything the exchanging merge needs, staged in shared memory by the tail (few arguments, no parameter-block addresses)
-struct FusedXchgArgs {
-    XchgView xv;
-    Rerank rr;
-    const u64* cand;
-    const float* qnorm;
-    float* D;
-    long long* I;
-    int* status;
-    long long id_offset;
-    unsigned long long timeout_ns;
-    uint32_t gen;
-    int parts, nq, k, sortn, out_mode, largest;
-};
-__device__ __noinline__ void fused_merge_xchg(const FusedXchgArgs* a, int q, int tid, unsigned char* smem) {
-    merge_xchg_query<UMMA_THREADS, false, UMMA_FUSED_ONESHOT, XCHG_MAX_RANKS * UMMA_MAX_K>(a->cand, a->parts, a->nq, a->k, a->sortn, a->out_mode, a->qnorm, a->id_offset, a->largest, a->rr, a->xv,
-                                   a->gen, a->timeout_ns, a->D, a->I, a->status, q, tid, smem);
-}
-
-// One-launch search, tail: grid barrier, then the CTAs merge the queries among themselves.  XCHG = 1 is the row-sharded
-// variant (merge + NVLink exchange); it is a separate kernel instantiation because the exchange code pushes the kernel over
-// the size at which ptxas stops emitting uniform-datapath branches in the hot loops.
-template <int XCHG>
+// One-launch search, tail: grid barrier, then the CTAs merge the queries among themselves.  (Row-sharded searches keep
+// the separate merge + NVLink exchange kernel: with the exchange code reachable from this kernel ptxas stops emitting
+// uniform-datapath branches in the hot loops -- the scan got 15 % slower, more than the saved launches are worth.)
 __device__ __forceinline__ void fused_tail(const UmmaParams& p, int part, int nparts, int tid, unsigned char* base, int* s_flag) {
     // ---------------- one-launch search: grid barrier, then the CTAs merge the queries among themselves ----------------
     // The launch is cooperative (all CTAs co-resident).  Every CTA's lists are written (the __syncthreads above);
@@ -305,21 +282,6 @@ __device__ __forceinline__ void fused_tail(const UmmaParams& p, int part, int np
     // the bootstrap words this CTA used are cleared for the next search on this workspace
     for (int i = tid; i < UMMA_M; i += UMMA_THREADS) p.boot[(size_t)part * UMMA_M + i] = 0u;
     if (part == 0 && tid == 0) p.boot[(size_t)nparts * UMMA_M] = 0u;
-    // the exchanging merge reads its arguments (the peers' buffer pointers are indexed by rank at run time) from shared
-    // memory: they get there through constant indices -- dynamic indexing of the parameter block would send the whole
-    // block to local memory, see stage_query_row
-    FusedXchgArgs* xa = reinterpret_cast<FusedXchgArgs*>(base + 96 * 1024);
-    if (XCHG && tid == 0) {
-#pragma unroll
-        for (int r = 0; r < XCHG_MAX_RANKS; ++r) {
-            xa->xv.vals[r] = p.xv.vals[r]; xa->xv.vals2[r] = p.xv.vals2[r]; xa->xv.ids[r] = p.xv.ids[r]; xa->xv.flags[r] = p.xv.flags[r];
-        }
-        xa->xv.cap = p.xv.cap; xa->xv.nq_cap = p.xv.nq_cap; xa->xv.G = p.xv.G; xa->xv.rank = p.xv.rank;
-        xa->rr = p.rr; xa->cand = p.cand; xa->qnorm = p.qnorm; xa->D = p.D; xa->I = p.I; xa->status = p.status;
-        xa->id_offset = p.id_offset; xa->timeout_ns = p.timeout_ns; xa->gen = p.xgen;
-        xa->parts = nparts; xa->nq = p.nq_total; xa->k = p.k; xa->sortn = p.sortn; xa->out_mode = p.out_mode; xa->largest = p.largest;
-    }
-    __syncthreads();
     for (int q = part; q < p.nq; q += nparts) {
         if (!ok) {
             for (int j = tid; j < p.k; j += UMMA_THREADS) {
@@ -329,10 +291,7 @@ __device__ __forceinline__ void fused_tail(const UmmaParams& p, int part, int np
             if (tid == 0 && p.status) { *(volatile int*)p.status = 2; __threadfence_system(); }
             continue;
         }
-        if (XCHG)
-            fused_merge_xchg(xa, q, tid, base);
-        else
-            fused_merge_plain(p.cand, nparts, p.nq_total, p.k, p.sortn, p.out_mode, p.qnorm, p.id_offset, p.rr, p.D, p.I, q, tid, base);
+        fused_merge_plain(p.cand, nparts, p.nq_total, p.k, p.sortn, p.out_mode, p.qnorm, p.id_offset, p.rr, p.D, p.I, q, tid, base);
         __syncthreads();
     }
 }
@@ -352,7 +311,7 @@ __device__ __forceinline__ void fused_tail(const UmmaParams& p, int part, int np
 // leaves room in tensor memory for two 128-column accumulator buffers (pitch <= 512: d = 384 went
 // from 74 % to 86 % of the HBM roofline); pitch 768 keeps NB = 1 with double buffering (a single
 // 128-column buffer serialises MMA and epilogue: 93.7 % vs 95.3 %).
-template <int CL, int NB, int XCHG = 0>
+template <int CL, int NB>
 __global__ void __launch_bounds__(UMMA_THREADS, 1) flat_scan_umma_kernel(const UmmaParams p) {
     constexpr int TILE_N = NB * BLK_ROWS;
     constexpr int UMMA_KB_STAGE_BYTES = NB * KBLOCK_BYTES;   // one k-block of a tile: NB adjacent 8 KB block pieces
@@ -743,7 +702,7 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) flat_scan_umma_kernel(const U
     tc_fence_after();
     if (warp == 0) tmem_dealloc(tmem_base, UMMA_TMEM_COLS);
 
-    if (CL == 1 && p.fuse_merge) fused_tail<XCHG>(p, part, nparts, tid, base, s_flag);
+    if (CL == 1 && p.fuse_merge) fused_tail(p, part, nparts, tid, base, s_flag);
 }
 
 // One launch per search: queries (fp32 / fp16 / bf16) -> [128-padded, pitch] 16-bit rows in TMEM-slot
@@ -805,7 +764,7 @@ struct UmmaTail {
     float* D = nullptr;
     long long* I = nullptr;
     const unsigned char* rerank_x = nullptr;      // corpus pointer when the 16-bit L2 re-rank is on
-    prs_xchg* xchg = nullptr;                      // row-sharded search: exchange context of this rank
+    prs_xchg* xchg = nullptr;                      // row-sharded search: keeps the separate merge + exchange kernel
     int device = 0;
 };
 
@@ -814,7 +773,7 @@ static inline bool umma_eligible(int storage, int d, int pitch, long long nq, in
     return (storage == PRS_F16 || storage == PRS_BF16) && pitch <= 768 && k <= UMMA_MAX_K && nq >= 1;
 }
 
-template <int CL, int NB, int XCHG = 0>
+template <int CL, int NB>
 static inline int umma_launch(const UmmaParams& p, int n_clusters, size_t smem, cudaStream_t stream) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(n_clusters * CL), 1, 1);
@@ -829,9 +788,8 @@ static inline int umma_launch(const UmmaParams& p, int n_clusters, size_t smem, 
         attr[0].id = cudaLaunchAttributeCooperative;      // the one-launch search has a grid barrier: all CTAs co-resident
         attr[0].val.cooperative = 1;
     }
-    static const int x_nocoop = getenv("PRS_X_NOCOOP") ? atoi(getenv("PRS_X_NOCOOP")) : 0;      // TEMP experiment
-    cfg.attrs = attr; cfg.numAttrs = (CL > 1 || (p.fuse_merge && !x_nocoop)) ? 1 : 0;
-    PRS_CUDA(cudaLaunchKernelEx(&cfg, flat_scan_umma_kernel<CL, NB, XCHG>, p));
+    cfg.attrs = attr; cfg.numAttrs = (CL > 1 || p.fuse_merge) ? 1 : 0;
+    PRS_CUDA(cudaLaunchKernelEx(&cfg, flat_scan_umma_kernel<CL, NB>, p));
     return 0;
 }
 
@@ -848,7 +806,6 @@ static inline int umma_max_clusters(size_t smem, int sm_count) {
     auto it = cache.find({device, smem});
     if (it != cache.end()) return it->second;
     if (cudaFuncSetAttribute(flat_scan_umma_kernel<CL, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return 0; }
-    if (CL == 1 && cudaFuncSetAttribute(flat_scan_umma_kernel<1, NB, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return 0; }
     int n = sm_count / CL;
     if (CL > 1) {
         cudaLaunchConfig_t cfg = {};
@@ -953,8 +910,7 @@ static inline int umma_scan(UmmaState& st, const UmmaPlan& pl, const void* x, co
         UmmaParams p;
         if (fused) p = *fused;                                  // one-launch search: prologue / tail fields (single pass)
         else { p.q = nullptr; p.qdtype = 0; p.d = 0; p.fuse_prep = 0; p.fuse_merge = 0; p.qnorm = nullptr; p.gbar = nullptr; p.sortn = 0;
-               p.out_mode = 0; p.largest = 1; p.use_xchg = 0; p.id_offset = 0; p.D = nullptr; p.I = nullptr; p.rr = Rerank{};
-               p.xgen = 0; p.timeout_ns = 0; p.status = nullptr; }
+               p.out_mode = 0; p.largest = 1; p.id_offset = 0; p.D = nullptr; p.I = nullptr; p.rr = Rerank{}; p.status = nullptr; }
         p.x = (const unsigned char*)x;
         p.qlow = (const uint16_t*)st.qlow.p + (size_t)q0 * pitch;
         p.xnorm = xnorm; p.n_rows = n; p.pitch = pitch;
@@ -970,8 +926,7 @@ static inline int umma_scan(UmmaState& st, const UmmaPlan& pl, const void* x, co
         if (timer) timer->begin(stream);
         int rc;
         const int CL = pl.CL, nc = pl.n_clusters;
-        if (CL == 1 && p.fuse_merge && p.use_xchg) rc = pl.NB == 2 ? umma_launch<1, 2, 1>(p, nc, pl.smem, stream) : umma_launch<1, 1, 1>(p, nc, pl.smem, stream);
-        else if (pl.NB == 2) rc = CL == 4 ? umma_launch<4, 2>(p, nc, pl.smem, stream) : (CL == 2 ? umma_launch<2, 2>(p, nc, pl.smem, stream) : umma_launch<1, 2>(p, nc, pl.smem, stream));
+        if (pl.NB == 2) rc = CL == 4 ? umma_launch<4, 2>(p, nc, pl.smem, stream) : (CL == 2 ? umma_launch<2, 2>(p, nc, pl.smem, stream) : umma_launch<1, 2>(p, nc, pl.smem, stream));
         else rc = CL == 4 ? umma_launch<4, 1>(p, nc, pl.smem, stream) : (CL == 2 ? umma_launch<2, 1>(p, nc, pl.smem, stream) : umma_launch<1, 1>(p, nc, pl.smem, stream));
         if (rc) return rc;
         if (timer) timer->end(stream);
@@ -990,8 +945,7 @@ static inline bool umma_local_device_ptr(const void* ptr, int device) {
 // With `tail` (and nq <= 128: one pass, no clusters) the whole search is ONE cooperative launch: the epilogue
 // threads convert their own query rows (when q is local device memory and d % 8 == 0; otherwise the preparation
 // kernel still runs -- it reads host-mapped or peer queries exactly once), and after a grid barrier the CTAs merge
-// the queries among themselves (merge / merge + NVLink exchange of topk_merge.cuh / xchg.cuh).  *fused tells the
-// caller that D / I are already on their way.
+// the queries among themselves (merge_query of topk_merge.cuh).  *fused tells the caller that D / I are already on their way.
 static inline int search_umma(UmmaState& st, const void* x, const float* xnorm, long long n, int d, int pitch, int storage,
                               int metric, int sm_count, const void* q, int qdtype, long long nq, int k, float* qnorm,
                               DevBuf& cand, DevBuf& cand_cnt, int* parts_out, cudaStream_t stream, ScanTimer* timer = nullptr, ScanTimer* timer_prep = nullptr,
@@ -1000,9 +954,8 @@ static inline int search_umma(UmmaState& st, const void* x, const float* xnorm, 
     int rc;
     if (fused_out) *fused_out = false;
     if ((rc = umma_plan(n, pitch, nq, sm_count, pl))) return rc;
-    static const int x_noprep = getenv("PRS_X_NOPREP") ? atoi(getenv("PRS_X_NOPREP")) : 0;      // TEMP experiment
-    const bool fuse_merge = tail && tail->enable && pl.CL == 1 && nq <= pl.qblock;
-    const bool fuse_prep = !x_noprep && fuse_merge && d % 8 == 0 && ((uintptr_t)q & 15u) == 0 && umma_local_device_ptr(q, tail->device);
+    const bool fuse_merge = tail && tail->enable && !tail->xchg && pl.CL == 1 && nq <= pl.qblock;
+    const bool fuse_prep = fuse_merge && d % 8 == 0 && ((uintptr_t)q & 15u) == 0 && umma_local_device_ptr(q, tail->device);
     if (!fuse_prep) {
         if ((rc = umma_prep(st, pl, q, qdtype, nq, d, pitch, storage, qnorm, stream, timer_prep))) return rc;
     } else {
@@ -1015,7 +968,6 @@ static inline int search_umma(UmmaState& st, const void* x, const float* xnorm, 
     if ((rc = cand_cnt.ensure((size_t)pl.n_clusters * nq * 4))) return rc;
     UmmaParams fp;
     const UmmaParams* fpp = nullptr;
-    prs_xchg* xc = fuse_merge ? tail->xchg : nullptr;
     if (fuse_merge) {
         if (!st.gbar.p) {
             if ((rc = st.gbar.ensure(256))) return rc;
@@ -1026,18 +978,12 @@ static inline int search_umma(UmmaState& st, const void* x, const float* xnorm, 
         fp.sortn = next_pow2((int)std::max<long long>(k + UMMA_THREADS, (long long)pl.n_clusters * k));
         fp.out_mode = tail->out_mode; fp.largest = tail->largest; fp.id_offset = tail->id_offset; fp.D = tail->D; fp.I = tail->I;
         fp.rr = Rerank{tail->rerank_x, fuse_prep ? nullptr : (const uint16_t*)st.qlow.p, q, qdtype, d, pitch, storage == PRS_BF16 ? 1 : 0};
-        fp.use_xchg = xc ? 1 : 0; fp.xgen = 0; fp.timeout_ns = 0; fp.status = nullptr;
-        if (xc) {
-            ++xc->gen;
-            if (xc->used) PRS_CUDA(cudaStreamWaitEvent(stream, xc->event, 0));
-            fp.xv = xc->view; fp.xgen = xc->gen; fp.timeout_ns = xc->timeout_ns; fp.status = xc->d_status;
-        }
+        fp.status = nullptr;
         fpp = &fp;
     }
     if ((rc = umma_scan(st, pl, x, xnorm, n, pitch, storage, metric, nq, k, 1, 0, (u64*)cand.p, (int*)cand_cnt.p, nullptr, nullptr, nullptr, 0,
                         stream, timer, nullptr, 0, fpp))) return rc;
     st.boot_clean = fuse_merge;                                  // the fused tail leaves the bootstrap words zeroed
-    if (xc) { PRS_CUDA(cudaEventRecord(xc->event, stream)); xc->used = true; }
     if (fused_out) *fused_out = fuse_merge;
     *parts_out = pl.n_clusters;
     return 0;

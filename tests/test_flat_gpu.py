@@ -442,6 +442,49 @@ def test_sharded_container_roundtrip_and_mmap(P, storage, tmp_path):
         C.read_shard(os.path.join(os.path.dirname(__file__), "golden", "indices", "drugs_sentence_chunks.index"))
 
 
+def test_one_launch_search_equals_three_kernel_sequence(P):
+    """The cooperative one-launch search (queries converted by the epilogue threads, grid barrier, CTAs merge the
+    queries among themselves) must return bit for bit what prep -> scan -> merge return, search after search
+    (the bootstrap words and the grid barrier reset themselves), for fp32 / fp16 / bf16 queries and both metrics."""
+    import torch
+    dev = torch.device("cuda", 0)
+    for (n, d, nq, k, storage, metric) in [(1000, 200, 9, 7, "bf16", P.METRIC_L2), (20000, 768, 64, 10, "fp16", P.METRIC_INNER_PRODUCT),
+                                           (100000, 384, 128, 16, "bf16", P.METRIC_L2), (125, 384, 1, 5, "fp16", P.METRIC_L2),
+                                           (5000, 64, 33, 3, "fp16", P.METRIC_INNER_PRODUCT), (3000, 100, 5, 4, "fp16", P.METRIC_L2)]:
+        rng = np.random.default_rng(n + d)
+        x = rng.standard_normal((n, d)).astype(np.float32)
+        one = P.FlatIndex(d, metric, storage)
+        one.add(x)
+        three = P.FlatIndex(d, metric, storage)
+        three.add(x)
+        three.set_fused(False)
+        for rep in range(25):
+            qh = rng.standard_normal((nq, d)).astype(np.float32)
+            q = torch.from_numpy(qh).to(dev)
+            if rep % 3 == 1:
+                q = q.half()
+            elif rep % 3 == 2:
+                q = q.bfloat16()
+            D, I = one.search(q, k)
+            Dr, Ir = three.search(q, k)
+            assert one.last_path == "tcgen05" and not three.last_fused
+            assert one.last_fused                                  # (d % 8 != 0 keeps the preparation kernel, the merge is still fused)
+            assert torch.equal(I, Ir) and torch.equal(D, Dr), (n, d, nq, k, storage, metric, rep)
+        # numpy (pageable host) queries take the staged copy and the same kernels
+        D, I = one.search(qh, k)
+        Dr, Ir = three.search(qh, k)
+        assert np.array_equal(I, Ir) and np.array_equal(D, Dr)
+    # more than 128 queries or k > 16 are not one launch
+    big = P.FlatIndex(64, P.METRIC_INNER_PRODUCT, "fp16")
+    big.add(np.random.default_rng(0).standard_normal((40000, 64)).astype(np.float32))
+    big.search(np.zeros((129, 64), np.float32), 5)
+    assert not big.last_fused
+    big.search(np.zeros((4, 64), np.float32), 17)
+    assert not big.last_fused
+    big.search(np.zeros((4, 64), np.float32), 16)
+    assert big.last_fused
+
+
 def test_auto_path_selection(P):
     rng = np.random.default_rng(6)
     x = rng.standard_normal((2048, 256)).astype(np.float32)

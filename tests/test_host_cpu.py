@@ -45,6 +45,31 @@ def test_library_is_sm100a_only_with_tcgen05_and_tma():
         assert mnemonic in sass, mnemonic
 
 
+def test_scan_kernel_hot_loop_keeps_uniform_datapath_branches():
+    """Regression guard for a codegen cliff measured on B200 (one-launch search): when the kernel's parameter
+    block has its address taken / is indexed dynamically, or too much merge code becomes reachable from the scan kernel,
+    ptxas drops the uniform-datapath branches (BRA.U / UISETP) of the epilogue loop and guards its __syncwarp with
+    WARPSYNC.ALL -- the scan kernel then runs ~15 % slower.  Every instantiation must keep them."""
+    import shutil
+    import subprocess
+    if not shutil.which("cuobjdump"):
+        pytest.skip("cuobjdump not on PATH")
+    import persian_rag_system_b200 as P
+    sass = subprocess.run(["cuobjdump", "-sass", P._lib.LIB_PATH], capture_output=True, text=True).stdout
+    funcs = re.split(r"\n\s*Function : ", sass)
+    seen = 0
+    for f in funcs:
+        if "flat_scan_umma_kernel" not in f.split("\n", 1)[0]:
+            continue
+        seen += 1
+        lines = [l for l in f.split("\n") if re.match(r"\s+/\*[0-9a-f]{4,6}\*/", l)]
+        first = next(i for i, l in enumerate(lines) if "LDTM" in l)
+        window = "\n".join(lines[max(0, first - 40): first + 500])
+        assert "BRA.U" in window and "UISETP" in window, f.split("\n", 1)[0]
+        assert "WARPSYNC.ALL" not in "\n".join(lines[max(0, first - 40): first]), f.split("\n", 1)[0]
+    assert seen == 6
+
+
 def test_no_cpu_fallback_without_a_device(P):
     arch = P.lib().prs_device_arch(0)
     if arch == 100:
