@@ -9,7 +9,8 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libprs.so")
+# PRS_LIB_PATH selects another build of the same library (A/B runs of experiment builds: `make EXPERIMENTS=1 OUT=...`)
+LIB_PATH = os.environ.get("PRS_LIB_PATH") or os.path.join(_HERE, "libprs.so")
 
 OK, EINVAL, ECUDA, EIO, ENOMEM, EUNSUP = 0, -1, -2, -3, -4, -5
 METRIC_INNER_PRODUCT, METRIC_L2 = 0, 1

@@ -844,7 +844,11 @@ static inline int umma_plan(long long n, int pitch, long long nq, int sm_count, 
     pl.dbg = dbg;
     const int kblocks = pitch >> 6;
     pl.NB = pitch <= 512 ? 2 : 1;                   // row blocks per MMA tile (two accumulator buffers must fit TMEM)
+    // very large batches at pitch 768: 128-row tiles with ONE accumulator buffer (half the MMA instructions per row,
+    // epilogue and MMA of a tile no longer overlap): B = 4096 8.62 -> 7.97 ms, neutral at B = 1024
+    if (pitch > 512 && nq >= 2048) pl.NB = 2;
     if (dbg_nb == 1) pl.NB = 1;
+    if (dbg_nb == 2) pl.NB = 2;                     // experiment: 128-row tiles even when only ONE accumulator buffer fits (pitch > 512)
     // k-blocks per pipeline stage: stages of up to 48 KB.  Few, large stages keep the per-stage
     // barrier round trips of the single MMA-issuing thread off the critical path (measured: 8 KB
     // stages 3443 GB/s, 16 KB 4431, 48 KB 4513 -> see profiles/)
@@ -858,7 +862,11 @@ static inline int umma_plan(long long n, int pitch, long long nq, int sm_count, 
     pl.smem = 1024 + (size_t)pl.stages * stage_bytes + fixed;
     pl.n_tiles = (n + pl.NB * BLK_ROWS - 1) / (pl.NB * BLK_ROWS);
     // cluster size: query blocks that share one pass over the corpus
-    pl.CL = nq > 2 * UMMA_M ? 4 : (nq > UMMA_M ? 2 : 1);
+    // Clusters of 2 for every batch above 128 queries.  Clusters of 4 halve the passes over HBM again, but only 33 of
+    // them fit the 148 SMs (132 SMs busy) and these batches are tensor bound, not HBM bound: measured at 1M x 768,
+    // B = 512 / 1024 / 4096: 1.13 / 2.24 / 8.92 ms with clusters of 4 versus 0.97 / 1.93 / 8.62 ms with clusters of 2
+    // (profiles/r2_bigbatch_experiments.log).
+    pl.CL = nq > UMMA_M ? 2 : 1;
     if (dbg_cl == 1 || dbg_cl == 2 || dbg_cl == 4) pl.CL = dbg_cl;
     if (no_clusters) pl.CL = 1;
     int max_clusters = 0;
@@ -916,7 +924,7 @@ static inline int umma_scan(UmmaState& st, const UmmaPlan& pl, const void* x, co
         p.xnorm = xnorm; p.n_rows = n; p.pitch = pitch;
         p.nq = (int)std::min<long long>(pl.qblock, nq - q0);
         p.k = k; p.l2 = metric == PRS_METRIC_L2; p.stages = pl.stages; p.is_bf16 = storage == PRS_BF16; p.kbs = pl.kbs; p.dbg = pl.dbg;
-        p.nbuf = 2;
+        p.nbuf = (pl.NB == 2 && pitch > 512) ? 1 : 2;       // two 128-column accumulators do not fit beside a 768-wide query block
         p.nq_total = (int)nq; p.q0 = (int)q0;
         p.cand = cand; p.cand_cnt = cand_cnt;
         p.tile_step = tile_step; p.mode = mode; p.tau = tau; p.coll = coll; p.coll_cnt = coll_cnt; p.coll_cap = coll_cap;
