@@ -109,6 +109,21 @@ __device__ __forceinline__ void umma_ts_f16(uint32_t d_tmem, uint32_t a_tmem, ui
         ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(0), "r"(0), "r"(0), "r"(0)
         : "memory");
 }
+// same with a compile-time accumulate flag and without the optional disable-output-lane operand (fewest instructions per MMA)
+template <int ACC>
+__device__ __forceinline__ void umma_ts_f16_c(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "n"(ACC) : "memory");
+}
+// one thread of a converged warp (elect.sync): what single-thread issue loops (TMA, tcgen05.mma) should branch on
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 // ---- thread-block cluster helpers (large batches: one corpus stage feeds CL query blocks) ----
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ void cluster_sync_all() {
@@ -359,7 +374,7 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) flat_scan_umma_kernel(const U
     // meanwhile and release the MMA warp through named barrier 2 (128 + 32 threads).
     if (warp == 0) {
         // ---------------- TMA producer ----------------
-        if (lane == 0) {
+        if (elect_one()) {
             int s = 0;
             uint32_t ph = 0;
             const size_t blk_bytes = (size_t)BLK_ROWS * p.pitch * 2;
@@ -395,35 +410,38 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) flat_scan_umma_kernel(const U
         uint32_t ph = 0;
         named_bar_sync(2, 160);                               // queries are in TMEM
         tc_fence_after();
-        for (long long ti = part; ti < n_tiles; ti += nparts, ++it) {
-            const int b = nbuf == 2 ? (it & 1) : 0;
-            const uint32_t aph = (uint32_t)(nbuf == 2 ? (it >> 1) : it) & 1u;
-            mbar_wait(&tmem_empty[b], aph ^ 1u);
-            tc_fence_after();
-            const uint32_t d_tmem = tmem_base + D_OFF + (uint32_t)(b * TILE_N);
-            for (int ks = 0; ks < kstages; ++ks) {
-                mbar_wait(&full[s], ph);
+        // ONE elected thread runs the whole issue loop (elect.sync: the compiler then emits straight-line uniform-datapath
+        // code; with `if (lane == 0)` every tcgen05.mma was wrapped in an ELECT / BRA.U.ANY retry loop).  Per MMA the
+        // loop is two adds and the instruction itself: the shared-memory descriptor of a stage is built once and only its
+        // 14-bit address field is stepped (32 bytes per k16 slice, one 8 KB block piece per k-block), the accumulate
+        // flag is a compile-time predicate except for the first slice of a tile.  Measured before: ~12 instructions and
+        // ~100 cycles per MMA in this warp, i.e. the ISSUE loop -- not the tensor pipe (36 % busy) -- bound large batches.
+        if (elect_one()) {
+            constexpr uint64_t DESC_HI = (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+            for (long long ti = part; ti < n_tiles; ti += nparts, ++it) {
+                const int b = nbuf == 2 ? (it & 1) : 0;
+                const uint32_t aph = (uint32_t)(nbuf == 2 ? (it >> 1) : it) & 1u;
+                mbar_wait(&tmem_empty[b], aph ^ 1u);
                 tc_fence_after();
-                if (lane == 0) {
-                    const uint32_t sb = smem_u32(ring + (size_t)s * STAGE_BYTES);
+                const uint32_t d_tmem = tmem_base + D_OFF + (uint32_t)(b * TILE_N);
+                uint32_t a_tmem = tmem_base;
+                for (int ks = 0; ks < kstages; ++ks) {
+                    mbar_wait(&full[s], ph);
+                    tc_fence_after();
+                    uint64_t bdesc = DESC_HI | (uint64_t)((smem_u32(ring + (size_t)s * STAGE_BYTES) >> 4) & 0x3FFFu);
                     for (int kbi = 0; kbi < p.kbs; ++kbi) {
-                        const int kb = ks * p.kbs + kbi;
+                        if (ks == 0 && kbi == 0) umma_ts_f16_c<0>(d_tmem, a_tmem, bdesc, idesc);     // first slice of the tile overwrites
+                        else umma_ts_f16_c<1>(d_tmem, a_tmem, bdesc, idesc);
 #pragma unroll
-                        for (int k4 = 0; k4 < 4; ++k4) {
-                            const uint64_t bdesc = umma_desc_sw128(sb + (uint32_t)kbi * UMMA_KB_STAGE_BYTES + (uint32_t)k4 * 32u);
-                            const uint32_t a_tmem = tmem_base + (uint32_t)(kb * 32 + k4 * 8);
-                            // dbg 128 (timing experiment, wrong results): odd MMAs accumulate into the OTHER buffer,
-                            // i.e. two independent accumulation chains instead of one
-                            const uint32_t d_use = ((UMMA_DBG(p) & 128) && (k4 & 1)) ? (tmem_base + D_OFF + (uint32_t)((b ^ 1) * TILE_N)) : d_tmem;
-                            umma_ts_f16(d_use, a_tmem, bdesc, idesc, (kb | k4) != 0 ? 1u : 0u);
-                        }
+                        for (int k4 = 1; k4 < 4; ++k4) umma_ts_f16_c<1>(d_tmem, a_tmem + (uint32_t)(k4 * 8), bdesc + (uint64_t)(k4 * 2), idesc);
+                        a_tmem += 32u;
+                        bdesc += (uint64_t)(UMMA_KB_STAGE_BYTES >> 4);
                     }
                     if (CL == 1) umma_commit(&empty[s]);       // frees the smem stage when these MMAs retire
                     else umma_commit_multicast(&empty[s], CMASK);   // ... in every CTA of the cluster
                     if (ks == kstages - 1) umma_commit(&tmem_full[b]);
+                    if (++s == p.stages) { s = 0; ph ^= 1u; }
                 }
-                __syncwarp();
-                if (++s == p.stages) { s = 0; ph ^= 1u; }
             }
         }
     } else {
