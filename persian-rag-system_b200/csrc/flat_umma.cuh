@@ -58,6 +58,7 @@ struct UmmaParams {
     long long n_rows;
     int pitch, nq, k, l2, stages, is_bf16, kbs;   // kbs: k-blocks per pipeline stage
     int nbuf;               // accumulator buffers in TMEM: 2 when pitch <= 512, else 1
+    int reboot;             // mode 0: republish the CTA's running best and refresh the cross-CTA bound at tiles 1, 3, 15, 63, ...
     int dbg;                // experiments only (PRS_UMMA_DEBUG): 1 no bootstrap+no inserts, 2 epilogue releases without reading, 4 no MMA
     int nq_total, q0;
     u64* cand;              // [grid][nq_total][k]
@@ -686,8 +687,16 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) flat_scan_umma_kernel(const U
                 __threadfence();
                 refresh_boot();
                 if (UMMA_DBG(p) & 8) thr = INFINITY;
+            } else if (p.reboot && p.mode == 0 && (it & (it + 1)) == 0 && (it == 1 || (__ffs(it + 1) & 1))) {
+                // it = 1, 3, 15, 63, 255, ...: publish this CTA's best score SO FAR and take the bound again.  The k-th
+                // largest of the CTAs' running maxima tightens like 1 / (rows seen): between two refreshes a warp then
+                // meets only a handful of admissible scores, instead of ~k ln(rows / k) per thread when every CTA has
+                // to find its threshold alone (large batches were bound by exactly those insertions: 35 % of the
+                // epilogue's instructions and warp divergence on 4 of 5 tiles).
+                if (top[0]) boot[(size_t)part * UMMA_M + m] = (uint32_t)(top[0] >> 32);
+                refresh_boot();
             } else if (!boot_done && (it & (it + 1)) == 0) {
-                refresh_boot();          // it = 1, 3, 7, 15, ...
+                refresh_boot();          // first-tile maxima still arriving: it = 1, 3, 7, 15, ...
             }
             // 64 columns at a time: registers, mask, the rare insertions.  After the LAST load the
             // accumulator buffer goes straight back to the MMA warp.
@@ -844,7 +853,7 @@ static inline int umma_max_clusters(size_t smem, int sm_count) {
 
 // everything about a search that depends only on shapes
 struct UmmaPlan {
-    int CL = 1, NB = 1, kbs = 1, stages = 2, n_clusters = 1, dbg = 0;
+    int CL = 1, NB = 1, kbs = 1, stages = 2, n_clusters = 1, dbg = 0, reboot = 0;
     size_t smem = 0;
     long long n_tiles = 0, qblock = 128, nq_pad = 128, boot_words = 0, nblocks = 1;
 };
@@ -885,6 +894,12 @@ static inline int umma_plan(long long n, int pitch, long long nq, int sm_count, 
     // B = 512 / 1024 / 4096: 1.13 / 2.24 / 8.92 ms with clusters of 4 versus 0.97 / 1.93 / 8.62 ms with clusters of 2
     // (profiles/r2_bigbatch_experiments.log).
     pl.CL = nq > UMMA_M ? 2 : 1;
+    // tensor-bound batches are limited by the epilogue's insertions: keep the cross-CTA bound fresh (HBM-bound batches have
+    // epilogue slack and do not need the extra refreshes)
+    pl.reboot = nq > UMMA_M ? 1 : 0;
+#ifdef PRS_EXPERIMENTS
+    { static const int x = getenv("PRS_UMMA_REBOOT") ? atoi(getenv("PRS_UMMA_REBOOT")) : -1; if (x >= 0) pl.reboot = x; }
+#endif
     if (dbg_cl == 1 || dbg_cl == 2 || dbg_cl == 4) pl.CL = dbg_cl;
     if (no_clusters) pl.CL = 1;
     int max_clusters = 0;
@@ -942,6 +957,7 @@ static inline int umma_scan(UmmaState& st, const UmmaPlan& pl, const void* x, co
         p.xnorm = xnorm; p.n_rows = n; p.pitch = pitch;
         p.nq = (int)std::min<long long>(pl.qblock, nq - q0);
         p.k = k; p.l2 = metric == PRS_METRIC_L2; p.stages = pl.stages; p.is_bf16 = storage == PRS_BF16; p.kbs = pl.kbs; p.dbg = pl.dbg;
+        p.reboot = pl.reboot;
         p.nbuf = (pl.NB == 2 && pitch > 512) ? 1 : 2;       // two 128-column accumulators do not fit beside a 768-wide query block
         p.nq_total = (int)nq; p.q0 = (int)q0;
         p.cand = cand; p.cand_cnt = cand_cnt;
