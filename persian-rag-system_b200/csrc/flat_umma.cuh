@@ -85,6 +85,9 @@ struct UmmaParams {
     long long* I;
     Rerank rr;
     int* status;            // host-mapped report word (grid-barrier timeout), may be null
+    int use_xchg;           // row-sharded search: the tail PUSHES the local lists to the peers (xchg_pull_kernel finishes)
+    uint32_t xgen;
+    XchgView xv;
 };
 
 // ---------------- PTX wrappers (tcgen05 / TMA) ----------------
@@ -261,9 +264,26 @@ __device__ __noinline__ void fused_merge_plain(const u64* cand, int parts, int n
                                                long long id_offset, Rerank rr, float* D, long long* I, int q, int tid, unsigned char* smem) {
     merge_query<UMMA_THREADS, false, UMMA_FUSED_ONESHOT>(cand, parts, nq, k, sortn, out_mode, qnorm, id_offset, rr, D, I, q, tid, smem);
 }
-// One-launch search, tail: grid barrier, then the CTAs merge the queries among themselves.  (Row-sharded searches keep
-// the separate merge + NVLink exchange kernel: with the exchange code reachable from this kernel ptxas stops emitting
-// uniform-datapath branches in the hot loops -- the scan got 15 % slower, more than the saved launches are worth.)
+// row-sharded variant of the tail: local merge + push to the peers' exchange buffers.  Arguments come through shared
+// memory (the peers' pointers are indexed by rank at run time; see stage_query_row for why not from the parameter block).
+struct FusedPushArgs {
+    XchgView xv;
+    Rerank rr;
+    const u64* cand;
+    const float* qnorm;
+    long long id_offset;
+    uint32_t gen;
+    int parts, nq, k, sortn, out_mode;
+};
+__device__ __noinline__ void fused_push(const FusedPushArgs* a, int q, int tid, unsigned char* smem) {
+    xchg_push_query<UMMA_THREADS, false, UMMA_FUSED_ONESHOT>(a->cand, a->parts, a->nq, a->k, a->sortn, a->out_mode, a->qnorm, a->id_offset, a->rr,
+                                                             a->xv, a->gen, q, tid, smem);
+}
+
+// One-launch search, tail: grid barrier, then the CTAs merge the queries among themselves.  Row-sharded searches only
+// PUSH here (local merge + stores into the peers' buffers); waiting for the peers and the G-way merge are a second, tiny
+// kernel: with the whole exchange reachable from this kernel ptxas stops emitting uniform-datapath branches in the hot
+// loops (the scan got 15 % slower), and pushing early lets the NVLink stores overlap the peers' tails.
 __device__ __forceinline__ void fused_tail(const UmmaParams& p, int part, int nparts, int tid, unsigned char* base, int* s_flag) {
     // ---------------- one-launch search: grid barrier, then the CTAs merge the queries among themselves ----------------
     // The launch is cooperative (all CTAs co-resident).  Every CTA's lists are written (the __syncthreads above);
@@ -298,7 +318,26 @@ __device__ __forceinline__ void fused_tail(const UmmaParams& p, int part, int np
     // the bootstrap words this CTA used are cleared for the next search on this workspace
     for (int i = tid; i < UMMA_M; i += UMMA_THREADS) p.boot[(size_t)part * UMMA_M + i] = 0u;
     if (part == 0 && tid == 0) p.boot[(size_t)nparts * UMMA_M] = 0u;
+    FusedPushArgs* xa = reinterpret_cast<FusedPushArgs*>(base + 96 * 1024);
+    if (p.use_xchg) {
+        if (tid == 0) {
+#pragma unroll
+            for (int r = 0; r < XCHG_MAX_RANKS; ++r) {
+                xa->xv.vals[r] = p.xv.vals[r]; xa->xv.vals2[r] = p.xv.vals2[r]; xa->xv.ids[r] = p.xv.ids[r]; xa->xv.flags[r] = p.xv.flags[r];
+            }
+            xa->xv.cap = p.xv.cap; xa->xv.nq_cap = p.xv.nq_cap; xa->xv.G = p.xv.G; xa->xv.rank = p.xv.rank;
+            xa->rr = p.rr; xa->cand = p.cand; xa->qnorm = p.qnorm; xa->id_offset = p.id_offset; xa->gen = p.xgen;
+            xa->parts = nparts; xa->nq = p.nq_total; xa->k = p.k; xa->sortn = p.sortn; xa->out_mode = p.out_mode;
+        }
+        __syncthreads();
+    }
     for (int q = part; q < p.nq; q += nparts) {
+        if (p.use_xchg) {
+            // (a barrier time-out leaves this rank's flags unset: the peers' pull kernels then time out and report)
+            if (ok) fused_push(xa, q, tid, base);
+            __syncthreads();
+            continue;
+        }
         if (!ok) {
             for (int j = tid; j < p.k; j += UMMA_THREADS) {
                 p.D[(size_t)q * p.k + j] = p.largest ? -3.402823466e+38f : 3.402823466e+38f;
@@ -791,7 +830,8 @@ struct UmmaTail {
     float* D = nullptr;
     long long* I = nullptr;
     const unsigned char* rerank_x = nullptr;      // corpus pointer when the 16-bit L2 re-rank is on
-    prs_xchg* xchg = nullptr;                      // row-sharded search: keeps the separate merge + exchange kernel
+    prs_xchg* xchg = nullptr;                      // row-sharded search: the tail pushes, xchg_pull_kernel finishes
+    ScanTimer* timer_merge = nullptr;
     int device = 0;
 };
 
@@ -951,7 +991,8 @@ static inline int umma_scan(UmmaState& st, const UmmaPlan& pl, const void* x, co
         UmmaParams p;
         if (fused) p = *fused;                                  // one-launch search: prologue / tail fields (single pass)
         else { p.q = nullptr; p.qdtype = 0; p.d = 0; p.fuse_prep = 0; p.fuse_merge = 0; p.qnorm = nullptr; p.gbar = nullptr; p.sortn = 0;
-               p.out_mode = 0; p.largest = 1; p.id_offset = 0; p.D = nullptr; p.I = nullptr; p.rr = Rerank{}; p.status = nullptr; }
+               p.out_mode = 0; p.largest = 1; p.id_offset = 0; p.D = nullptr; p.I = nullptr; p.rr = Rerank{}; p.status = nullptr;
+               p.use_xchg = 0; p.xgen = 0; }
         p.x = (const unsigned char*)x;
         p.qlow = (const uint16_t*)st.qlow.p + (size_t)q0 * pitch;
         p.xnorm = xnorm; p.n_rows = n; p.pitch = pitch;
@@ -987,7 +1028,8 @@ static inline bool umma_local_device_ptr(const void* ptr, int device) {
 // With `tail` (and nq <= 128: one pass, no clusters) the whole search is ONE cooperative launch: the epilogue
 // threads convert their own query rows (when q is local device memory and d % 8 == 0; otherwise the preparation
 // kernel still runs -- it reads host-mapped or peer queries exactly once), and after a grid barrier the CTAs merge
-// the queries among themselves (merge_query of topk_merge.cuh).  *fused tells the caller that D / I are already on their way.
+// the queries among themselves (merge_query of topk_merge.cuh; row-sharded: push here + xchg_pull_kernel).  *fused tells the
+// caller that D / I are already on their way.
 static inline int search_umma(UmmaState& st, const void* x, const float* xnorm, long long n, int d, int pitch, int storage,
                               int metric, int sm_count, const void* q, int qdtype, long long nq, int k, float* qnorm,
                               DevBuf& cand, DevBuf& cand_cnt, int* parts_out, cudaStream_t stream, ScanTimer* timer = nullptr, ScanTimer* timer_prep = nullptr,
@@ -996,7 +1038,7 @@ static inline int search_umma(UmmaState& st, const void* x, const float* xnorm, 
     int rc;
     if (fused_out) *fused_out = false;
     if ((rc = umma_plan(n, pitch, nq, sm_count, pl))) return rc;
-    const bool fuse_merge = tail && tail->enable && !tail->xchg && pl.CL == 1 && nq <= pl.qblock;
+    const bool fuse_merge = tail && tail->enable && pl.CL == 1 && nq <= pl.qblock;
     const bool fuse_prep = fuse_merge && d % 8 == 0 && ((uintptr_t)q & 15u) == 0 && umma_local_device_ptr(q, tail->device);
     if (!fuse_prep) {
         if ((rc = umma_prep(st, pl, q, qdtype, nq, d, pitch, storage, qnorm, stream, timer_prep))) return rc;
@@ -1021,11 +1063,32 @@ static inline int search_umma(UmmaState& st, const void* x, const float* xnorm, 
         fp.out_mode = tail->out_mode; fp.largest = tail->largest; fp.id_offset = tail->id_offset; fp.D = tail->D; fp.I = tail->I;
         fp.rr = Rerank{tail->rerank_x, fuse_prep ? nullptr : (const uint16_t*)st.qlow.p, q, qdtype, d, pitch, storage == PRS_BF16 ? 1 : 0};
         fp.status = nullptr;
+        fp.use_xchg = 0; fp.xgen = 0;
+        if (tail->xchg) {
+            // row-sharded: the tail pushes this rank's lists into the peers' buffers; xchg_pull_kernel (below) waits for
+            // theirs and merges.  Searches on one exchange context are ordered through its event.
+            prs_xchg* xc = tail->xchg;
+            ++xc->gen;
+            if (xc->used) PRS_CUDA(cudaStreamWaitEvent(stream, xc->event, 0));
+            fp.use_xchg = 1; fp.xgen = xc->gen; fp.xv = xc->view;
+        }
         fpp = &fp;
     }
     if ((rc = umma_scan(st, pl, x, xnorm, n, pitch, storage, metric, nq, k, 1, 0, (u64*)cand.p, (int*)cand_cnt.p, nullptr, nullptr, nullptr, 0,
                         stream, timer, nullptr, 0, fpp))) return rc;
     st.boot_clean = fuse_merge;                                  // the fused tail leaves the bootstrap words zeroed
+    if (fuse_merge && tail->xchg) {
+        prs_xchg* xc = tail->xchg;
+        const int sortn2 = next_pow2(std::max(k + XCHG_PULL_THREADS, xc->G * k));
+        const size_t smem2 = merge_smem_bytes(sortn2, XCHG_PULL_THREADS, k);
+        if (tail->timer_merge) tail->timer_merge->begin(stream);
+        xchg_pull_kernel<<<(unsigned)nq, XCHG_PULL_THREADS, smem2, stream>>>(k, sortn2, tail->out_mode, tail->largest, tail->rerank_x ? 1 : 0, xc->view,
+                                                                            xc->gen, xc->timeout_ns, tail->D, tail->I, xc->d_status);
+        if (tail->timer_merge) tail->timer_merge->end(stream);
+        PRS_LAUNCH_CHECK();
+        PRS_CUDA(cudaEventRecord(xc->event, stream));
+        xc->used = true;
+    }
     if (fused_out) *fused_out = fuse_merge;
     *parts_out = pl.n_clusters;
     return 0;

@@ -59,18 +59,20 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
 // carries its direct-form distance (vals2), which becomes the output value and the final order.
 // status: host-mapped word; set to 1 when a peer's lists did not arrive within timeout_ns -- the
 // query's output is then the empty-result sentinel (ids -1), never a merge of stale lists.
-// One query (all NT threads of the CTA call it).
-template <int NT, bool STREAM = true, int ONESHOT = MERGE_ONESHOT, int ONESHOT2 = MERGE_ONESHOT>
-__device__ __forceinline__ void merge_xchg_query(
+// The exchange of one query has two halves, usable from one kernel (merge_xchg_kernel) or from two (the one-launch scan
+// pushes in its tail, xchg_pull_kernel finishes): all NT threads of the CTA call them.
+//
+// PUSH: local merge over this rank's CTAs (+ direct-form distances), the local list stored into every rank's buffer,
+// the flag of (slot, this rank, query) released at system scope.
+template <int NT, bool STREAM = true, int ONESHOT = MERGE_ONESHOT>
+__device__ __forceinline__ void xchg_push_query(
     const u64* __restrict__ cand, int parts, int nq, int k, int sortn,
-    int out_mode, const float* __restrict__ qnorm, long long id_offset, int largest, const Rerank& rr,
-    const XchgView& xv, uint32_t gen, unsigned long long timeout_ns, float* __restrict__ D, long long* __restrict__ I,
-    volatile int* status, int q, int tid, unsigned char* msm) {
+    int out_mode, const float* __restrict__ qnorm, long long id_offset, const Rerank& rr,
+    const XchgView& xv, uint32_t gen, int q, int tid, unsigned char* msm) {
     u64* buf = reinterpret_cast<u64*>(msm);
     u64* heads = buf + sortn;
-    int* s_n = reinterpret_cast<int*>(heads + NT);                 // [0..1] block_topk_lists, [2] timeout flag
+    int* s_n = reinterpret_cast<int*>(heads + NT);
     float* dd = reinterpret_cast<float*>(s_n + 4);                 // [k]
-    long long* ids_s = reinterpret_cast<long long*>(dd + ((k + 1) & ~1));   // [k]
     const int G = xv.G, slot = (int)(gen & 1u);
     const bool rerank = out_mode == 2 && rr.x != nullptr;
 
@@ -80,35 +82,22 @@ __device__ __forceinline__ void merge_xchg_query(
         return __ldcg(cand + ((size_t)part * nq + q) * k + j);
     };
     const int n = block_topk_lists<NT, STREAM, ONESHOT>(fetch, parts, k, k, buf, sortn, heads, s_n, tid);
-    if (tid == 0) s_n[2] = 0;
     if (rerank) {
         __syncthreads();
         direct_l2_of_keys<NT>(buf, n, rr, q, dd, tid);
     }
     __syncthreads();
-    // keep the local list in registers: buf is reused by the second merge
-    u64 mine[(PRS_MAX_K + NT - 1) / NT];
-    float mine_dd[(PRS_MAX_K + NT - 1) / NT];
-#pragma unroll
-    for (int r = 0; r < (PRS_MAX_K + NT - 1) / NT; ++r) {
-        const int j = tid + r * NT;
-        mine[r] = (j < n) ? buf[j] : 0ull;
-        mine_dd[r] = (rerank && j < n) ? dd[j] : 0.f;
-    }
-
     // ---- 2. push the local list into every rank's buffer (slot, my rank, query q) ----
     const size_t ebase = ((size_t)slot * G + xv.rank) * (size_t)xv.cap + (size_t)q * k;
-#pragma unroll
-    for (int r = 0; r < (PRS_MAX_K + NT - 1) / NT; ++r) {
-        const int j = tid + r * NT;
-        if (j >= k) break;
-        float dv;
+    for (int j = tid; j < k; j += NT) {
+        float dv, d2 = 0.f;
         long long iv;
         if (j < n) {
-            const u64 key = mine[r];
+            const u64 key = buf[j];
             const float s = key_score(key);
             dv = out_mode == 0 ? s : (out_mode == 1 ? -s : fmaxf(0.f, qnorm[q] - s));
             iv = (long long)key_id<PRS_TIE_LOW_ID>(key) + id_offset;
+            if (rerank) d2 = dd[j];
         } else {
             dv = out_mode == 0 ? -3.402823466e+38f : 3.402823466e+38f;
             iv = -1;
@@ -116,14 +105,30 @@ __device__ __forceinline__ void merge_xchg_query(
         for (int p = 0; p < G; ++p) {
             xv.vals[p][ebase + j] = dv;
             xv.ids[p][ebase + j] = iv;
-            if (rerank) xv.vals2[p][ebase + j] = mine_dd[r];
+            if (rerank) xv.vals2[p][ebase + j] = d2;
         }
     }
     // bar.sync orders the CTA's stores before the flag writers; st.release.sys is cumulative, so the
     // peer that acquires the flag sees the whole list (no per-thread system fence needed)
     __syncthreads();
     if (tid < G) st_release_sys(xv.flags[tid] + ((size_t)slot * G + xv.rank) * xv.nq_cap + q, gen);
-    // ---- 3. wait for the other ranks' lists of this query (they arrive in MY memory) ----
+}
+
+// PULL: bounded wait for the other ranks' lists of this query (they arrive in MY memory), then the G-way merge.
+// smem: buf [sortn] | heads [NT] | s_n [4] | dd [k] | ids [k]
+template <int NT, bool STREAM = true, int ONESHOT2 = MERGE_ONESHOT>
+__device__ __forceinline__ void xchg_pull_query(
+    int k, int sortn, int out_mode, int largest, bool rerank, const XchgView& xv, uint32_t gen, unsigned long long timeout_ns,
+    float* __restrict__ D, long long* __restrict__ I, volatile int* status, int q, int tid, unsigned char* msm) {
+    u64* buf = reinterpret_cast<u64*>(msm);
+    u64* heads = buf + sortn;
+    int* s_n = reinterpret_cast<int*>(heads + NT);                 // [0..1] block_topk_lists, [2] timeout flag
+    float* dd = reinterpret_cast<float*>(s_n + 4);                 // [k]
+    long long* ids_s = reinterpret_cast<long long*>(dd + ((k + 1) & ~1));   // [k]
+    const int G = xv.G, slot = (int)(gen & 1u);
+    if (tid == 0) s_n[2] = 0;
+    __syncthreads();
+    // ---- 3. wait for the other ranks' lists of this query ----
     if (tid < G) {
         const uint32_t* f = xv.flags[xv.rank] + ((size_t)slot * G + tid) * xv.nq_cap + q;
         unsigned long long t0 = 0;
@@ -202,6 +207,18 @@ __device__ __forceinline__ void merge_xchg_query(
     }
 }
 
+// both halves in one kernel (searches that are not one launch: clusters, wide k, the fp32 scan)
+template <int NT>
+__device__ __forceinline__ void merge_xchg_query(
+    const u64* __restrict__ cand, int parts, int nq, int k, int sortn,
+    int out_mode, const float* __restrict__ qnorm, long long id_offset, int largest, const Rerank& rr,
+    const XchgView& xv, uint32_t gen, unsigned long long timeout_ns, float* __restrict__ D, long long* __restrict__ I,
+    volatile int* status, int q, int tid, unsigned char* msm) {
+    xchg_push_query<NT>(cand, parts, nq, k, sortn, out_mode, qnorm, id_offset, rr, xv, gen, q, tid, msm);
+    __syncthreads();
+    xchg_pull_query<NT>(k, sortn, out_mode, largest, out_mode == 2 && rr.x != nullptr, xv, gen, timeout_ns, D, I, status, q, tid, msm);
+}
+
 __global__ void __launch_bounds__(MERGE_THREADS) merge_xchg_kernel(
     const u64* __restrict__ cand, int parts, int nq, int k, int sortn,
     int out_mode, const float* __restrict__ qnorm, long long id_offset, int largest, const Rerank rr,
@@ -210,6 +227,16 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_xchg_kernel(
     extern __shared__ __align__(16) unsigned char msm[];
     merge_xchg_query<MERGE_THREADS>(cand, parts, nq, k, sortn, out_mode, qnorm, id_offset, largest, rr, xv, gen, timeout_ns, D, I, status,
                                     (int)blockIdx.x, (int)threadIdx.x, msm);
+}
+
+// second launch of a row-sharded one-launch search: the scan kernel's tail has already pushed this rank's lists
+constexpr int XCHG_PULL_THREADS = 64;
+__global__ void __launch_bounds__(XCHG_PULL_THREADS) xchg_pull_kernel(int k, int sortn, int out_mode, int largest, int rerank, const XchgView xv,
+                                                                      uint32_t gen, unsigned long long timeout_ns, float* __restrict__ D,
+                                                                      long long* __restrict__ I, volatile int* status) {
+    extern __shared__ __align__(16) unsigned char msm[];
+    xchg_pull_query<XCHG_PULL_THREADS, true, 256>(k, sortn, out_mode, largest, rerank != 0, xv, gen, timeout_ns, D, I, status, (int)blockIdx.x,
+                                                  (int)threadIdx.x, msm);
 }
 
 }  // namespace prs

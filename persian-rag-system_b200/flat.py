@@ -124,9 +124,10 @@ class FlatIndex:
         check(self._L.prs_index_set_path(self._h, code))
 
     def set_fused(self, enable: bool) -> None:
-        """One-launch search (prep + scan + merge in one cooperative kernel, default on) vs the three-kernel sequence."""
+        """One-launch search (prep + scan + merge in one cooperative kernel, default on) vs the three-kernel sequence.
+        `enable=2` also fuses row-sharded searches (push in the scan kernel's tail + a small pull kernel)."""
         self._single_only("set_fused")
-        check(self._L.prs_index_set_fused(self._h, 1 if enable else 0))
+        check(self._L.prs_index_set_fused(self._h, int(enable)))
 
     @property
     def last_fused(self) -> bool:

@@ -65,7 +65,9 @@ def _worker(rank, world, port, out_dir):
             lo, hi = shard_bounds(n, world, rank)
             sh.add_local(base[lo:hi], lo, n)
             ok = True
-            for rep in range(3):                               # slot alternation / generation counter
+            for rep in range(4):                               # slot alternation / generation counter
+                if rep == 2:
+                    sh.local.set_fused(2)                      # push in the scan kernel's tail + pull kernel (nq <= 128, k <= 16)
                 D, I = sh.search(qd, k)
                 ok = ok and bool(torch.equal(I, Iw)) and bool(torch.equal(D, Dw))
             sh.check_exchange()
