@@ -158,6 +158,12 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         : "r"(taddr) : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// three-input maximum (one FMNMX3 on sm_100)
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+    float d;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
     asm volatile(
         "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
@@ -535,7 +541,7 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) flat_scan_umma_kernel(const U
         }
         const int G = nparts;
         uint32_t* const boot = p.boot + (size_t)crank * p.boot_stride;    // one bootstrap array per query block
-        float thr = -INFINITY;          // admission threshold = max(bootstrap bound, this CTA's k-th best)
+        float thr = qvalid ? -INFINITY : INFINITY;   // admission threshold = max(bootstrap bound, this CTA's k-th best); empty slots admit nothing
         bool boot_done = false;
         // mode 1 (wide k): fixed threshold tau[q]; every score that reaches it goes, unsorted, into this
         // thread's private slice of the collection buffer (no atomics: one thread owns (part, query))
@@ -603,6 +609,21 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) flat_scan_umma_kernel(const U
         };
         // fast path: one compare per score into a bit mask (no branches, small code)
         auto survivors = [&](const uint32_t (&v)[BLK_ROWS], int nv, uint32_t (&hm)[2]) {
+            // Once the thresholds are tight almost no tile holds an admissible score: take the maximum of the 64
+            // scores first (3-input max: 32 instructions) and build the bit masks (128+ instructions) only when it
+            // reaches the threshold.  The four epilogue warps have a scheduler each and no other warp to hide their
+            // latencies behind, so their instruction count per tile is what bounds tensor-bound batches.
+            {
+                float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+                for (int j = 0; j < BLK_ROWS; j += 4) {
+                    m0 = fmax3(m0, __uint_as_float(v[j]), __uint_as_float(v[j + 1]));
+                    m1 = fmax3(m1, __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+                }
+                // (invalid columns of a short tile and NaNs are sorted out by the masks; a NaN maximum compares false,
+                // exactly like the per-score test)
+                if (!(fmaxf(m0, m1) >= thr) && nv >= BLK_ROWS) { hm[0] = hm[1] = 0u; return; }
+            }
 #pragma unroll
             for (int hh = 0; hh < 2; ++hh) {
                 hm[hh] = 0u;
