@@ -932,9 +932,10 @@ static inline int umma_plan(long long n, int pitch, long long nq, int sm_count, 
     pl.dbg = dbg;
     const int kblocks = pitch >> 6;
     pl.NB = pitch <= 512 ? 2 : 1;                   // row blocks per MMA tile (two accumulator buffers must fit TMEM)
-    // very large batches at pitch 768: 128-row tiles with ONE accumulator buffer (half the MMA instructions per row,
-    // epilogue and MMA of a tile no longer overlap): B = 4096 8.62 -> 7.97 ms, neutral at B = 1024
-    if (pitch > 512 && nq >= 2048) pl.NB = 2;
+    // tensor-bound batches at pitch 768: 128-row tiles with ONE accumulator buffer (half the MMA instructions per row --
+    // a TS-mode MMA costs ~54 cycles whatever N <= 64 is -- while the now lean epilogue and the MMAs of a tile no longer
+    // overlap): B = 256 / 1024 / 4096 0.440 / 1.715 / 7.28 -> 0.429 / 1.686 / 6.90 ms (profiles/r2_bigbatch_experiments.log)
+    if (pitch > 512 && nq > UMMA_M) pl.NB = 2;
     if (dbg_nb == 1) pl.NB = 1;
     if (dbg_nb == 2) pl.NB = 2;                     // experiment: 128-row tiles even when only ONE accumulator buffer fits (pitch > 512)
     // k-blocks per pipeline stage: stages of up to 48 KB.  Few, large stages keep the per-stage

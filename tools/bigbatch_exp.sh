@@ -1,5 +1,5 @@
 #!/bin/bash
-# large-batch experiments on the experiments build (make EXPERIMENTS=1 OUT=../libprs_x.so): tile width x cluster size
+# large-batch experiments on the experiments build (make EXPERIMENTS=1 OBJDIR=build_x OUT=../libprs_x.so): tile width x cluster size x bound refresh
 export PRS_LIB_PATH=$PWD/persian-rag-system_b200/libprs_x.so
 run() { env "$@" python - <<'PY'
 import os, torch, sys
@@ -18,13 +18,14 @@ for B in (256, 512, 1024, 4096):
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(6): idx.search(q, 10)
+    for _ in range(8): idx.search(q, 10)
     e1.record(); torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / 6
+    ms = e0.elapsed_time(e1) / 8
     out.append(f"B={B}: {ms:.3f} ms {2.0*n*d*B/(ms*1e-3)/1e12:.0f} TF")
-print(os.environ.get("PRS_UMMA_NB", "-"), os.environ.get("PRS_UMMA_CLUSTER", "-"), "d=%d" % d, " | ".join(out), flush=True)
+print("NB", os.environ.get("PRS_UMMA_NB", "-"), "CL", os.environ.get("PRS_UMMA_CLUSTER", "-"), "REBOOT", os.environ.get("PRS_UMMA_REBOOT", "-"), "d=%d" % d, " | ".join(out), flush=True)
 PY
 }
-for nb in 0 2; do for cl in 0 2 4; do run PRS_UMMA_NB=$nb PRS_UMMA_CLUSTER=$cl; done; done
+for nb in 0 2; do for cl in 2 4; do run PRS_UMMA_NB=$nb PRS_UMMA_CLUSTER=$cl; done; done
+run PRS_UMMA_NB=2 PRS_UMMA_CLUSTER=2 PRS_UMMA_REBOOT=0
+run PRS_UMMA_NB=0 PRS_UMMA_CLUSTER=2 PRS_UMMA_REBOOT=0
 run PRS_UMMA_NB=0 PRS_UMMA_CLUSTER=2 DD=384
-run PRS_UMMA_NB=0 PRS_UMMA_CLUSTER=4 DD=384
