@@ -264,6 +264,18 @@ int prs_hybrid_fuse_device(const float* D_dense, const int64_t* I_dense, int kd,
                            double sparse_weight, int top_k, double* S_out, int64_t* I_out, int device, void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * IVF-Flat (the reference's branch for >= 1000 embeddings, scripts/phase3_pdf_chunking.py:45-57:
+ * faiss.IndexIVFFlat(faiss.IndexFlatL2(d), d, nlist); index.train(first 10 000 rows); default nprobe = 1).
+ * Nearest-centroid assignment, the coarse probe and the scan of an inverted list are exact flat searches and use
+ * the prs_index_* entry points (host logic: ivf.py).  This is the remaining piece: the k-means centroid update,
+ * centroids[c] = mean of the rows assigned to c, summed in row order in float32 like faiss's compute_centroids
+ * (bit-identical to a sequential restatement).  x [n, d] float32, assign [n] int64 in [0, k), centroids [k, d]
+ * in/out (an empty cluster keeps its centroid), counts [k] out -- all on the device.  Asynchronous on `stream`.
+ * ------------------------------------------------------------------------------------- */
+int prs_centroid_update_device(const float* x, int64_t n, int d, const int64_t* assign, int k, float* centroids,
+                               int64_t* counts, int device, void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * Encoder output epilogue: attention-masked mean pooling (+ optional L2 normalisation).
  * replaces the tail of SentenceTransformer.encode  src/retrieval.py:98, src/create_embeddings.py:97-101
  *   out[b,:] = sum_t hidden[b,t,:]*mask[b,t] / max(sum_t mask[b,t], 1e-9);  if normalize:

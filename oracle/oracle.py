@@ -547,3 +547,127 @@ def check_topk_lists(I_a, D_a, I_ref, D_ref, rtol, atol=0.0, what=""):
                 assert abs(last - v) <= 2 * (rtol * abs(last) + atol) + t, \
                     f"{what}: q{r} id {I_ref[r, j]} (value {v}) missing and not tied with boundary {last}"
     return nflip
+
+
+# --------------------------------------------------------------------------------------
+# faiss 1.7.4 IndexIVFFlat (scripts/phase3_pdf_chunking.py:45-57), restated: TEST INFRASTRUCTURE.
+# PARITY UNPINNED like every faiss call (no wheel here); what IS pinned: std::mt19937's published first
+# output for the default seed (tests/test_oracle.py), which anchors the permutation faiss draws its
+# initial centroids from.
+# --------------------------------------------------------------------------------------
+class _StdMt19937:
+    """std::mt19937 with init_genrand seeding (faiss RandomGenerator: `std::mt19937 mt((unsigned)seed)`)."""
+
+    def __init__(self, seed: int):
+        self.mt = [0] * 624
+        self.mt[0] = seed & 0xFFFFFFFF
+        for i in range(1, 624):
+            p = self.mt[i - 1]
+            self.mt[i] = (1812433253 * (p ^ (p >> 30)) + i) & 0xFFFFFFFF
+        self.pos = 624
+
+    def __call__(self) -> int:
+        if self.pos == 624:
+            mt = self.mt
+            for i in range(624):
+                y = (mt[i] & 0x80000000) | (mt[(i + 1) % 624] & 0x7FFFFFFF)
+                mt[i] = mt[(i + 397) % 624] ^ (y >> 1) ^ (0x9908B0DF if y & 1 else 0)
+            self.pos = 0
+        y = self.mt[self.pos]
+        self.pos += 1
+        y ^= y >> 11
+        y ^= (y << 7) & 0x9D2C5680
+        y ^= (y << 15) & 0xEFC60000
+        return (y ^ (y >> 18)) & 0xFFFFFFFF
+
+
+def faiss_rand_perm_oracle(n: int, seed: int) -> np.ndarray:
+    """faiss utils/random.cpp rand_perm: `for i in [0, n-1): swap(perm[i], perm[i + rng.rand_int(n - i)])`,
+    rand_int(max) = mt() % max."""
+    rng = _StdMt19937(seed)
+    perm = list(range(n))
+    for i in range(n - 1):
+        j = i + rng() % (n - i)
+        perm[i], perm[j] = perm[j], perm[i]
+    return np.asarray(perm, dtype=np.int64)
+
+
+class IVFFlatOracle:
+    """faiss.IndexIVFFlat(faiss.IndexFlatL2(d), d, nlist) as the reference builds and queries it:
+    Level1Quantizer clustering defaults (niter 10, seed 1234, max_points_per_centroid 256), nprobe 1."""
+
+    def __init__(self, d: int, nlist: int, nprobe: int = 1, niter: int = 10, seed: int = 1234):
+        self.d, self.nlist, self.nprobe, self.niter, self.seed = d, nlist, nprobe, niter, seed
+        self.centroids = None
+        self.lists = [[] for _ in range(nlist)]
+        self.x = np.empty((0, d), np.float32)
+
+    def _assign(self, x, centroids):
+        # IndexFlatL2.search(x, 1): faiss takes the sgemm (expanded) path for >= 20 queries; this oracle's form=0 does
+        # the same in scalar C.  Near-ties can therefore land on either side in ANY implementation.
+        return flat_search_c(centroids, x, 1, METRIC_L2, form=0)[1][:, 0]
+
+    def train(self, x: np.ndarray) -> None:
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        n, k = x.shape[0], self.nlist
+        if n > k * 256:                                    # subsample_training_set
+            x = x[faiss_rand_perm_oracle(n, self.seed)[: k * 256]]
+            n = x.shape[0]
+        c = x[faiss_rand_perm_oracle(n, self.seed + 1)[:k]].copy()
+        for _ in range(self.niter):
+            a = self._assign(x, c)
+            cnt = np.zeros(k, np.int64)
+            for ci in range(k):                            # compute_centroids: float32 sums in point order, then * (1 / count)
+                rows = x[a == ci]
+                cnt[ci] = rows.shape[0]
+                if rows.shape[0]:
+                    s = np.zeros(self.d, np.float32)
+                    for r in rows:
+                        s += r
+                    c[ci] = s * (np.float32(1.0) / np.float32(rows.shape[0]))
+            if (cnt == 0).any():                           # split_clusters
+                rng = _StdMt19937(1234)
+                eps = np.float32(1.0 / 1024.0)
+                for ci in range(k):
+                    if cnt[ci]:
+                        continue
+                    cj = 0
+                    while True:
+                        p = (float(cnt[cj]) - 1.0) / float(n - k)
+                        if float(np.float32(rng()) / np.float32(0xFFFFFFFF)) < p:
+                            break
+                        cj = (cj + 1) % k
+                    c[ci] = c[cj]
+                    for j in range(self.d):
+                        if j % 2 == 0:
+                            c[ci, j] *= np.float32(1) + eps
+                            c[cj, j] *= np.float32(1) - eps
+                        else:
+                            c[ci, j] *= np.float32(1) - eps
+                            c[cj, j] *= np.float32(1) + eps
+                    cnt[ci] = cnt[cj] // 2
+                    cnt[cj] -= cnt[ci]
+        self.centroids = c
+
+    def add(self, x: np.ndarray) -> None:
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        a = self._assign(x, self.centroids) if x.shape[0] >= 20 else flat_search_c(self.centroids, x, 1, METRIC_L2, form=1)[1][:, 0]
+        base = self.x.shape[0]
+        for i, l in enumerate(a):
+            self.lists[int(l)].append(base + i)
+        self.x = np.concatenate([self.x, x])
+
+    def search(self, q: np.ndarray, k: int):
+        q = np.ascontiguousarray(q, dtype=np.float32)
+        nq = q.shape[0]
+        D = np.full((nq, k), np.finfo(np.float32).max, np.float32)
+        I = np.full((nq, k), -1, np.int64)
+        probe = flat_search_c(self.centroids, q, self.nprobe, METRIC_L2, form=0)[1]
+        for r in range(nq):
+            ids = np.asarray([i for l in probe[r] if l >= 0 for i in self.lists[int(l)]], dtype=np.int64)
+            if ids.size == 0:
+                continue
+            d, loc = flat_search_c(self.x[ids], q[r:r + 1], min(k, ids.size), METRIC_L2, form=1)
+            order = np.lexsort((ids[loc[0]], d[0]))
+            D[r, : order.size], I[r, : order.size] = d[0][order], ids[loc[0]][order]
+        return D, I

@@ -13,12 +13,13 @@ from .index_build import create_model_embeddings, index_path_for, setup_faiss_in
 from .sparse import BM25Index, SparseIndex, TfidfIndex
 from .pooling import mean_pool_normalize
 from .hybrid import hybrid_fuse
+from .ivf import IndexIVFFlat
 from .retrieval import MultiModelRetrieval, RetrievalSystem
 from .sharded import ShardedFlatIndex, ShardedSparseIndex
 from .container import read_sharded, write_sharded
 
 __all__ = [
-    "FlatIndex", "IndexFlatL2", "IndexFlatIP", "read_index", "write_index",
+    "FlatIndex", "IndexFlatL2", "IndexFlatIP", "IndexIVFFlat", "read_index", "write_index",
     "SparseIndex", "BM25Index", "TfidfIndex", "mean_pool_normalize", "hybrid_fuse",
     "RetrievalSystem", "MultiModelRetrieval", "ShardedFlatIndex", "ShardedSparseIndex", "read_sharded", "write_sharded", "create_model_embeddings", "setup_faiss_index", "index_path_for",
     "METRIC_L2", "METRIC_INNER_PRODUCT", "METRIC_IP", "F32", "F16", "BF16", "F64", "MAX_K", "PrsError", "build", "lib",

@@ -85,6 +85,7 @@ SIGNATURES = {
     "prs_sparse_set_id_offset": (c_int, [c_void_p, c_i64]),
     "prs_hybrid_fuse_device": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_i64, c_i64, ctypes.c_double, ctypes.c_double,
                                        c_int, c_void_p, c_void_p, c_int, c_void_p]),
+    "prs_centroid_update_device": (c_int, [c_void_p, c_i64, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p]),
     "prs_pool_norm": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
 }
 

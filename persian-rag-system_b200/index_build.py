@@ -11,8 +11,9 @@ package:
 Differences, all additive: an `encoder` can be passed instead of loading SentenceTransformer (the
 encoders are unchanged by this project); `storage` selects fp32 (byte-exact faiss file, default)
 or fp16 / bf16 (T64 layout, tcgen05 scan); encoder batches that arrive as CUDA tensors are added
-without a host round trip.  The reference's IVF branch (n >= 1000, approximate, nprobe = 1) is NOT
-reproduced: an exact scan of the same rows is returned instead (out of scope).
+without a host round trip.  The reference's IVF branch (n >= 1000: IndexIVFFlat, nlist = min(100, max(10, n//20)),
+trained on the first 10 000 rows, nprobe = 1) is reproduced by ivf.IndexIVFFlat on the same flat-scan kernels;
+`exact=True` keeps the exact index instead.
 """
 from __future__ import annotations
 
@@ -49,14 +50,27 @@ def _add_rows(index: FlatIndex, rows) -> None:
         index.add(np.asarray(rows).astype("float32"))
 
 
-def setup_faiss_index(embeddings, index_type: str = "flat", storage: str = "fp32", device: Optional[int] = None) -> FlatIndex:
-    """Exact squared-L2 index over `embeddings` ([n, d] numpy or CUDA tensor), added in 1000-row
-    batches like the reference (scripts/phase3_pdf_chunking.py:59-64).  `index_type` is accepted for
-    signature compatibility; every value builds the exact flat index (see module docstring)."""
+def setup_faiss_index(embeddings, index_type: str = "flat", storage: str = "fp32", device: Optional[int] = None, exact: bool = False):
+    """The reference's builder (scripts/phase3_pdf_chunking.py:39-71): a flat squared-L2 index for
+    `index_type == "flat"` or fewer than 1000 embeddings, otherwise IVF-Flat with
+    `nlist = min(100, max(10, n // 20))` trained on the first 10 000 rows (faiss's default nprobe = 1 at search
+    time); rows are added in 1000-row batches (:59-64).  `exact=True` keeps the exact flat index for every size
+    (a superset in recall of the approximate branch the reference silently switches to)."""
     n, d = int(embeddings.shape[0]), int(embeddings.shape[1])
-    print(f"Setting up flat L2 index for {n} embeddings ({storage} rows in HBM)...")
-    index = IndexFlatL2(d, storage=storage, device=device)
-    index.reserve(n)
+    if index_type == "flat" or n < 1000 or exact:
+        print(f"Setting up flat L2 index for {n} embeddings ({storage} rows in HBM)...")
+        index = IndexFlatL2(d, storage=storage, device=device)
+        index.reserve(n)
+    else:
+        from .ivf import IndexIVFFlat
+        nlist = min(100, max(10, n // 20))
+        print(f"Setting up IVF-Flat index for {n} embeddings (nlist={nlist}, nprobe=1, {storage} lists in HBM)...")
+        index = IndexIVFFlat(d, nlist, storage=storage, device=device)
+        print("  Training FAISS index...")
+        training = embeddings[: min(10000, n)]
+        if hasattr(training, "detach"):
+            training = training.detach().float().cpu().numpy()
+        index.train(np.asarray(training).astype("float32"))
     for start in range(0, n, 1000):
         _add_rows(index, embeddings[start:start + 1000])
     print("✓ index resident on the device")

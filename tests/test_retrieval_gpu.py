@@ -273,3 +273,53 @@ def test_create_model_embeddings_writes_the_faiss_file_the_reference_would(P, wo
     idx = P.setup_faiss_index(x, index_type="ivf")
     D, I = idx.search(x[:5], 1)
     assert I[:, 0].tolist() == [0, 1, 2, 3, 4] and np.allclose(D[:, 0], 0.0, atol=1e-6)
+
+
+# ------------------------------------------------------------------ IVF-Flat branch of the reference's builder (§8 f-4)
+def test_ivf_flat_branch_matches_the_restated_faiss_semantics(P):
+    """scripts/phase3_pdf_chunking.py:45-57: >= 1000 embeddings -> IndexIVFFlat(IndexFlatL2(d), d, min(100, max(10, n//20))),
+    trained on the first 10 000 rows, searched with nprobe = 1.  k-means (faiss's permutation-based initialisation,
+    10 Lloyd iterations, float32 row-order centroid sums), list assignment and the probed-list scan are compared
+    with the oracle restatement; every distance computation runs on the flat-scan kernels."""
+    rng = np.random.default_rng(4)
+    d, n = 32, 2400
+    centers = rng.standard_normal((40, d)).astype(np.float32) * 8
+    x = (centers[rng.integers(0, 40, n)] + 0.4 * rng.standard_normal((n, d))).astype(np.float32)
+    q = (x[rng.integers(0, n, 50)] + 0.05 * rng.standard_normal((50, d))).astype(np.float32)
+    idx = P.setup_faiss_index(x, index_type="ivf")
+    assert isinstance(idx, P.IndexIVFFlat) and idx.nlist == min(100, max(10, n // 20)) == 100 and idx.nprobe == 1
+    assert idx.ntotal == n and idx.is_trained and int(idx.list_sizes().sum()) == n
+    ora = O.IVFFlatOracle(d, 100)
+    ora.train(x[:10000])
+    # same permutation, same row-order float32 sums: the centroids agree to rounding wherever no training row sits on a
+    # cluster boundary within fp32 rounding (assignment near-ties may fall on either side in any implementation)
+    same = np.isclose(idx.centroids, ora.centroids, rtol=1e-5, atol=1e-6).all(axis=1)
+    assert same.mean() > 0.9, same.mean()
+    # from identical centroids on: identical lists and identical search results
+    both = P.IndexIVFFlat(d, 100)
+    both.set_centroids(ora.centroids)
+    for s in range(0, n, 1000):
+        both.add(x[s:s + 1000])
+    ora.add(x)
+    assert [sorted(l) for l in ora.lists] == [a.tolist() for a in both._ids]
+    for k in (1, 5, 64):
+        D, I = both.search(q, k)
+        Do, Io = ora.search(q, k)
+        O.check_topk_lists(I, D, Io, Do, rtol=1e-5, atol=1e-6, what=f"ivf k{k}")
+        assert (I == Io).mean() > 0.99
+    # a list with fewer than k rows pads with (FLT_MAX, -1), like faiss's heap
+    small = int(np.argmin(np.where(both.list_sizes() > 0, both.list_sizes(), 10**9)))
+    qs = ora.centroids[small:small + 1]
+    D, I = both.search(qs, 64)
+    nrows = int(both.list_sizes()[small])
+    assert (I[0, :nrows] >= 0).all() and (I[0, nrows:] == -1).all() and (D[0, nrows:] == np.finfo(np.float32).max).all()
+    # the retriever works on top of it unchanged (src/retrieval.py:102 only needs .search / .ntotal)
+    r = P.RetrievalSystem(method="dense", encoder=FakeEncoder({f"q{i}": q[i] for i in range(50)}, d))
+    r.chunks = [{"id": f"c{i}", "text": "t"} for i in range(n)]
+    r.faiss_index, r.is_ready = both, True
+    hits = r.retrieve("q3", top_k=5)
+    assert [c["id"] for c, _ in hits] == [f"c{j}" for j in Io[3, :5] if j >= 0][:len(hits)] or len(hits) == 5
+    # below 1000 rows, or index_type "flat", the builder stays flat; exact=True opts out of the approximate branch
+    assert isinstance(P.setup_faiss_index(x[:999], index_type="ivf"), P.FlatIndex)
+    assert isinstance(P.setup_faiss_index(x, index_type="flat"), P.FlatIndex)
+    assert isinstance(P.setup_faiss_index(x, index_type="ivf", exact=True), P.FlatIndex)
