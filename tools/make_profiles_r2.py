@@ -76,7 +76,11 @@ with open("profiles/r2_scan_kernel_ncu_full.md", "w") as f:
             "(query conversion + scan + grid barrier + merge in this kernel).  Times under ncu are replayed / cold: the bench's CUDA-event time is the number of record.\n\n")
     traffic["fp16_1000000x768_b64_tcgen05"] = full("gpurun_out/r2_scan_b64.ncu-rep", f, "B = 64 (HBM bound): one-launch search.")
     full("gpurun_out/r2_scan_b256.ncu-rep", f, "B = 256 (tensor bound): cluster of 2 CTAs, TMA multicast of the corpus stages; one of the scan launches.")
-    full("gpurun_out/r2_scan_b1024.ncu-rep", f, "B = 1024 (tensor bound): cluster of 4 CTAs, two passes of 512 queries; one of the scan launches.")
+    full("gpurun_out/r2_scan_b1024.ncu-rep", f, "B = 1024 (tensor bound), BEFORE the issue-loop fix: cluster of 4 CTAs, two passes of 512 queries; one of the scan launches.")
+    if os.path.exists("gpurun_out/r3b_scan_b1024.ncu-rep"):
+        full("gpurun_out/r3b_scan_b1024.ncu-rep", f, "B = 1024 AFTER the round-2 changes (elected single-thread issue loop, clusters of 2, cross-CTA bound refresh, "
+             "3-input-max epilogue): one of four passes of 256 queries.  Instructions per launch fell from 320 M (two passes) to 87 M per pass-equivalent; "
+             "the epilogue now WAITS for the MMAs (44 % of its samples at the accumulator barrier): the tensor pipe / TMEM capacity bounds the kernel.")
 with open("profiles/r2_sparse_ncu.md", "w") as f:
     f.write("# ncu --set full of sparse_score_batched_kernel (round 2)\n\n`ncu --set full --import-source on --clock-control none -k regex:sparse_score_batched -s 2 -c 1 "
             "python tools/prof_sparse.py 2000000 1024 throughput` (C4 generator, 2 M docs x 200 k terms, 1 024 queries, k = 10; 4.93 G postings touched = 39.5 GB algorithmic).\n\n")
