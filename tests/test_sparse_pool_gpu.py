@@ -282,6 +282,43 @@ def test_pool_random_vs_torch(P, B, T, H, dtype):
         torch.testing.assert_close(got, want, rtol=1e-5, atol=1e-5)
 
 
+@pytest.mark.parametrize("B,T,H,dtype,kind", [
+    (5, 100, 768, "float16", "left"),        # left-padded batch: the copied row range starts inside the slice
+    (7, 77, 384, "float32", "holes"),        # masked rows between unmasked ones are skipped, not added
+    (4, 64, 512, "bfloat16", "empty"),       # fully masked sequences: zeros, no NaN
+    (1300, 40, 384, "float16", "prefix"),    # B large enough for one CTA per sequence (no token split)
+    (3, 300, 1024, "float32", "prefix"),     # 256 lanes per row (R = 1), slices of 38 tokens
+    (9, 33, 64, "float16", "prefix"),        # 8 lanes per row: 32 rows per pass
+    (2, 9000, 128, "float16", "holes"),      # long sequences
+    (6, 50, 1032, "float32", "prefix"),      # 258 lanes per row: the one-CTA-per-sequence kernel
+    (6, 50, 100, "float16", "prefix"),       # H not a multiple of 8: the one-CTA-per-sequence kernel
+])
+def test_pool_mask_shapes_vs_torch(P, B, T, H, dtype, kind):
+    import torch
+    g = torch.Generator(device="cuda").manual_seed(B * 7 + T + H)
+    h = torch.randn((B, T, H), generator=g, device="cuda").to(getattr(torch, dtype))
+    lens = torch.randint(1, T + 1, (B,), generator=g, device="cuda")
+    ar = torch.arange(T, device="cuda")[None, :]
+    if kind == "prefix":
+        mask = ar < lens[:, None]
+    elif kind == "left":
+        mask = ar >= (T - lens)[:, None]
+    elif kind == "holes":
+        mask = (ar < lens[:, None]) & (torch.rand((B, T), generator=g, device="cuda") < 0.6)
+    else:
+        mask = torch.zeros((B, T), dtype=torch.bool, device="cuda")
+        mask[0, : T // 2] = True
+    mask = mask.to(torch.int64)
+    me = mask.unsqueeze(-1).float()
+    pooled = (h.float() * me).sum(1) / me.sum(1).clamp(min=1e-9)
+    for normalize in (False, True):
+        want = torch.nn.functional.normalize(pooled, p=2, dim=1) if normalize else pooled
+        got = P.mean_pool_normalize(h, mask, normalize)
+        assert not torch.isnan(got).any()
+        torch.testing.assert_close(got, want, rtol=1e-5, atol=1e-5)
+        assert torch.equal(got, P.mean_pool_normalize(h, mask, normalize))       # deterministic
+
+
 def test_pool_then_search_stays_on_device(P):
     """f-3: encoder output -> pool/normalise kernel -> flat search, no host hop in between."""
     import torch
