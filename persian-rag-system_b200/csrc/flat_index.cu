@@ -185,6 +185,7 @@ struct prs_index {
     Workspace* cur = &slot[0];          // workspace of the search being issued (set under mu)
     unsigned next_slot = 0;
     DevBuf hD, hI, hQ, stage;
+    PinnedBuf pQ, pD, pI;                // page-locked staging of small pageable host calls
     ScanTimer timer, timer_prep, timer_merge;
 };
 static thread_local struct prs_xchg* t_xchg = nullptr;   // set by the calling thread for the duration of a sharded search
@@ -494,6 +495,7 @@ void prs_index_free(prs_index* idx) {
         if (w.event) cudaEventDestroy(w.event);
     }
     idx->hD.release(); idx->hI.release(); idx->hQ.release(); idx->stage.release();
+    idx->pQ.release(); idx->pD.release(); idx->pI.release();
     delete idx;
 }
 
@@ -617,11 +619,23 @@ int prs_index_search_host(prs_index* idx, const float* q, int64_t nq, int k, flo
     // transfer of the step) and the merge kernel stores the k results per query straight into the
     // caller's pinned D / I (the device->host transfer); one stream synchronisation ends the call.
     // (The CUDA-core scan re-reads the queries in every CTA, so it keeps the staged copy.)
-    if (idx->path_force != 1 && idx->n > 0 &&
-        (umma_eligible(idx->storage, idx->d, idx->pitch, nq, k) || umma_wide_eligible(idx->storage, idx->pitch, nq, k, idx->n)) &&
-        mapped_host_pointer(q, &dq) && mapped_host_pointer(D, &dD) && mapped_host_pointer(I, &dI)) {
+    const bool zero_copy = idx->path_force != 1 && idx->n > 0 &&
+        (umma_eligible(idx->storage, idx->d, idx->pitch, nq, k) || umma_wide_eligible(idx->storage, idx->pitch, nq, k, idx->n));
+    if (zero_copy && mapped_host_pointer(q, &dq) && mapped_host_pointer(D, &dD) && mapped_host_pointer(I, &dI)) {
         if ((rc = search_device_impl(idx, dq, PRS_F32, nq, k, (float*)dD, (int64_t*)dI, 0))) return rc;
         PRS_CUDA(cudaStreamSynchronize(0));
+        return 0;
+    }
+    // Pageable caller buffers (what `index.search(numpy)` passes), small batches: the same zero-copy search through the
+    // index's own page-locked buffers -- one host memcpy in, one out -- instead of three staged driver copies.
+    if (zero_copy && (size_t)nq * idx->d * 4 <= (size_t)(4u << 20) && (size_t)nq * k * 8 <= (size_t)(4u << 20)) {
+        const size_t qb = (size_t)nq * idx->d * 4, db = (size_t)nq * k * 4, ib = (size_t)nq * k * 8;
+        if ((rc = idx->pQ.ensure(qb)) || (rc = idx->pD.ensure(db)) || (rc = idx->pI.ensure(ib))) return rc;
+        memcpy(idx->pQ.p, q, qb);
+        if ((rc = search_device_impl(idx, idx->pQ.dp, PRS_F32, nq, k, (float*)idx->pD.dp, (int64_t*)idx->pI.dp, 0))) return rc;
+        PRS_CUDA(cudaStreamSynchronize(0));
+        memcpy(D, idx->pD.p, db);
+        memcpy(I, idx->pI.p, ib);
         return 0;
     }
     {

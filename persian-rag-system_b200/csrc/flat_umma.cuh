@@ -59,7 +59,7 @@ struct UmmaParams {
     int pitch, nq, k, l2, stages, is_bf16, kbs;   // kbs: k-blocks per pipeline stage
     int nbuf;               // accumulator buffers in TMEM: 2 when pitch <= 512, else 1
     int reboot;             // mode 0: republish the CTA's running best and refresh the cross-CTA bound at tiles 1, 3, 15, 63, ...
-    int dbg;                // experiments only (PRS_UMMA_DEBUG): 1 no bootstrap+no inserts, 2 epilogue releases without reading, 4 no MMA
+    int dbg;                // experiments only (PRS_UMMA_DEBUG): 1 no bootstrap+no inserts, 2 epilogue releases without reading, 16 no corpus copies
     int nq_total, q0;
     u64* cand;              // [grid][nq_total][k]
     int* cand_cnt;          // [grid][nq_total]
@@ -430,6 +430,11 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) flat_scan_umma_kernel(const U
                 const unsigned char* src = p.x + (size_t)(NB * t) * blk_bytes;
                 for (int ks = 0; ks < kstages; ++ks) {
                     mbar_wait(&empty[s], ph ^ 1u);
+                    if (UMMA_DBG(p) & 16) {                     // experiment: no copies at all (what do MMA + epilogue cost alone?)
+                        mbar_arrive_expect_tx(&full[s], 0u);
+                        if (++s == p.stages) { s = 0; ph ^= 1u; }
+                        continue;
+                    }
                     mbar_arrive_expect_tx(&full[s], (uint32_t)(p.kbs * nblk) * KBLOCK_BYTES);
                     unsigned char* dst = ring + (size_t)s * STAGE_BYTES;
                     int c = 0;
@@ -552,9 +557,14 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) flat_scan_umma_kernel(const U
         if (collect) { boot_done = true; thr = qvalid ? __ldg(p.tau + qglobal) : INFINITY; }
         if (p.mode == 2) boot_done = true;
         // thread-private top-k of this CTA for this query: 16 sorted keys in registers (key 0 = empty)
+        // The list is RIGHT-ALIGNED: slots [0, 16 - k) hold an all-ones sentinel no key can displace, the k live slots
+        // follow, so the k-th best is always top[15] -- a fixed register.  (With the list left-aligned the k-dependent
+        // reads made the compiler keep all of top[] in local memory: 16 loads + 16 stores + a chain of 16 predicated
+        // loads per insertion, ~1 500 cycles in a warp that has its scheduler to itself.)
         u64 top[UMMA_MAX_K];
 #pragma unroll
-        for (int j = 0; j < UMMA_MAX_K; ++j) top[j] = 0ull;
+        for (int j = 0; j < UMMA_MAX_K; ++j) top[j] = (j < UMMA_MAX_K - p.k) ? ~0ull : 0ull;
+        uint32_t best_ord = 0u;                      // ord() of this thread's best score so far (0 = none yet)
 
         // Bootstrap bound.  Every CTA publishes, per query, the best score of its FIRST tile; groups
         // of 4 CTAs are folded to their maximum and the k-th largest group maximum is taken.  Those
@@ -577,9 +587,9 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) flat_scan_umma_kernel(const U
                 }
                 gm[g] = max(max(a[0], a[1]), max(a[2], a[3]));
             }
-            uint32_t best[UMMA_MAX_K];
+            uint32_t best[UMMA_MAX_K];                      // right-aligned like top[]: the k-th largest ends up in best[15]
 #pragma unroll
-            for (int j = 0; j < UMMA_MAX_K; ++j) best[j] = 0u;
+            for (int j = 0; j < UMMA_MAX_K; ++j) best[j] = (j < UMMA_MAX_K - p.k) ? 0xFFFFFFFFu : 0u;
 #pragma unroll
             for (int g = 0; g < NGRP; ++g) {
                 uint32_t v = gm[g];
@@ -590,9 +600,7 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) flat_scan_umma_kernel(const U
                     best[j] = hi;
                 }
             }
-            uint32_t kth = 0u;
-#pragma unroll
-            for (int j = 0; j < UMMA_MAX_K; ++j) kth = (j == p.k - 1) ? best[j] : kth;
+            const uint32_t kth = best[UMMA_MAX_K - 1];
             if (kth) thr = fmaxf(thr, ord2f(kth));
             boot_done = published >= 4 * G;
         };
@@ -634,18 +642,28 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) flat_scan_umma_kernel(const U
                 if (!qvalid) hm[hh] = 0u;
             }
         };
-        // rare path: a score reached the threshold.  One copy of the code for all columns.
+        // rare path: a score reached the threshold.  One copy of the code for all columns, written for instruction-level
+        // parallelism: the epilogue warp is alone on its scheduler, so a dependent chain costs its full latency per link.
         auto insert_hits = [&](const uint32_t (&v)[BLK_ROWS], const uint32_t (&hm)[2], long long rbase) {
 #pragma unroll 1
             for (int hh = 0; hh < 2; ++hh) {
-                uint32_t mask = hm[hh];
+                uint32_t mask = hh ? hm[1] : hm[0];
 #pragma unroll 1
                 while (mask) {
                     const int j = __ffs(mask) - 1 + hh * 32;
                     mask &= mask - 1;
-                    uint32_t bits = 0u;
+                    // v[j]: a six-level select tree (63 selects, depth 6) instead of a 64-long dependent chain
+                    uint32_t s5[32], s4[16], s3[8], s2[4];
 #pragma unroll
-                    for (int jj = 0; jj < BLK_ROWS; ++jj) bits = (jj == j) ? v[jj] : bits;
+                    for (int i = 0; i < 32; ++i) s5[i] = (j & 1) ? v[2 * i + 1] : v[2 * i];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) s4[i] = (j & 2) ? s5[2 * i + 1] : s5[2 * i];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) s3[i] = (j & 4) ? s4[2 * i + 1] : s4[2 * i];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) s2[i] = (j & 8) ? s3[2 * i + 1] : s3[2 * i];
+                    const uint32_t s1a = (j & 16) ? s2[1] : s2[0], s1b = (j & 16) ? s2[3] : s2[2];
+                    const uint32_t bits = (j & 32) ? s1b : s1a;
                     const float sc = __uint_as_float(bits);
                     if (collect) {
                         if (ccount == p.coll_cap) {
@@ -661,19 +679,22 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) flat_scan_umma_kernel(const U
                         }
                         if (sc >= thr) cslice[ccount++] = make_key<PRS_TIE_LOW_ID>(sc, (uint32_t)(rbase + j));
                     } else if (sc >= thr) {
-                        // branch-free sorted insertion (descending); the key that falls off the end is dropped
-                        u64 key = make_key<PRS_TIE_LOW_ID>(sc, (uint32_t)(rbase + j));
+                        // sorted insertion (descending), every slot on its own: slots above the key keep their value, the
+                        // first slot below it takes the key, the rest take their upper neighbour (the last one falls off)
+                        const u64 key = make_key<PRS_TIE_LOW_ID>(sc, (uint32_t)(rbase + j));
+                        bool below[UMMA_MAX_K];
+#pragma unroll
+                        for (int i = 0; i < UMMA_MAX_K; ++i) below[i] = key > top[i];
+                        u64 nt[UMMA_MAX_K];
 #pragma unroll
                         for (int i = 0; i < UMMA_MAX_K; ++i) {
-                            const bool up = key > top[i];
-                            const u64 lo = up ? top[i] : key;
-                            top[i] = up ? key : top[i];
-                            key = lo;
+                            const u64 shifted = (i > 0 && below[i - 1]) ? top[i > 0 ? i - 1 : 0] : key;
+                            nt[i] = below[i] ? shifted : top[i];
                         }
-                        u64 kth = 0ull;
 #pragma unroll
-                        for (int i = 0; i < UMMA_MAX_K; ++i) kth = (i == p.k - 1) ? top[i] : kth;
-                        if (kth) thr = fmaxf(thr, key_score(kth));
+                        for (int i = 0; i < UMMA_MAX_K; ++i) top[i] = nt[i];
+                        best_ord = max(best_ord, (uint32_t)(key >> 32));
+                        if (top[UMMA_MAX_K - 1]) thr = fmaxf(thr, key_score(top[UMMA_MAX_K - 1]));
                     }
                 }
             }
@@ -753,7 +774,7 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) flat_scan_umma_kernel(const U
                 // meets only a handful of admissible scores, instead of ~k ln(rows / k) per thread when every CTA has
                 // to find its threshold alone (large batches were bound by exactly those insertions: 35 % of the
                 // epilogue's instructions and warp divergence on 4 of 5 tiles).
-                if (top[0]) boot[(size_t)part * UMMA_M + m] = (uint32_t)(top[0] >> 32);
+                if (best_ord) boot[(size_t)part * UMMA_M + m] = best_ord;
                 refresh_boot();
             } else if (!boot_done && (it & (it + 1)) == 0) {
                 refresh_boot();          // first-tile maxima still arriving: it = 1, 3, 7, 15, ...
@@ -778,7 +799,8 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) flat_scan_umma_kernel(const U
             int n = 0;
 #pragma unroll
             for (int j = 0; j < UMMA_MAX_K; ++j) {
-                if (j < p.k) { p.cand[o * p.k + j] = top[j]; n += top[j] != 0ull; }   // all k slots, 0 = empty (sorted: empties last)
+                const int jj = j - (UMMA_MAX_K - p.k);                                 // the live slots are the last k
+                if (jj >= 0) { p.cand[o * p.k + jj] = top[j]; n += top[j] != 0ull; }    // all k slots, 0 = empty (sorted: empties last)
             }
             p.cand_cnt[o] = n;
         }

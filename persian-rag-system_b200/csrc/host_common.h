@@ -67,6 +67,24 @@ struct DevBuf {
     void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
 };
 
+// grow-only page-locked host buffer the device can address (zero-copy staging of small host calls)
+struct PinnedBuf {
+    void* p = nullptr;       // host address
+    void* dp = nullptr;      // the same memory as the device sees it
+    size_t bytes = 0;
+    int ensure(size_t need) {
+        if (need <= bytes) return 0;
+        release();
+        const size_t want = need + need / 2;
+        if (cudaHostAlloc(&p, want, cudaHostAllocMapped) != cudaSuccess || cudaHostGetDevicePointer(&dp, p, 0) != cudaSuccess) {
+            cudaGetLastError(); release(); set_error("cudaHostAlloc(%zu) failed", want); return PRS_ENOMEM;
+        }
+        bytes = want;
+        return 0;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; dp = nullptr; bytes = 0; }
+};
+
 // bench instrumentation: brackets the dominant (scan) kernel launches with CUDA events on the
 // launching stream; collect() synchronises them and returns the summed device time.
 struct ScanTimer {
