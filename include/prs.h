@@ -99,8 +99,9 @@ int prs_index_last_path(const prs_index* idx);
  * and the merge run as ONE cooperative kernel -- the epilogue threads convert their own query rows, a grid barrier
  * replaces the kernel boundaries, and the CTAs merge the queries among themselves.  (Host-mapped or peer-resident
  * queries keep the preparation kernel, which reads them exactly once.)  0 restores the three-kernel sequence (A/B
- * measurements).  Row-sharded searches keep the three kernels by default; 2 makes them push their lists to the peers in the
- * scan kernel's tail and finish with one small wait-and-merge kernel (correct, measured slightly slower at N = 2).
+ * measurements).  Row-sharded searches are two launches by default (the scan prepares its own queries, the merge + exchange
+ * kernel follows); 2 makes them push their lists to the peers in the scan kernel's tail and finish with one small
+ * wait-and-merge kernel (correct, measured slightly slower at N = 2); 3 asks for the two-launch form on an unsharded index.
  * prs_index_last_fused: 1 if the last search was one launch. */
 int prs_index_set_fused(prs_index* idx, int enable);
 int prs_index_last_fused(const prs_index* idx);

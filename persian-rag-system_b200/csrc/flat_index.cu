@@ -275,7 +275,15 @@ static int launch_merge(prs_index* idx, int parts, long long nq, int k, int out_
     // 16-bit storage + L2 (tcgen05 scan, expanded form): the merge recomputes the selected rows' distances in
     // the direct form from the stored rows and the 16-bit queries the prep kernel left behind
     Rerank rr{nullptr, nullptr, nullptr, 0, idx->d, idx->pitch, idx->storage == PRS_BF16 ? 1 : 0};
-    if (out_mode == 2 && idx->l2_rerank) { rr.x = (const unsigned char*)idx->x; rr.qlow = (const uint16_t*)idx->cur->umma.qlow.p; }
+    UmmaState& us = idx->cur->umma;
+    if (out_mode == 2 && idx->l2_rerank) {
+        rr.x = (const unsigned char*)idx->x;
+        if (us.prep_in_scan) { rr.q = us.q_orig; rr.qdtype = us.q_dtype; }      // no 16-bit image: round the original queries on the fly
+        else rr.qlow = (const uint16_t*)us.qlow.p;
+    }
+    uint32_t* zero = us.prep_in_scan ? (uint32_t*)us.boot.p : nullptr;
+    const long long zero_words = us.prep_in_scan ? us.zero_words : 0;
+    us.prep_in_scan = false;                                                      // consumed by this merge
     if (t_xchg) {
         prs_xchg* x = t_xchg;
         ++x->gen;
@@ -284,7 +292,7 @@ static int launch_merge(prs_index* idx, int parts, long long nq, int k, int out_
         merge_xchg_kernel<<<(unsigned)nq, MERGE_THREADS, smem, st>>>((const u64*)idx->cur->cand.p, parts,
                                                                     (int)nq, k, sortn, out_mode, qnorm, idx->id_offset,
                                                                     idx->metric == PRS_METRIC_IP ? 1 : 0, rr, x->view, x->gen,
-                                                                    x->timeout_ns, D, (long long*)I, x->d_status);
+                                                                    x->timeout_ns, D, (long long*)I, x->d_status, zero, zero_words);
         PRS_LAUNCH_CHECK();
         PRS_CUDA(cudaEventRecord(x->event, st));
         x->used = true;
@@ -293,7 +301,7 @@ static int launch_merge(prs_index* idx, int parts, long long nq, int k, int out_
     PRS_CUDA(cudaFuncSetAttribute(merge_cand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     merge_cand_kernel<<<(unsigned)nq, MERGE_THREADS, smem, st>>>((const u64*)idx->cur->cand.p, parts,
                                                                 (int)nq, k, sortn, out_mode, qnorm, idx->id_offset, rr, D,
-                                                                (long long*)I);
+                                                                (long long*)I, zero, zero_words);
     PRS_LAUNCH_CHECK();
     return 0;
 }
@@ -369,6 +377,7 @@ static int search_device_impl(prs_index* idx, const void* q, int qdtype, long lo
     // stream after the previous one (same-stream searches are ordered already)
     prs_index::Workspace* ws = &idx->slot[idx->next_slot++ % prs_index::NSLOT];
     idx->cur = ws;
+    ws->umma.prep_in_scan = false;
     if (!ws->event) PRS_CUDA(cudaEventCreateWithFlags(&ws->event, cudaEventDisableTiming));
     if (ws->used && ws->stream != st) PRS_CUDA(cudaStreamWaitEvent(st, ws->event, 0));
     struct Rec { prs_index::Workspace* w; cudaStream_t s; ~Rec() { cudaEventRecord(w->event, s); w->stream = s; w->used = true; } } rec{ws, st};
@@ -414,10 +423,12 @@ static int search_device_impl(prs_index* idx, const void* q, int qdtype, long lo
         int parts = 0;
         const int out_mode = idx->metric == PRS_METRIC_L2 ? 2 : 0;
         UmmaTail tail;
-        // row-sharded searches keep the three-kernel sequence unless fuse == 2: measured at N = 2 (1M x 768, B = 64) the
-        // push-in-the-tail variant is 0.1855 ms per step against 0.1810 ms (the scan kernel's tail then pays the NVLink
-        // store acknowledgements before it can release its flags)
-        tail.enable = t_xchg ? idx->fuse == 2 : idx->fuse != 0;
+        // row-sharded searches are TWO launches -- the scan (which prepares its own queries) and the merge + exchange kernel --
+        // unless fuse == 2: measured at N = 2 (1M x 768, B = 64) the push-in-the-tail variant is 0.1855 ms per step against
+        // 0.1810 ms (the scan kernel's tail then pays the NVLink store acknowledgements before it can release its flags).
+        // fuse == 3 asks for the same two launches on an unsharded index (tests)
+        tail.enable = t_xchg ? idx->fuse == 2 : (idx->fuse == 1 || idx->fuse == 2);
+        tail.prep_in_scan = idx->fuse != 0;             // row-sharded default: scan (with its own query preparation) + merge/exchange
         tail.out_mode = out_mode; tail.largest = idx->metric == PRS_METRIC_IP ? 1 : 0; tail.id_offset = idx->id_offset;
         tail.D = D; tail.I = (long long*)I; tail.device = idx->device;
         tail.rerank_x = (out_mode == 2 && idx->l2_rerank) ? (const unsigned char*)idx->x : nullptr;
@@ -557,7 +568,7 @@ int prs_index_set_path(prs_index* idx, int path) {
 
 int prs_index_set_fused(prs_index* idx, int enable) {
     if (!idx) { set_error("null index"); return PRS_EINVAL; }
-    idx->fuse = enable < 0 ? 0 : (enable > 2 ? 2 : enable);
+    idx->fuse = enable < 0 ? 0 : (enable > 3 ? 3 : enable);
     return 0;
 }
 int prs_index_last_fused(const prs_index* idx) { return idx ? idx->last_fused : -1; }

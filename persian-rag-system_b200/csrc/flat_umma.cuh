@@ -861,6 +861,12 @@ __global__ void __launch_bounds__(128) prep_queries_kernel(const TQ* __restrict_
 struct UmmaState {
     DevBuf qlow, boot, tau, gmax, coll, coll_cnt, gbar;
     bool boot_clean = false;      // the bootstrap words are all zero (left so by the one-launch search's tail)
+    // the last search converted the queries inside the scan kernel and left the merge to a separate kernel: that kernel
+    // re-ranks from the ORIGINAL queries (there is no qlow image) and zeroes `zero_words` bootstrap words for the next search
+    bool prep_in_scan = false;
+    const void* q_orig = nullptr;
+    int q_dtype = 0;
+    long long zero_words = 0;
     void invalidate() {}
     void release() { qlow.release(); boot.release(); tau.release(); gmax.release(); coll.release(); coll_cnt.release(); gbar.release(); }
 };
@@ -876,6 +882,7 @@ struct UmmaTail {
     prs_xchg* xchg = nullptr;                      // row-sharded search: the tail pushes, xchg_pull_kernel finishes
     ScanTimer* timer_merge = nullptr;
     int device = 0;
+    bool prep_in_scan = false;                     // without `enable`: the scan still converts the queries itself (two launches)
 };
 
 static inline bool umma_eligible(int storage, int d, int pitch, long long nq, int k) {
@@ -1082,8 +1089,12 @@ static inline int search_umma(UmmaState& st, const void* x, const float* xnorm, 
     int rc;
     if (fused_out) *fused_out = false;
     if ((rc = umma_plan(n, pitch, nq, sm_count, pl))) return rc;
-    const bool fuse_merge = tail && tail->enable && pl.CL == 1 && nq <= pl.qblock;
-    const bool fuse_prep = fuse_merge && d % 8 == 0 && ((uintptr_t)q & 15u) == 0 && umma_local_device_ptr(q, tail->device);
+    const bool one_pass = tail && pl.CL == 1 && nq <= pl.qblock;
+    const bool fuse_merge = one_pass && tail->enable;
+    const bool fuse_prep = one_pass && (tail->enable || tail->prep_in_scan) && d % 8 == 0 && ((uintptr_t)q & 15u) == 0 &&
+                           umma_local_device_ptr(q, tail->device);
+    st.prep_in_scan = fuse_prep && !fuse_merge;
+    st.q_orig = q; st.q_dtype = qdtype; st.zero_words = 0;
     if (!fuse_prep) {
         if ((rc = umma_prep(st, pl, q, qdtype, nq, d, pitch, storage, qnorm, stream, timer_prep))) return rc;
     } else {
@@ -1096,6 +1107,14 @@ static inline int search_umma(UmmaState& st, const void* x, const float* xnorm, 
     if ((rc = cand_cnt.ensure((size_t)pl.n_clusters * nq * 4))) return rc;
     UmmaParams fp;
     const UmmaParams* fpp = nullptr;
+    if (fuse_prep && !fuse_merge) {
+        // two launches: the scan prepares its queries, a separate merge (+ exchange) kernel follows and clears the bootstrap words
+        fp.q = q; fp.qdtype = qdtype; fp.d = d; fp.fuse_prep = 1; fp.fuse_merge = 0; fp.qnorm = qnorm;
+        fp.gbar = nullptr; fp.sortn = 0; fp.out_mode = 0; fp.largest = 1; fp.id_offset = 0; fp.D = nullptr; fp.I = nullptr;
+        fp.rr = Rerank{}; fp.status = nullptr; fp.use_xchg = 0; fp.xgen = 0;
+        fpp = &fp;
+        st.zero_words = (long long)(st.boot.bytes / 4);
+    }
     if (fuse_merge) {
         if (!st.gbar.p) {
             if ((rc = st.gbar.ensure(256))) return rc;
@@ -1120,7 +1139,7 @@ static inline int search_umma(UmmaState& st, const void* x, const float* xnorm, 
     }
     if ((rc = umma_scan(st, pl, x, xnorm, n, pitch, storage, metric, nq, k, 1, 0, (u64*)cand.p, (int*)cand_cnt.p, nullptr, nullptr, nullptr, 0,
                         stream, timer, nullptr, 0, fpp))) return rc;
-    st.boot_clean = fuse_merge;                                  // the fused tail leaves the bootstrap words zeroed
+    st.boot_clean = fuse_merge || st.prep_in_scan;               // the fused tail / the separate merge kernel leaves the bootstrap words zeroed
     if (fuse_merge && tail->xchg) {
         prs_xchg* xc = tail->xchg;
         const int sortn2 = next_pow2(std::max(k + XCHG_PULL_THREADS, xc->G * k));

@@ -199,8 +199,10 @@ __device__ __forceinline__ void merge_query(const u64* __restrict__ cand, int pa
 __global__ void __launch_bounds__(MERGE_THREADS) merge_cand_kernel(
     const u64* __restrict__ cand, int parts, int nq, int k, int sortn,
     int out_mode, const float* __restrict__ qnorm, long long id_offset, const Rerank rr, float* __restrict__ D,
-    long long* __restrict__ I) {
+    long long* __restrict__ I, uint32_t* __restrict__ zero, long long zero_words) {
     extern __shared__ __align__(16) unsigned char msm[];
+    // the scan kernel's bootstrap words, cleared for the next search when no preparation kernel will do it
+    for (long long i = (long long)blockIdx.x * MERGE_THREADS + threadIdx.x; i < zero_words; i += (long long)gridDim.x * MERGE_THREADS) zero[i] = 0u;
     merge_query<MERGE_THREADS>(cand, parts, nq, k, sortn, out_mode, qnorm, id_offset, rr, D, I, (int)blockIdx.x, (int)threadIdx.x, msm);
 }
 

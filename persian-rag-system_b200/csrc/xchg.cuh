@@ -223,8 +223,10 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_xchg_kernel(
     const u64* __restrict__ cand, int parts, int nq, int k, int sortn,
     int out_mode, const float* __restrict__ qnorm, long long id_offset, int largest, const Rerank rr,
     const XchgView xv, uint32_t gen, unsigned long long timeout_ns, float* __restrict__ D, long long* __restrict__ I,
-    volatile int* status) {
+    volatile int* status, uint32_t* __restrict__ zero, long long zero_words) {
     extern __shared__ __align__(16) unsigned char msm[];
+    // the scan kernel's bootstrap words, cleared for the next search when no preparation kernel will do it
+    for (long long i = (long long)blockIdx.x * MERGE_THREADS + threadIdx.x; i < zero_words; i += (long long)gridDim.x * MERGE_THREADS) zero[i] = 0u;
     merge_xchg_query<MERGE_THREADS>(cand, parts, nq, k, sortn, out_mode, qnorm, id_offset, largest, rr, xv, gen, timeout_ns, D, I, status,
                                     (int)blockIdx.x, (int)threadIdx.x, msm);
 }

@@ -125,7 +125,8 @@ class FlatIndex:
 
     def set_fused(self, enable: bool) -> None:
         """One-launch search (prep + scan + merge in one cooperative kernel, default on) vs the three-kernel sequence.
-        `enable=2` also fuses row-sharded searches (push in the scan kernel's tail + a small pull kernel)."""
+        `enable=2` also fuses row-sharded searches (push in the scan kernel's tail + a small pull kernel); `enable=3`:
+        two launches (the scan prepares its own queries, a separate merge kernel follows -- the row-sharded default)."""
         self._single_only("set_fused")
         check(self._L.prs_index_set_fused(self._h, int(enable)))
 

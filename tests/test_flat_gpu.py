@@ -458,6 +458,9 @@ def test_one_launch_search_equals_three_kernel_sequence(P):
         three = P.FlatIndex(d, metric, storage)
         three.add(x)
         three.set_fused(False)
+        two = P.FlatIndex(d, metric, storage)                      # scan with its own query preparation + separate merge kernel
+        two.add(x)
+        two.set_fused(3)
         for rep in range(25):
             qh = rng.standard_normal((nq, d)).astype(np.float32)
             q = torch.from_numpy(qh).to(dev)
@@ -470,6 +473,8 @@ def test_one_launch_search_equals_three_kernel_sequence(P):
             assert one.last_path == "tcgen05" and not three.last_fused
             assert one.last_fused                                  # (d % 8 != 0 keeps the preparation kernel, the merge is still fused)
             assert torch.equal(I, Ir) and torch.equal(D, Dr), (n, d, nq, k, storage, metric, rep)
+            D2, I2 = two.search(q, k)
+            assert not two.last_fused and torch.equal(I2, Ir) and torch.equal(D2, Dr), ("two launches", n, d, nq, k, storage, metric, rep)
         # numpy (pageable host) queries take the staged copy and the same kernels
         D, I = one.search(qh, k)
         Dr, Ir = three.search(qh, k)

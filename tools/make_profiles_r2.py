@@ -67,20 +67,27 @@ def full(rep, f, note):
     return tr
 
 
-launches("gpurun_out/r2_launches.csv", "profiles/r2_launches_summary.md",
-         "ncu launch list (round 2): `python bench.py --steps 3 --warmup 2 --extras none --capacity-rows 0 --no-sweep --no-cpu-baseline`")
+launches("gpurun_out/r5_launches.csv", "profiles/r2_launches_summary.md",
+         "ncu launch list (round 2, final code): `python bench.py --steps 3 --warmup 3 --extras none --capacity-rows 0 --no-sweep --no-cpu-baseline`")
 traffic = {}
 with open("profiles/r2_scan_kernel_ncu_full.md", "w") as f:
-    f.write("# ncu --set full of the scan kernel (round 2)\n\n`ncu --set full --clock-control none -k regex:flat_scan_umma -s 6 -c 1` on `python bench.py --steps 3 --warmup 2 "
-            "--extras none --capacity-rows 0 --no-sweep --no-cpu-baseline [--batch B]` (1M x 768 fp16, k=10, IP).  B = 64 is the one-launch search "
-            "(query conversion + scan + grid barrier + merge in this kernel).  Times under ncu are replayed / cold: the bench's CUDA-event time is the number of record.\n\n")
-    traffic["fp16_1000000x768_b64_tcgen05"] = full("gpurun_out/r2_scan_b64.ncu-rep", f, "B = 64 (HBM bound): one-launch search.")
-    full("gpurun_out/r2_scan_b256.ncu-rep", f, "B = 256 (tensor bound): cluster of 2 CTAs, TMA multicast of the corpus stages; one of the scan launches.")
-    full("gpurun_out/r2_scan_b1024.ncu-rep", f, "B = 1024 (tensor bound), BEFORE the issue-loop fix: cluster of 4 CTAs, two passes of 512 queries; one of the scan launches.")
-    if os.path.exists("gpurun_out/r3b_scan_b1024.ncu-rep"):
-        full("gpurun_out/r3b_scan_b1024.ncu-rep", f, "B = 1024 AFTER the round-2 changes (elected single-thread issue loop, clusters of 2, cross-CTA bound refresh, "
-             "3-input-max epilogue): one of four passes of 256 queries.  Instructions per launch fell from 320 M (two passes) to 87 M per pass-equivalent; "
-             "the epilogue now WAITS for the MMAs (44 % of its samples at the accumulator barrier): the tensor pipe / TMEM capacity bounds the kernel.")
+    f.write("# ncu --set full of the scan kernel (round 2, final code)\n\n`ncu --set full --clock-control none --import-source on -k regex:flat_scan_umma -s 6 -c 1` on `python bench.py --steps 3 --warmup 3 "
+            "--extras none --capacity-rows 0 --no-sweep --no-cpu-baseline [--batch B]` (1M x 768 fp16, k=10, IP; `tools/gpu_round2.sh`).  B = 64 is the one-launch search "
+            "(query conversion + scan + grid barrier + merge in this kernel).  Times under ncu are replayed / cold and at ncu's clocks: the bench's CUDA-event time is the number of record.\n\n")
+    traffic["fp16_1000000x768_b64_tcgen05"] = full("gpurun_out/r5_scan_b64.ncu-rep", f, "B = 64 (HBM bound): one-launch search.")
+    full("gpurun_out/r5_scan_b256.ncu-rep", f, "B = 256 (tensor bound): clusters of 2 CTAs (TMA multicast of the corpus stages), 128-row tiles, one accumulator buffer; the whole batch is one launch.")
+    full("gpurun_out/r5_scan_b1024.ncu-rep", f, "B = 1024 (tensor bound): one of four passes of 256 queries, same configuration.  Per-thread top-k lists are in registers now "
+         "(launch__registers 202, no local memory): the first capture of this round (`r3b`, kept below) had them in local memory.")
+    f.write("\n---\n\n# Earlier captures of this round (history)\n\n")
+    for rep, note in (("gpurun_out/r2_scan_b1024.ncu-rep", "B = 1024 BEFORE the MMA issue-loop fix: cluster of 4 CTAs, two passes of 512 queries (tensor pipe 34-38 % busy)."),
+                      ("gpurun_out/r3b_scan_b1024.ncu-rep", "B = 1024 after the issue-loop fix, clusters of 2, bound refresh, 3-input-max epilogue, BEFORE the register-resident lists.")):
+        if os.path.exists(rep):
+            full(rep, f, note)
+with open("profiles/r2_pool_ncu.md", "w") as f:
+    f.write("# ncu --set full of pool_norm_cluster_kernel (round 2, rewritten kernel)\n\n`ncu --set full --import-source on --clock-control none -k regex:pool_norm_cluster -s 3 -c 1 "
+            "python tools/prof_pool.py 256 512 768 float16 full` (B = 256 sequences x 512 tokens x 768 fp16, all tokens unmasked: 201 MB).  "
+            "CUDA-event timings of the same shape (old vs new kernel, fp16 / fp32, ragged masks, other shapes): `r2_pool_experiments.log`.\n\n")
+    full("gpurun_out/r5_pool.ncu-rep", f, "Token-slice clusters (S = 2 for B = 256), 3-stage bulk-copy ring of 12 KB stages, 4 CTAs per SM.")
 with open("profiles/r2_sparse_ncu.md", "w") as f:
     f.write("# ncu --set full of sparse_score_batched_kernel (round 2)\n\n`ncu --set full --import-source on --clock-control none -k regex:sparse_score_batched -s 2 -c 1 "
             "python tools/prof_sparse.py 2000000 1024 throughput` (C4 generator, 2 M docs x 200 k terms, 1 024 queries, k = 10; 4.93 G postings touched = 39.5 GB algorithmic).\n\n")
