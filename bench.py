@@ -471,7 +471,7 @@ def run_b200(a):
             idx.search(qn[s], a.k)
         tp = (time.perf_counter() - t0) / a.steps
         e2e_pageable = {"value": a.batch / tp, "unit": "queries/s", "ms_per_step": tp * 1e3,
-                        "api": "FlatIndex.search(numpy float32 [B, d]) -> numpy (D, I): pageable host memory, staged copies, outputs allocated per call"}
+                        "api": "FlatIndex.search(numpy float32 [B, d]) -> numpy (D, I): pageable host memory (one host memcpy into the index's page-locked buffer, zero-copy from there), outputs allocated per call"}
     last_I = Ih.numpy().copy()
     last_D = Dh.numpy().copy()
     # the host-buffer result of the last step must equal the device-resident search of the same batch

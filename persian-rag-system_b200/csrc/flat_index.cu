@@ -333,6 +333,9 @@ static int search_simt(prs_index* idx, const float* qf, int q_stride, long long 
         const int tile_rows = tile_rows_for(R0);
         const long long n_tiles = (idx->n + tile_rows - 1) / tile_rows;
         grid = (int)std::min<long long>(idx->sm_count, n_tiles);
+        // a corpus of a few tiles (<= 256 KB: the reference's own indices hold 125-500 rows) goes through ONE CTA, which then
+        // writes D / I itself: one launch instead of scan + merge (latency is all that matters at this size)
+        if (!t_xchg && (long long)idx->n * row_bytes <= 256 * 1024) grid = 1;
     }
     if ((rc = idx->cur->lists.ensure((size_t)grid * SIMT_NW * qb_max * cap * 8))) return rc;
     if ((rc = idx->cur->cand.ensure((size_t)grid * nq * k * 8))) return rc;
@@ -357,12 +360,15 @@ static int search_simt(prs_index* idx, const float* qf, int q_stride, long long 
         p.stages = stages;
         p.lists = (u64*)idx->cur->lists.p; p.cand = (u64*)idx->cur->cand.p; p.cand_cnt = (int*)idx->cur->cand_cnt.p;
         p.nq_total = (int)nq; p.q0 = (int)done; p.sortn = sortn;
+        p.D = D; p.I = (long long*)I; p.id_offset = idx->id_offset; p.out_mode = idx->metric == PRS_METRIC_L2 ? 1 : 0;
+        p.direct = (grid == 1 && !t_xchg) ? 1 : 0;     // one CTA holds the whole (tiny) index: it writes D / I itself
         const size_t smem = 512 + qbytes + (size_t)stages * tile_bytes;
         idx->timer.begin(st);
         if ((rc = launch_simt(idx->storage, idx->metric == PRS_METRIC_L2, QB, R, p, grid, smem, st))) return rc;
         idx->timer.end(st);
         done += QB;
     }
+    if (grid == 1 && !t_xchg) return 0;                // the scan kernel wrote D / I (SimtParams::direct)
     return launch_merge(idx, grid, nq, k, idx->metric == PRS_METRIC_L2 ? 1 : 0, nullptr, D, I, st);
 }
 
@@ -644,6 +650,32 @@ int prs_index_search_host(prs_index* idx, const float* q, int64_t nq, int k, flo
         if ((rc = idx->pQ.ensure(qb)) || (rc = idx->pD.ensure(db)) || (rc = idx->pI.ensure(ib))) return rc;
         memcpy(idx->pQ.p, q, qb);
         if ((rc = search_device_impl(idx, idx->pQ.dp, PRS_F32, nq, k, (float*)idx->pD.dp, (int64_t*)idx->pI.dp, 0))) return rc;
+        PRS_CUDA(cudaStreamSynchronize(0));
+        memcpy(D, idx->pD.p, db);
+        memcpy(I, idx->pI.p, ib);
+        return 0;
+    }
+    // Other small pageable calls (the CUDA-core scan re-reads its queries in every CTA, so they are copied to the device):
+    // the copy comes out of the index's page-locked buffer (a true asynchronous DMA, no driver staging) and the merge
+    // kernel stores the results straight into page-locked memory -- no device->host copies at all.  This is the
+    // reference's own call shape (nq = 1, k = 5 on a 125-row fp32 index, src/retrieval.py:102).
+    if ((size_t)nq * idx->d * 4 <= (size_t)(4u << 20) && (size_t)nq * k * 8 <= (size_t)(4u << 20)) {
+        const size_t qb = (size_t)nq * idx->d * 4, db = (size_t)nq * k * 4, ib = (size_t)nq * k * 8;
+        if ((rc = idx->pQ.ensure(qb)) || (rc = idx->pD.ensure(db)) || (rc = idx->pI.ensure(ib))) return rc;
+        {
+            std::lock_guard<std::mutex> lock(idx->mu);
+            if ((rc = idx->hQ.ensure(qb))) return rc;
+        }
+        memcpy(idx->pQ.p, q, qb);
+        // a tiny index is scanned by ONE CTA (search_simt): it reads its few queries straight from the page-locked buffer
+        const bool one_cta = !zero_copy && idx->path_force != 2 && idx->n > 0 && nq <= 8 &&
+                             (long long)idx->n * idx->pitch * elem_size(idx->storage) <= 256 * 1024;
+        const void* qsrc = idx->pQ.dp;
+        if (!one_cta) {
+            PRS_CUDA(cudaMemcpyAsync(idx->hQ.p, idx->pQ.p, qb, cudaMemcpyHostToDevice, 0));
+            qsrc = idx->hQ.p;
+        }
+        if ((rc = search_device_impl(idx, qsrc, PRS_F32, nq, k, (float*)idx->pD.dp, (int64_t*)idx->pI.dp, 0))) return rc;
         PRS_CUDA(cudaStreamSynchronize(0));
         memcpy(D, idx->pD.p, db);
         memcpy(I, idx->pI.p, ib);

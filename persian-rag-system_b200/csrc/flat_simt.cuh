@@ -39,6 +39,13 @@ struct SimtParams {
     int* cand_cnt;       // [grid][nq_total]
     int nq_total, q0;    // q0: index of this group's first query in the whole batch
     int sortn;           // power of two >= k + SIMT_THREADS
+    // single-CTA searches (an index of a few tiles: the reference's own 125-row indices) write the result themselves
+    // instead of leaving one candidate list for merge_cand_kernel: one launch per search
+    float* D;            // [nq_total, k]
+    long long* I;
+    long long id_offset;
+    int direct;          // 1: grid == 1, write D / I here;  out_mode 0: D = score (IP), 1: D = -score (direct-form L2)
+    int out_mode;
 };
 
 template <typename T> struct Vec16;
@@ -293,14 +300,58 @@ __global__ void __launch_bounds__(SIMT_THREADS, 1) flat_scan_simt_kernel(const S
     for (int qq = 0; qq < p.nq; ++qq) {
         const u64* base = p.lists + ((size_t)blockIdx.x * SIMT_NW * QB + qq) * p.cap;
         const int cap = p.cap;
+        const size_t o = ((size_t)blockIdx.x * p.nq_total + p.q0 + qq);
+        int total = 0;
+#pragma unroll
+        for (int w = 0; w < SIMT_NW; ++w) total += s_cnts[w * QB + qq];
+        auto emit = [&](int j, u64 key) {            // slot j of this query's result (key 0 = empty)
+            if (p.direct) {
+                const size_t r = (size_t)(p.q0 + qq) * p.k + j;
+                if (key) {
+                    const float sc = key_score(key);
+                    p.D[r] = p.out_mode == 0 ? sc : -sc;
+                    p.I[r] = (long long)key_id<PRS_TIE_LOW_ID>(key) + p.id_offset;
+                } else {
+                    p.D[r] = p.out_mode == 0 ? -3.402823466e+38f : 3.402823466e+38f;
+                    p.I[r] = -1;
+                }
+            } else {
+                p.cand[o * p.k + j] = key;             // all k slots, 0 = empty
+            }
+        };
+        if (total <= 128) {
+            // few candidates (small indices): one warp gathers them into registers and sorts them, no block-wide rounds
+            if (warp == 0) {
+                u64 v[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int e = lane * 4 + i;
+                    int off = 0;
+                    u64 val = 0ull;
+#pragma unroll
+                    for (int w = 0; w < SIMT_NW; ++w) {
+                        const int c = s_cnts[w * QB + qq];
+                        if (e >= off && e < off + c) val = base[(size_t)w * QB * cap + (e - off)];
+                        off += c;
+                    }
+                    v[i] = val;
+                }
+                warp_sort_desc<4>(v, lane);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { const int e = lane * 4 + i; if (e < p.k) emit(e, v[i]); }
+                if (lane == 0 && !p.direct) p.cand_cnt[o] = total < p.k ? total : p.k;
+            }
+            for (int j = 128 + tid; j < p.k; j += SIMT_THREADS) emit(j, 0ull);      // k > 128: the remaining slots are empty
+            __syncthreads();
+            continue;
+        }
         auto fetch = [&](long long i) -> u64 {
             const int w = (int)(i / cap), j = (int)(i - (long long)w * cap);
             return (j < s_cnts[w * QB + qq]) ? base[(size_t)w * QB * cap + j] : 0ull;
         };
         const int n = block_topk_stream(fetch, (long long)SIMT_NW * cap, p.k, buf, p.sortn, s_n, tid, SIMT_THREADS, 1);
-        const size_t o = ((size_t)blockIdx.x * p.nq_total + p.q0 + qq);
-        for (int j = tid; j < p.k; j += SIMT_THREADS) p.cand[o * p.k + j] = j < n ? buf[j] : 0ull;   // all k slots, 0 = empty
-        if (tid == 0) p.cand_cnt[o] = n;
+        for (int j = tid; j < p.k; j += SIMT_THREADS) emit(j, j < n ? buf[j] : 0ull);
+        if (tid == 0 && !p.direct) p.cand_cnt[o] = n;
         __syncthreads();
     }
 }

@@ -27,7 +27,15 @@ struct XchgView {
     uint32_t* flags[XCHG_MAX_RANKS];
     long long cap;                        // entries per (slot, rank)
     int nq_cap, G, rank;
+#ifdef PRS_EXPERIMENTS
+    int dbg;                              // PRS_XCHG_DBG: 1 do not wait for the peers' flags, 2 do not store into the peers (results are WRONG)
+#endif
 };
+#ifdef PRS_EXPERIMENTS
+#define XCHG_DBG(xv) ((xv).dbg)
+#else
+#define XCHG_DBG(xv) 0
+#endif
 
 __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
     uint32_t v;
@@ -103,6 +111,7 @@ __device__ __forceinline__ void xchg_push_query(
             iv = -1;
         }
         for (int p = 0; p < G; ++p) {
+            if ((XCHG_DBG(xv) & 2) && p != xv.rank) continue;
             xv.vals[p][ebase + j] = dv;
             xv.ids[p][ebase + j] = iv;
             if (rerank) xv.vals2[p][ebase + j] = d2;
@@ -134,6 +143,7 @@ __device__ __forceinline__ void xchg_pull_query(
         unsigned long long t0 = 0;
         int spins = 0;
         while (ld_relaxed_sys(f) != gen) {
+            if (XCHG_DBG(xv) & 1) break;
             __nanosleep(32);
             if ((++spins & 1023) == 0) {                                      // look at the clock every ~50 us
                 const unsigned long long now = global_timer_ns();
@@ -269,6 +279,9 @@ static inline size_t xchg_ids_bytes(const prs_xchg* x) { return (size_t)2 * x->G
 static inline size_t xchg_flags_bytes(const prs_xchg* x) { return (((size_t)2 * x->G * x->nq_cap * 4) + 255) & ~(size_t)255; }
 static inline void xchg_fill_view(prs_xchg* x) {
     x->view.cap = x->cap; x->view.nq_cap = x->nq_cap; x->view.G = x->G; x->view.rank = x->rank;
+#ifdef PRS_EXPERIMENTS
+    x->view.dbg = getenv("PRS_XCHG_DBG") ? atoi(getenv("PRS_XCHG_DBG")) : 0;
+#endif
     for (int p = 0; p < x->G; ++p) {
         unsigned char* b = (unsigned char*)x->peer_base[p];
         x->view.ids[p] = (long long*)b;                                  // 8-byte aligned first
