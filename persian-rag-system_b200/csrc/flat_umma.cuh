@@ -592,6 +592,7 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) flat_scan_umma_kernel(const U
             for (int j = 0; j < UMMA_MAX_K; ++j) best[j] = (j < UMMA_MAX_K - p.k) ? 0xFFFFFFFFu : 0u;
 #pragma unroll
             for (int g = 0; g < NGRP; ++g) {
+                if (g * FOLD >= G) break;                   // uniform: clusters of 2 publish 74 values, not 148
                 uint32_t v = gm[g];
 #pragma unroll
                 for (int j = 0; j < UMMA_MAX_K; ++j) {

@@ -180,6 +180,34 @@ def test_random_fp32_exact(P, n, d, nq, k, metric):
     assert flips <= 2 and nflip <= max(2, (nq * min(k, n)) // 200)
 
 
+@pytest.mark.parametrize("n", [125, 170, 171, 400])          # 170 x 384 fp32 is the last size one CTA takes (256 KB)
+@pytest.mark.parametrize("metric", [O.METRIC_L2, O.METRIC_IP])
+def test_small_index_single_cta_search(P, n, metric):
+    """The reference's own call shape (src/retrieval.py:102: nq = 1, k = 5 on a 125-row fp32 index) goes through ONE
+    CTA that writes D / I itself (no merge launch), with the queries read from page-locked memory: same answers as
+    the oracle for pageable numpy, pinned and device inputs, several query groups, k beyond the corpus and k > 128."""
+    import torch
+    d = 384
+    rng = np.random.default_rng(n + metric)
+    x = rng.standard_normal((n, d)).astype(np.float32)
+    x[n // 2] = x[3]                                          # an exact duplicate: lower id first
+    idx = P.FlatIndex(d, metric, "fp32")
+    idx.add(x)
+    for nq, k in ((1, 5), (9, 5), (20, 16), (2, 150), (3, n + 7)):
+        q = (x[rng.integers(0, n, nq)] + 0.05 * rng.standard_normal((nq, d))).astype(np.float32)
+        Dr, Ir = O.flat_search_c(x, q, k, metric, form=1)
+        D, I = idx.search(q, k)                               # pageable numpy
+        assert idx.last_path == "cuda-core"
+        # k reaches past the corpus: inner products near zero are sums of 384 O(1) terms, hence the absolute floor
+        O.check_topk_lists(I, D, Ir, Dr, rtol=RTOL_F32, atol=5e-5, what=f"small n{n} nq{nq} k{k}")
+        assert (I[:, min(k, n):] == -1).all()
+        Dd, Id = idx.search(torch.from_numpy(q).cuda(), k)    # device tensors
+        assert np.array_equal(Id.cpu().numpy(), I) and np.array_equal(Dd.cpu().numpy(), D)
+        qp = torch.from_numpy(q).pin_memory()                 # caller-pinned host buffers
+        Dp, Ip = idx.search(qp.numpy(), k)
+        assert np.array_equal(Ip, I) and np.array_equal(Dp, D)
+
+
 def test_empty_index_and_padding(P):
     idx = P.IndexFlatL2(16)
     D, I = idx.search(np.zeros((2, 16), np.float32), 3)
