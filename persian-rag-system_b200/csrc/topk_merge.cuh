@@ -11,6 +11,26 @@ namespace prs {
 constexpr int MERGE_THREADS = 256;
 constexpr int MERGE_ONESHOT = 4096;     // inputs up to this many keys are sorted in shared memory in one shot
 
+// One warp sorts buf[0, cnt) (cnt <= 128, unordered, in shared memory) descending in registers and writes back
+// max(cnt rounded up, k) slots (missing ones as 0 = empty).  Called by the 32 lanes of one warp; the caller
+// synchronises the CTA before and after.
+template <int NPL>
+__device__ __forceinline__ void warp_sort_buf_npl(u64* buf, int cnt, int k, int lane) {
+    u64 v[NPL];
+#pragma unroll
+    for (int i = 0; i < NPL; ++i) { const int e = lane * NPL + i; v[i] = e < cnt ? buf[e] : 0ull; }
+    __syncwarp();
+    warp_sort_desc<NPL>(v, lane);
+#pragma unroll
+    for (int i = 0; i < NPL; ++i) buf[lane * NPL + i] = v[i];
+    for (int e = 32 * NPL + lane; e < k; e += 32) buf[e] = 0ull;
+}
+__device__ __forceinline__ void warp_sort_buf_desc(u64* buf, int cnt, int k, int lane) {
+    if (cnt <= 32) warp_sort_buf_npl<1>(buf, cnt, k, lane);
+    else if (cnt <= 64) warp_sort_buf_npl<2>(buf, cnt, k, lane);
+    else warp_sort_buf_npl<4>(buf, cnt, k, lane);
+}
+
 // CTA-level top-k over `parts` lists of L keys each (list p = keys [p*L, (p+1)*L), sorted
 // descending, 0 = empty).  buf: sortn keys of shared memory (power of two, >= k + MERGE_THREADS);
 // heads: NT keys of shared memory; s_n: two ints.
@@ -57,6 +77,12 @@ __device__ __forceinline__ int block_topk_lists(Fetch fetch, int parts, int L, i
     }
     __syncthreads();
     const int cnt = s_n[0];
+    if (cnt <= 128) {
+        // the usual case (k .. 3k survivors): ONE warp sorts them in registers -- no block-wide barrier per bitonic stage
+        if (tid < 32) warp_sort_buf_desc(buf, cnt, k, tid);
+        named_bar_sync(1, NT);
+        return cnt < k ? cnt : k;
+    }
     int n2 = 2;
     while (n2 < cnt) n2 <<= 1;
     for (int i = cnt + tid; i < n2; i += NT) buf[i] = 0ull;

@@ -176,7 +176,27 @@ __device__ __forceinline__ void xchg_pull_query(
         const float s = sanitize(largest ? v : -v);
         return ((u64)f2ord(s) << 32) | (u64)(~(uint32_t)(part * k + j));
     };
-    const int n2 = block_topk_lists<NT, STREAM, ONESHOT2>(fetch2, G, k, k, buf, sortn, heads, s_n, tid);
+    int n2;
+    if (G * k <= 128) {
+        // a handful of keys (G lists of k): one warp fetches them all and sorts them in registers
+        if (tid < 32) {
+            int valid = 0;
+            for (int e = tid; e < 128; e += 32) {
+                const u64 key = e < G * k ? fetch2((long long)e) : 0ull;
+                buf[e] = key;
+                valid += key != 0ull;
+            }
+#pragma unroll
+            for (int o = 16; o; o >>= 1) valid += __shfl_xor_sync(0xffffffffu, valid, o);
+            __syncwarp();
+            warp_sort_buf_desc(buf, G * k, k, tid);
+            if (tid == 0) s_n[0] = valid < k ? valid : k;
+        }
+        __syncthreads();
+        n2 = s_n[0];
+    } else {
+        n2 = block_topk_lists<NT, STREAM, ONESHOT2>(fetch2, G, k, k, buf, sortn, heads, s_n, tid);
+    }
     if (rerank) {
         // selected by the expanded form; output the direct-form distances ordered by (distance, global id)
         __syncthreads();
