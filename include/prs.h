@@ -242,7 +242,9 @@ int prs_sparse_search_device(prs_sparse* sp, const int64_t* q_indptr, const int3
 /* scoring kernel: 0 = exact order (default: float64 accumulation in query-entry order, the summation order of
  * rank_bm25 / scipy), 1 = throughput (queries batched per CTA share their postings, fixed-point accumulation
  * with shared-memory integer atomics, k + 16 candidates).  Both re-score their candidates exactly in float64,
- * so the returned scores are bit-identical; the id lists can differ only among docs whose scores tie to ~1e-7. */
+ * so the returned scores are bit-identical; the id lists can differ only among docs whose scores tie to ~1e-7.
+ * 2 = automatic: exact order for single queries and small batches (the reference's call shape), throughput for
+ * batches of 16 queries or more (its structures are built on the first such batch). */
 int prs_sparse_set_mode(prs_sparse* sp, int mode);
 int prs_sparse_mode(const prs_sparse* sp);
 /* sum of postings touched by the last search (8 or 12 bytes each): the algorithmic bytes */

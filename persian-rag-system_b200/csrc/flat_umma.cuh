@@ -200,18 +200,25 @@ __device__ __noinline__ u64 slice_kth_largest(const u64* s, int n, int k) {
 // the storage type on the way into its TMEM lane and returns ||q~||^2 of the rounded row.  Out of line on purpose, and
 // with scalar arguments: taking the address of the kernel's parameter block (or indexing its arrays dynamically) makes
 // the compiler copy it to local memory and drop the uniform-datapath branches of the hot loops (measured: +15 % scan time).
-__device__ __noinline__ float stage_query_row(const void* q, int qdtype, int d, int is_bf16, uint32_t a_addr, int ncol, bool qvalid, size_t qoff) {
+// NORM = false (inner product: nobody reads ||q~||^2) drops the convert-back + FMA pair per element -- 3 of the 5
+// instructions per element pair of a loop that runs in a warp with a scheduler to itself.
+template <bool NORM>
+__device__ __forceinline__ float stage_query_row_t(const void* q, int qdtype, int d, int is_bf16, uint32_t a_addr, int ncol, bool qvalid, size_t qoff) {
     float qn = 0.f;
     auto pack2 = [&](float a, float b) -> uint32_t {
         if (is_bf16) {
             const __nv_bfloat16 x0 = __float2bfloat16_rn(a), x1 = __float2bfloat16_rn(b);
-            const float f0 = __bfloat162float(x0), f1 = __bfloat162float(x1);
-            qn = fmaf(f0, f0, qn); qn = fmaf(f1, f1, qn);
+            if (NORM) {
+                const float f0 = __bfloat162float(x0), f1 = __bfloat162float(x1);
+                qn = fmaf(f0, f0, qn); qn = fmaf(f1, f1, qn);
+            }
             return (uint32_t)__bfloat16_as_ushort(x0) | ((uint32_t)__bfloat16_as_ushort(x1) << 16);
         }
         const __half x0 = __float2half_rn(a), x1 = __float2half_rn(b);
-        const float f0 = __half2float(x0), f1 = __half2float(x1);
-        qn = fmaf(f0, f0, qn); qn = fmaf(f1, f1, qn);
+        if (NORM) {
+            const float f0 = __half2float(x0), f1 = __half2float(x1);
+            qn = fmaf(f0, f0, qn); qn = fmaf(f1, f1, qn);
+        }
         return (uint32_t)__half_as_ushort(x0) | ((uint32_t)__half_as_ushort(x1) << 16);
     };
     const int nch = d >> 3;                           // 16-byte chunks (8 elements) that hold data
@@ -262,6 +269,11 @@ __device__ __noinline__ float stage_query_row(const void* q, int qdtype, int d, 
         }
     }
     return qn;
+}
+__device__ __noinline__ float stage_query_row(const void* q, int qdtype, int d, int is_bf16, uint32_t a_addr, int ncol, bool qvalid, size_t qoff,
+                                              int need_norm) {
+    return need_norm ? stage_query_row_t<true>(q, qdtype, d, is_bf16, a_addr, ncol, qvalid, qoff)
+                     : stage_query_row_t<false>(q, qdtype, d, is_bf16, a_addr, ncol, qvalid, qoff);
 }
 
 // The two merges of the one-launch search, out of line with scalar arguments (see stage_query_row): inlined, they
@@ -537,7 +549,7 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) flat_scan_umma_kernel(const U
                 // one-launch search: this thread converts ITS query row on the way into tensor memory (out of line:
                 // the conversion code is large and must not sit between the hot loops of the three warp roles)
                 const size_t qg = (size_t)p.q0 + (size_t)crank * UMMA_M + qi;
-                const float qn = stage_query_row(p.q, p.qdtype, p.d, p.is_bf16, a_addr, ncol, qvalid, qg * (size_t)p.d);
+                const float qn = stage_query_row(p.q, p.qdtype, p.d, p.is_bf16, a_addr, ncol, qvalid, qg * (size_t)p.d, p.l2);
                 if (part == 0 && qvalid && p.qnorm) p.qnorm[qg] = qn;
             }
             tmem_st_wait();

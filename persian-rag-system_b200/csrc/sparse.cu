@@ -816,7 +816,7 @@ static int sparse_search_core(prs_sparse* sp, const long long* d_qptr, const int
                               double* dS, long long* dI, cudaStream_t st) {
     int rc;
     const int kk = std::min(k + SP_MARGIN, PRS_MAX_K + SP_MARGIN);
-    const bool fast = sp->mode == 1 && kk <= SB_MAXKK;
+    const bool fast = (sp->mode == 1 || (sp->mode == 2 && nq >= 2 * SB_QG)) && kk <= SB_MAXKK;     // mode 2 = by batch size
     if (fast && (rc = sparse_prepare_fast(sp))) return rc;
     if (!sp->event) PRS_CUDA(cudaEventCreateWithFlags(&sp->event, cudaEventDisableTiming));
     if (sp->used) PRS_CUDA(cudaStreamWaitEvent(st, sp->event, 0));
@@ -1056,7 +1056,7 @@ int prs_sparse_set_id_offset(prs_sparse* sp, int64_t off) {
     return 0;
 }
 int prs_sparse_set_mode(prs_sparse* sp, int mode) {
-    if (!sp || (mode != 0 && mode != 1)) { set_error("sparse_set_mode: mode must be 0 (exact order) or 1 (throughput)"); return PRS_EINVAL; }
+    if (!sp || mode < 0 || mode > 2) { set_error("sparse_set_mode: mode must be 0 (exact order), 1 (throughput) or 2 (throughput for batches of >= 16 queries)"); return PRS_EINVAL; }
     DeviceGuard g(sp->device);
     std::lock_guard<std::mutex> lock(sp->mu);
     sp->mode = mode;

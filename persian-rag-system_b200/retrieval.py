@@ -122,13 +122,14 @@ class RetrievalSystem:
 
     def _build_bm25(self):
         # whitespace tokens, no lower-casing, no stop words: src/retrieval.py:66
-        self.bm25_index = BM25Index([record["text"].split() for record in self.chunks])
+        # "auto": single queries are scored in rank_bm25's summation order, batches of >= 16 queries by the throughput kernel
+        self.bm25_index = BM25Index([record["text"].split() for record in self.chunks], mode="auto")
         print("✓ BM25 postings on device")
 
     def _build_tfidf(self):
         # TfidfVectorizer(max_features=10000, stop_words=None, ngram_range=(1, 2)): src/retrieval.py:78-83
         self.tfidf_vectorizer = TfidfIndex([record["text"] for record in self.chunks],
-                                           max_features=10000, ngram_range=(1, 2))
+                                           max_features=10000, ngram_range=(1, 2), mode="auto")
         self.tfidf_matrix = self.tfidf_vectorizer.index
         print("✓ TF-IDF postings on device")
 

@@ -50,13 +50,14 @@ class SparseIndex:
         """"exact": float64 accumulation in query-entry order (rank_bm25 / scipy summation order), one
         query per CTA.  "throughput": 8 queries per CTA share the postings they have in common,
         fixed-point accumulation, k + 16 candidates.  Both re-score their candidates exactly in float64
-        (identical scores); id lists can differ only among docs whose scores tie to ~1e-7 relative."""
-        code = {"exact": 0, "throughput": 1, "fast": 1, 0: 0, 1: 1}[mode]
+        (identical scores); id lists can differ only among docs whose scores tie to ~1e-7 relative.
+        "auto": exact order below 16 queries per call, throughput from there on."""
+        code = {"exact": 0, "throughput": 1, "fast": 1, "auto": 2, 0: 0, 1: 1, 2: 2}[mode]
         check(self._L.prs_sparse_set_mode(self._h, code))
 
     @property
     def mode(self) -> str:
-        return {0: "exact", 1: "throughput"}[int(self._L.prs_sparse_mode(self._h))]
+        return {0: "exact", 1: "throughput", 2: "auto"}[int(self._L.prs_sparse_mode(self._h))]
 
     @property
     def ndocs(self) -> int:

@@ -173,6 +173,13 @@ def test_throughput_mode_random_corpus_vs_oracle(P):
     assert fast.index.last_postings == exact.index.last_postings                # counted by a kernel on that path
     Sd, Id = exact.search_device(qs[:5], 3)
     assert np.array_equal(Sd.cpu().numpy(), Se[:5, :3]) and np.array_equal(Id.cpu().numpy(), Ie[:5, :3])
+    # "auto" (what RetrievalSystem uses): below 16 queries the exact-order kernel, from 16 on the throughput kernel
+    auto = P.BM25Index(docs, mode="auto")
+    assert auto.index.mode == "auto"
+    Sa, Ia = auto.search(qs[:15], 10)
+    assert np.array_equal(Sa, Se[:15]) and np.array_equal(Ia, Ie[:15])
+    Sa, Ia = auto.search(qs, 10)
+    assert np.array_equal(Sa, S) and np.array_equal(Ia, I)
 
 
 def test_throughput_mode_raw_csr_many_tiles_negative_weights_and_shared_terms(P):
