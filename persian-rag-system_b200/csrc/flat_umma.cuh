@@ -146,6 +146,34 @@ __device__ __forceinline__ void umma_commit_multicast(uint64_t* bar, uint16_t ma
                  ::"r"(smem_u32(bar)), "h"(mask) : "memory");
 }
 
+// ---- CTA pair (cta_group::2): the two CTAs of a cluster execute ONE MMA of M = 256 -- each holds its own 128 query rows
+// (A) and accumulator rows (D) in its tensor memory and HALF of the corpus tile (B) in its shared memory; the even CTA issues.
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_dst, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+template <int ACC>
+__device__ __forceinline__ void umma_ts_f16_pair(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "n"(ACC) : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {       // arrives on the barrier at this offset in BOTH CTAs
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+// arrive on the mbarrier at the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank) {
+    uint32_t ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(bar)), "r"(rank));
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(ra) : "memory");
+}
+
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -384,11 +412,17 @@ __device__ __forceinline__ void fused_tail(const UmmaParams& p, int part, int np
 // leaves room in tensor memory for two 128-column accumulator buffers (pitch <= 512: d = 384 went
 // from 74 % to 86 % of the HBM roofline); pitch 768 keeps NB = 1 with double buffering (a single
 // 128-column buffer serialises MMA and epilogue: 93.7 % vs 95.3 %).
-template <int CL, int NB>
+template <int CL, int NB, int PAIR = 0>
 __global__ void __launch_bounds__(UMMA_THREADS, 1) flat_scan_umma_kernel(const UmmaParams p) {
+    static_assert(!PAIR || CL == 2, "a CTA pair is a cluster of two");
     constexpr int TILE_N = NB * BLK_ROWS;
-    constexpr int UMMA_KB_STAGE_BYTES = NB * KBLOCK_BYTES;   // one k-block of a tile: NB adjacent 8 KB block pieces
-    const int crank = CL > 1 ? (int)cluster_ctarank() : 0;           // which query block of the pass this CTA serves
+    // one k-block of a tile in THIS CTA's shared memory: NB adjacent 8 KB block pieces; a pair CTA holds HALF of the tile's
+    // rows -- one block of the two (NB = 2) or rows [32 * rank, 32 * rank + 32) of the block (NB = 1: 4 KB per k-block)
+    constexpr int UMMA_KB_STAGE_BYTES = PAIR ? NB * KBLOCK_BYTES / 2 : NB * KBLOCK_BYTES;
+    // which query block of the pass this CTA serves = its rank in the (CL, 1, 1) cluster.  Taken from blockIdx (clusters are
+    // consecutive blocks) rather than %cluster_ctarank: the compiler then knows it is uniform, which the pair's epilogue needs
+    // to keep its uniform-datapath branches (see the codegen note in DESIGN.md)
+    const int crank = CL > 1 ? (int)(blockIdx.x % CL) : 0;
     const int part = (int)blockIdx.x / CL;                            // cluster index = candidate-list slot
     const int nparts = (int)gridDim.x / CL;
     constexpr uint16_t CMASK = (uint16_t)((1u << CL) - 1u);
@@ -407,7 +441,8 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) flat_scan_umma_kernel(const U
     uint64_t* empty = full + UMMA_MAX_STAGES;
     uint64_t* tmem_full = empty + UMMA_MAX_STAGES;
     uint64_t* tmem_empty = tmem_full + 2;
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    uint64_t* peer_ready = tmem_empty + 2;                             // pair: the odd CTA's queries are in ITS tensor memory
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(peer_ready + 1);
     int* s_flag = reinterpret_cast<int*>(tmem_ptr + 1);
 
     const int kblocks = p.pitch >> 6;
@@ -417,11 +452,14 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) flat_scan_umma_kernel(const U
     const long long n_tiles = (n_tiles_all + p.tile_step - 1) / p.tile_step;   // tiles this launch visits: t * tile_step
 
     if (tid == 0) {
-        for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], CL); }
-        for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 4); }
+        // pair: the leader's `full` also takes the peer's "my half landed", its `tmem_empty` the peer's four epilogue warps;
+        // one multicast commit frees a stage in both CTAs
+        for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], (PAIR && crank == 0) ? 2 : 1); mbar_init(&empty[s], PAIR ? 1 : CL); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], PAIR ? 8 : 4); }
+        mbar_init(peer_ready, 1);
         mbar_fence_init();
     }
-    if (warp == 0) tmem_alloc(tmem_ptr, UMMA_TMEM_COLS);
+    if (warp == 0) { if (PAIR) tmem_alloc_pair(tmem_ptr, UMMA_TMEM_COLS); else tmem_alloc(tmem_ptr, UMMA_TMEM_COLS); }
     tc_fence_before();
     __syncthreads();
     if (CL > 1) cluster_sync_all();          // every CTA's barriers exist before a peer multicasts onto them
@@ -440,6 +478,33 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) flat_scan_umma_kernel(const U
                 const long long t = ti * p.tile_step;
                 const int nblk = (int)((n_blocks - NB * t < NB) ? (n_blocks - NB * t) : NB);   // the last tile may be short
                 const unsigned char* src = p.x + (size_t)(NB * t) * blk_bytes;
+                if (PAIR && NB == 2) {
+                    // this CTA's half of the tile: row block NB*t + crank (nothing if the last tile has one block only)
+                    const bool have = crank < nblk;
+                    for (int ks = 0; ks < kstages; ++ks) {
+                        mbar_wait(&empty[s], ph ^ 1u);
+                        mbar_arrive_expect_tx(&full[s], have ? (uint32_t)p.kbs * KBLOCK_BYTES : 0u);
+                        if (have) {
+                            const unsigned char* g = src + (size_t)crank * blk_bytes + (size_t)(ks * p.kbs) * KBLOCK_BYTES;
+                            // the kbs k-blocks of one row block are contiguous in HBM and in the stage: ONE copy
+                            bulk_g2s(ring + (size_t)s * STAGE_BYTES, g, (uint32_t)p.kbs * KBLOCK_BYTES, &full[s]);
+                        }
+                        if (++s == p.stages) { s = 0; ph ^= 1u; }
+                    }
+                    continue;
+                }
+                if (PAIR && NB == 1) {
+                    // 64-row tiles: rows [32 * crank, +32) of the block -- the first / second 4 KB of every 8 KB k-block piece
+                    for (int ks = 0; ks < kstages; ++ks) {
+                        mbar_wait(&empty[s], ph ^ 1u);
+                        mbar_arrive_expect_tx(&full[s], (uint32_t)p.kbs * (KBLOCK_BYTES / 2));
+                        for (int kbi = 0; kbi < p.kbs; ++kbi)
+                            bulk_g2s(ring + (size_t)s * STAGE_BYTES + (size_t)kbi * (KBLOCK_BYTES / 2),
+                                     src + (size_t)(ks * p.kbs + kbi) * KBLOCK_BYTES + (size_t)crank * (KBLOCK_BYTES / 2), KBLOCK_BYTES / 2, &full[s]);
+                        if (++s == p.stages) { s = 0; ph ^= 1u; }
+                    }
+                    continue;
+                }
                 for (int ks = 0; ks < kstages; ++ks) {
                     mbar_wait(&empty[s], ph ^ 1u);
                     if (UMMA_DBG(p) & 16) {                     // experiment: no copies at all (what do MMA + epilogue cost alone?)
@@ -468,11 +533,26 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) flat_scan_umma_kernel(const U
         // instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 [4,6)=1,
         // a/b_format [7,10)/[10,13) (0 F16, 1 BF16), K-major A and B, N>>3 at [17,23), M>>4 at [24,29)
         const uint32_t fmt = p.is_bf16 ? 1u : 0u;
-        const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(TILE_N >> 3) << 17) | ((uint32_t)(UMMA_M >> 4) << 24);
+        const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(TILE_N >> 3) << 17) |
+                               ((uint32_t)((PAIR ? 2 * UMMA_M : UMMA_M) >> 4) << 24);
         int s = 0, it = 0;
         uint32_t ph = 0;
         named_bar_sync(2, 160);                               // queries are in TMEM
         tc_fence_after();
+        if (PAIR && crank != 0) {
+            // The odd CTA of a pair issues no MMA.  Its idle issuer thread tells the leader that this CTA's queries are
+            // staged, then forwards "my half of the stage landed" to the leader's `full` barrier, stage after stage.
+            if (elect_one()) {
+                mbar_arrive_remote(peer_ready, 0u);
+                for (long long ti = part; ti < n_tiles; ti += nparts) {
+                    for (int ks = 0; ks < kstages; ++ks) {
+                        mbar_wait(&full[s], ph);
+                        mbar_arrive_remote(&full[s], 0u);
+                        if (++s == p.stages) { s = 0; ph ^= 1u; }
+                    }
+                }
+            }
+        } else
         // ONE elected thread runs the whole issue loop (elect.sync: the compiler then emits straight-line uniform-datapath
         // code; with `if (lane == 0)` every tcgen05.mma was wrapped in an ELECT / BRA.U.ANY retry loop).  Per MMA the
         // loop is two adds and the instruction itself: the shared-memory descriptor of a stage is built once and only its
@@ -481,31 +561,59 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) flat_scan_umma_kernel(const U
         // ~100 cycles per MMA in this warp, i.e. the ISSUE loop -- not the tensor pipe (36 % busy) -- bound large batches.
         if (elect_one()) {
             constexpr uint64_t DESC_HI = (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+            if (PAIR) { mbar_wait(peer_ready, 0u); tc_fence_after(); }
+#ifdef PRS_EXPERIMENTS
+            long long w_acc = 0, w_full = 0, t_begin = clock64();      // PRS_UMMA_DEBUG & 32: where does the issue thread wait?
+#endif
             for (long long ti = part; ti < n_tiles; ti += nparts, ++it) {
                 const int b = nbuf == 2 ? (it & 1) : 0;
                 const uint32_t aph = (uint32_t)(nbuf == 2 ? (it >> 1) : it) & 1u;
+#ifdef PRS_EXPERIMENTS
+                const long long c0 = clock64();
+#endif
                 mbar_wait(&tmem_empty[b], aph ^ 1u);
+#ifdef PRS_EXPERIMENTS
+                w_acc += clock64() - c0;
+#endif
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + D_OFF + (uint32_t)(b * TILE_N);
                 uint32_t a_tmem = tmem_base;
                 for (int ks = 0; ks < kstages; ++ks) {
+#ifdef PRS_EXPERIMENTS
+                    const long long c1 = clock64();
+#endif
                     mbar_wait(&full[s], ph);
+#ifdef PRS_EXPERIMENTS
+                    w_full += clock64() - c1;
+#endif
                     tc_fence_after();
                     uint64_t bdesc = DESC_HI | (uint64_t)((smem_u32(ring + (size_t)s * STAGE_BYTES) >> 4) & 0x3FFFu);
                     for (int kbi = 0; kbi < p.kbs; ++kbi) {
-                        if (ks == 0 && kbi == 0) umma_ts_f16_c<0>(d_tmem, a_tmem, bdesc, idesc);     // first slice of the tile overwrites
-                        else umma_ts_f16_c<1>(d_tmem, a_tmem, bdesc, idesc);
+                        if (PAIR) {
+                            if (ks == 0 && kbi == 0) umma_ts_f16_pair<0>(d_tmem, a_tmem, bdesc, idesc);
+                            else umma_ts_f16_pair<1>(d_tmem, a_tmem, bdesc, idesc);
 #pragma unroll
-                        for (int k4 = 1; k4 < 4; ++k4) umma_ts_f16_c<1>(d_tmem, a_tmem + (uint32_t)(k4 * 8), bdesc + (uint64_t)(k4 * 2), idesc);
+                            for (int k4 = 1; k4 < 4; ++k4) umma_ts_f16_pair<1>(d_tmem, a_tmem + (uint32_t)(k4 * 8), bdesc + (uint64_t)(k4 * 2), idesc);
+                        } else {
+                            if (ks == 0 && kbi == 0) umma_ts_f16_c<0>(d_tmem, a_tmem, bdesc, idesc);     // first slice of the tile overwrites
+                            else umma_ts_f16_c<1>(d_tmem, a_tmem, bdesc, idesc);
+#pragma unroll
+                            for (int k4 = 1; k4 < 4; ++k4) umma_ts_f16_c<1>(d_tmem, a_tmem + (uint32_t)(k4 * 8), bdesc + (uint64_t)(k4 * 2), idesc);
+                        }
                         a_tmem += 32u;
                         bdesc += (uint64_t)(UMMA_KB_STAGE_BYTES >> 4);
                     }
-                    if (CL == 1) umma_commit(&empty[s]);       // frees the smem stage when these MMAs retire
+                    if (PAIR) umma_commit_pair(&empty[s]);     // frees the stage in both CTAs of the pair
+                    else if (CL == 1) umma_commit(&empty[s]);  // frees the smem stage when these MMAs retire
                     else umma_commit_multicast(&empty[s], CMASK);   // ... in every CTA of the cluster
-                    if (ks == kstages - 1) umma_commit(&tmem_full[b]);
+                    if (ks == kstages - 1) { if (PAIR) umma_commit_pair(&tmem_full[b]); else umma_commit(&tmem_full[b]); }
                     if (++s == p.stages) { s = 0; ph ^= 1u; }
                 }
             }
+#ifdef PRS_EXPERIMENTS
+            if ((UMMA_DBG(p) & 32) && blockIdx.x == 0)
+                printf("issue thread of CTA 0: %d tiles, total %lld cycles, waiting for the accumulator %lld, for stages %lld\n", it, clock64() - t_begin, w_acc, w_full);
+#endif
         }
     } else {
         // ---------------- epilogue: one thread per query ----------------
@@ -736,7 +844,7 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) flat_scan_umma_kernel(const U
             if (UMMA_DBG(p) & 2) {
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&tmem_empty[b]);
+                if (lane == 0) { if (PAIR && crank != 0) mbar_arrive_remote(&tmem_empty[b], 0u); else mbar_arrive(&tmem_empty[b]); }
                 continue;
             }
             if (p.mode == 2) {
@@ -748,7 +856,7 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) flat_scan_umma_kernel(const U
                     if (h == NB - 1) {
                         tc_fence_before();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(&tmem_empty[b]);
+                        if (lane == 0) { if (PAIR && crank != 0) mbar_arrive_remote(&tmem_empty[b], 0u); else mbar_arrive(&tmem_empty[b]); }
                     }
                     const int nv = nvalid - h * BLK_ROWS;
 #pragma unroll
@@ -800,7 +908,7 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) flat_scan_umma_kernel(const U
                 if (h == NB - 1) {
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&tmem_empty[b]);
+                    if (lane == 0) { if (PAIR && crank != 0) mbar_arrive_remote(&tmem_empty[b], 0u); else mbar_arrive(&tmem_empty[b]); }
                 }
                 survivors(v, nvalid - h * BLK_ROWS, hm);
                 if (hm[0] | hm[1]) insert_hits(v, hm, row0 + h * BLK_ROWS);
@@ -822,7 +930,7 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) flat_scan_umma_kernel(const U
     __syncthreads();
     if (CL > 1) cluster_sync_all();          // no CTA leaves while a peer's commits can still arrive on its barriers
     tc_fence_after();
-    if (warp == 0) tmem_dealloc(tmem_base, UMMA_TMEM_COLS);
+    if (warp == 0) { if (PAIR) tmem_dealloc_pair(tmem_base, UMMA_TMEM_COLS); else tmem_dealloc(tmem_base, UMMA_TMEM_COLS); }
 
     if (CL == 1 && p.fuse_merge) fused_tail(p, part, nparts, tid, base, s_flag);
 }
@@ -903,7 +1011,7 @@ static inline bool umma_eligible(int storage, int d, int pitch, long long nq, in
     return (storage == PRS_F16 || storage == PRS_BF16) && pitch <= 768 && k <= UMMA_MAX_K && nq >= 1;
 }
 
-template <int CL, int NB>
+template <int CL, int NB, int PAIR = 0>
 static inline int umma_launch(const UmmaParams& p, int n_clusters, size_t smem, cudaStream_t stream) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(n_clusters * CL), 1, 1);
@@ -919,14 +1027,14 @@ static inline int umma_launch(const UmmaParams& p, int n_clusters, size_t smem, 
         attr[0].val.cooperative = 1;
     }
     cfg.attrs = attr; cfg.numAttrs = (CL > 1 || p.fuse_merge) ? 1 : 0;
-    PRS_CUDA(cudaLaunchKernelEx(&cfg, flat_scan_umma_kernel<CL, NB>, p));
+    PRS_CUDA(cudaLaunchKernelEx(&cfg, flat_scan_umma_kernel<CL, NB, PAIR>, p));
     return 0;
 }
 
 // how many clusters of CL CTAs (1 CTA per SM at this shared-memory size) the device runs at once.
 // Cached per (device, shared-memory size) under a mutex: indices on different devices and threads
 // plan concurrently.
-template <int CL, int NB>
+template <int CL, int NB, int PAIR = 0>
 static inline int umma_max_clusters(size_t smem, int sm_count) {
     static std::mutex mu;
     static std::map<std::pair<int, size_t>, int> cache;
@@ -935,7 +1043,7 @@ static inline int umma_max_clusters(size_t smem, int sm_count) {
     std::lock_guard<std::mutex> lock(mu);
     auto it = cache.find({device, smem});
     if (it != cache.end()) return it->second;
-    if (cudaFuncSetAttribute(flat_scan_umma_kernel<CL, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return 0; }
+    if (cudaFuncSetAttribute(flat_scan_umma_kernel<CL, NB, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return 0; }
     int n = sm_count / CL;
     if (CL > 1) {
         cudaLaunchConfig_t cfg = {};
@@ -947,7 +1055,7 @@ static inline int umma_max_clusters(size_t smem, int sm_count) {
         attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr; cfg.numAttrs = 1;
         int q = 0;
-        if (cudaOccupancyMaxActiveClusters(&q, flat_scan_umma_kernel<CL, NB>, &cfg) != cudaSuccess) { cudaGetLastError(); return 0; }
+        if (cudaOccupancyMaxActiveClusters(&q, flat_scan_umma_kernel<CL, NB, PAIR>, &cfg) != cudaSuccess) { cudaGetLastError(); return 0; }
         n = q;
     }
     cache[{device, smem}] = n;
@@ -956,13 +1064,15 @@ static inline int umma_max_clusters(size_t smem, int sm_count) {
 
 // everything about a search that depends only on shapes
 struct UmmaPlan {
-    int CL = 1, NB = 1, kbs = 1, stages = 2, n_clusters = 1, dbg = 0, reboot = 0;
+    int CL = 1, NB = 1, kbs = 1, stages = 2, n_clusters = 1, dbg = 0, reboot = 0, pair = 0;
     size_t smem = 0;
     long long n_tiles = 0, qblock = 128, nq_pad = 128, boot_words = 0, nblocks = 1;
 };
 
-static inline int umma_plan(long long n, int pitch, long long nq, int sm_count, UmmaPlan& pl, bool no_clusters = false) {
+static inline int umma_plan(long long n, int pitch, long long nq, int sm_count, UmmaPlan& pl, bool no_clusters = false, bool allow_pair = true) {
 #ifdef PRS_EXPERIMENTS
+    static const int dbg_pair = getenv("PRS_UMMA_PAIR") ? atoi(getenv("PRS_UMMA_PAIR")) : 0;
+    if (dbg_pair != 1) allow_pair = false;        // the CTA-pair variant is an experiment (PRS_UMMA_PAIR=1): see below
     static const int dbg = getenv("PRS_UMMA_DEBUG") ? atoi(getenv("PRS_UMMA_DEBUG")) : 0;
     static const int dbg_kbs = getenv("PRS_UMMA_KBS") ? atoi(getenv("PRS_UMMA_KBS")) : 0;
     static const int dbg_cl = getenv("PRS_UMMA_CLUSTER") ? atoi(getenv("PRS_UMMA_CLUSTER")) : 0;
@@ -980,14 +1090,31 @@ static inline int umma_plan(long long n, int pitch, long long nq, int sm_count, 
     if (pitch > 512 && nq > UMMA_M) pl.NB = 2;
     if (dbg_nb == 1) pl.NB = 1;
     if (dbg_nb == 2) pl.NB = 2;                     // experiment: 128-row tiles even when only ONE accumulator buffer fits (pitch > 512)
+    // EXPERIMENT (experiments build, PRS_UMMA_PAIR=1): batches above 128 queries as CTA PAIRS (tcgen05 cta_group::2) -- the two
+    // CTAs of a cluster hold 128 queries each and HALF of every tile; the even CTA issues one M = 256 MMA over both halves.
+    // Against two CTAs that each receive the whole tile by multicast this halves the bytes every SM takes in, and the
+    // M = 256, N = 128 instruction runs at the full rate (64 cycles per K = 16: tools/probes/pair_probe.cu).  Correct (the
+    // parity tests pass) but NOT faster end to end: the accumulator hand-over (commit -> both epilogues -> remote arrive ->
+    // issue thread) costs ~2 600 cycles per tile across two SMs against ~1 250 inside one, and the epilogue's tensor-memory
+    // reads slow down when the MMAs run at full rate: 1M x 768, B = 1024: 1.60 ms against 1.53 ms for the multicast
+    // clusters; d = 384: 0.90 against 0.82 ms (profiles/r2_bigbatch_experiments.log, fourth series).
+#ifdef PRS_EXPERIMENTS
+    pl.pair = (allow_pair && nq > UMMA_M && !no_clusters && dbg_cl <= 0) ? 1 : 0;
+#else
+    pl.pair = 0;
+    (void)allow_pair;
+#endif
+    if (pl.pair) pl.NB = pitch <= 512 ? 2 : 1;      // two accumulator buffers always: 2 x 128 columns beside <= 512-wide queries, else 2 x 64
+    if (pl.pair && dbg_nb >= 1 && dbg_nb <= 2) pl.NB = dbg_nb;
+    const int half_blocks = pl.pair ? pl.NB : 2 * pl.NB;   // 4 KB half block pieces per k-block in ONE CTA's shared memory
     // k-blocks per pipeline stage: stages of up to 48 KB.  Few, large stages keep the per-stage
     // barrier round trips of the single MMA-issuing thread off the critical path (measured: 8 KB
     // stages 3443 GB/s, 16 KB 4431, 48 KB 4513 -> see profiles/)
     pl.kbs = 1;
-    for (int c = 2; c <= 6 / pl.NB; ++c) if (kblocks % c == 0) pl.kbs = c;
+    for (int c = 2; c <= 12 / half_blocks; ++c) if (kblocks % c == 0) pl.kbs = c;
     if (dbg_kbs > 0 && kblocks % (dbg_kbs > 0 ? dbg_kbs : 1) == 0) pl.kbs = dbg_kbs;
-    const size_t stage_bytes = (size_t)pl.kbs * pl.NB * KBLOCK_BYTES;
-    const size_t fixed = 4 * (size_t)pl.NB * BLK_ROWS * 4 + (2 * UMMA_MAX_STAGES + 4) * 8 + 16;
+    const size_t stage_bytes = (size_t)pl.kbs * half_blocks * (KBLOCK_BYTES / 2);
+    const size_t fixed = 4 * (size_t)pl.NB * BLK_ROWS * 4 + (2 * UMMA_MAX_STAGES + 5) * 8 + 16;
     pl.stages = (int)((226 * 1024 - 1024 - fixed) / stage_bytes);
     if (pl.stages > UMMA_MAX_STAGES) pl.stages = UMMA_MAX_STAGES;
     pl.smem = 1024 + (size_t)pl.stages * stage_bytes + fixed;
@@ -1007,7 +1134,13 @@ static inline int umma_plan(long long n, int pitch, long long nq, int sm_count, 
     if (dbg_cl == 1 || dbg_cl == 2 || dbg_cl == 4) pl.CL = dbg_cl;
     if (no_clusters) pl.CL = 1;
     int max_clusters = 0;
-    for (;;) {
+#ifdef PRS_EXPERIMENTS
+    if (pl.pair) {
+        max_clusters = pl.NB == 2 ? umma_max_clusters<2, 2, 1>(pl.smem, sm_count) : umma_max_clusters<2, 1, 1>(pl.smem, sm_count);
+        if (max_clusters <= 0) return umma_plan(n, pitch, nq, sm_count, pl, no_clusters, false);   // no pairs on this device: multicast clusters
+    }
+#endif
+    for (; !pl.pair;) {
         const int CL = pl.CL;
         if (pl.NB == 2) max_clusters = CL == 4 ? umma_max_clusters<4, 2>(pl.smem, sm_count) : (CL == 2 ? umma_max_clusters<2, 2>(pl.smem, sm_count) : umma_max_clusters<1, 2>(pl.smem, sm_count));
         else max_clusters = CL == 4 ? umma_max_clusters<4, 1>(pl.smem, sm_count) : (CL == 2 ? umma_max_clusters<2, 1>(pl.smem, sm_count) : umma_max_clusters<1, 1>(pl.smem, sm_count));
@@ -1073,6 +1206,10 @@ static inline int umma_scan(UmmaState& st, const UmmaPlan& pl, const void* x, co
         if (timer) timer->begin(stream);
         int rc;
         const int CL = pl.CL, nc = pl.n_clusters;
+#ifdef PRS_EXPERIMENTS
+        if (pl.pair) rc = pl.NB == 2 ? umma_launch<2, 2, 1>(p, nc, pl.smem, stream) : umma_launch<2, 1, 1>(p, nc, pl.smem, stream);
+        else
+#endif
         if (pl.NB == 2) rc = CL == 4 ? umma_launch<4, 2>(p, nc, pl.smem, stream) : (CL == 2 ? umma_launch<2, 2>(p, nc, pl.smem, stream) : umma_launch<1, 2>(p, nc, pl.smem, stream));
         else rc = CL == 4 ? umma_launch<4, 1>(p, nc, pl.smem, stream) : (CL == 2 ? umma_launch<2, 1>(p, nc, pl.smem, stream) : umma_launch<1, 1>(p, nc, pl.smem, stream));
         if (rc) return rc;
