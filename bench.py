@@ -23,6 +23,7 @@ inside the timed region), `sweep` (batch 1..1024, device-resident, outside the K
 from __future__ import annotations
 
 import argparse
+import faulthandler
 import json
 import os
 import subprocess
@@ -64,6 +65,8 @@ def parse():
                          "c4 = batch x k sweep on the 50M x 384 per-GPU share; 'none' skips them")
     ap.add_argument("--no-fuse", action="store_true", help="three-kernel search (prep, scan, merge) instead of the one-launch search (A/B)")
     ap.add_argument("--no-sweep", action="store_true")
+    ap.add_argument("--secondary-budget-s", type=float, default=420.0,
+                    help="seconds the measurements AFTER the headline (sweep, CPU baseline, extra configs) may take before the line is printed without them")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sweep-out", default="")
     return ap.parse_args()
@@ -528,10 +531,15 @@ def run_b200(a):
         out["pipelined"] = pipelined
     if rank == 0:
         out["clocks"] = sampler.summary()
+    # From here on only SECONDARY measurements follow (sweep, CPU baseline, extra configs).  If one of them ever stalls,
+    # the headline line must still come out: a watchdog prints what has been measured so far and ends the process.
+    watchdog = _arm_watchdog(out, rank, a.secondary_budget_s)
 
     # ---- batch sweep (device resident, 1 GPU): the B = 1..1024 picture of configs[1] ----
     if world == 1 and not a.no_sweep:
         sweep = []
+        sw_clk = ClockSampler(local)            # tensor-bound batches draw the most power: record clocks / cap reasons per batch size
+        sw_clk.start()
         for B in (1, 2, 4, 8, 16, 32, 64, 128, 256, 512, 1024):
             q = torch.randn(B, a.d, generator=gq, device=dev)
             q /= q.norm(dim=1, keepdim=True)
@@ -541,18 +549,28 @@ def run_b200(a):
             torch.cuda.synchronize()
             idx.set_timing(True); idx.scan_time()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            r0 = len(sw_clk.rows)
+            sw_clk.on = True
             e0.record()
             for _ in range(iters):
                 idx.search(q, a.k)
             e1.record()
             torch.cuda.synchronize()
+            sw_clk.on = False
             ms = e0.elapsed_time(e1) / iters
             sms, sn = idx.scan_time()
             idx.set_timing(False)
             gbs = alg_bytes / (ms * 1e-3) / 1e9
-            sweep.append({"batch": B, "ms": round(ms, 4), "qps": round(B / (ms * 1e-3), 1), "path": idx.last_path,
-                          "corpus_gbs": round(gbs, 1), "frac_hbm": round(gbs / peak, 4),
-                          "scan_ms": round(sms / iters, 4), "tflops": round(2.0 * n_local * a.d * B / (ms * 1e-3) / 1e12, 2)})
+            row = {"batch": B, "ms": round(ms, 4), "qps": round(B / (ms * 1e-3), 1), "path": idx.last_path,
+                   "corpus_gbs": round(gbs, 1), "frac_hbm": round(gbs / peak, 4),
+                   "scan_ms": round(sms / iters, 4), "tflops": round(2.0 * n_local * a.d * B / (ms * 1e-3) / 1e12, 2)}
+            rows = sw_clk.rows[r0:]
+            if rows:
+                row["sm_mhz"] = float(np.median([m for m, _ in rows]))
+                cap = getattr(sw_clk.nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)
+                row["sw_power_cap"] = bool(any(r & cap for _, r in rows))
+            sweep.append(row)
+        sw_clk.stop()
         out["sweep"] = sweep
         if a.sweep_out:
             json.dump(sweep, open(a.sweep_out, "w"), indent=1)
@@ -609,6 +627,7 @@ def run_b200(a):
             out["configs3_bm25_10M_docs"] = measure_configs3(dev, peak)
         except Exception as e:
             out["configs3_bm25_10M_docs"] = {"error": repr(e)[:300]}
+    watchdog.cancel()
     if rank == 0:
         print(json.dumps(out))
     if world > 1:
@@ -930,8 +949,29 @@ def measure_capacity(a, world, rank, local, dev, peak, sweep=False):
             "aggregate_scan_gbs": world * shard_bytes / (scan * 1e-3) / 1e9, "ids_valid": ok}
 
 
+def _arm_watchdog(out, rank, budget_s):
+    """After `budget_s` seconds: dump every thread's stack to stderr, print the JSON collected so far (rank 0) with
+    `secondary_incomplete`, and end the process.  Cancelled by the normal end of the run."""
+    def bail():
+        try:
+            faulthandler.dump_traceback(file=sys.stderr, all_threads=True)
+            if rank == 0:
+                o = dict(out)
+                o["secondary_incomplete"] = f"a secondary measurement did not finish within {budget_s} s; stacks on stderr"
+                print(json.dumps(o))
+                sys.stdout.flush()
+        finally:
+            os._exit(0)
+    t = threading.Timer(float(budget_s), bail)
+    t.daemon = True
+    t.start()
+    return t
+
+
 def main():
     a = parse()
+    faulthandler.enable()
+    faulthandler.dump_traceback_later(600, exit=False)        # a run this long is stuck: leave the stacks on stderr
     if a.impl == "reference":
         run_reference(a)
     else:
