@@ -214,6 +214,31 @@ class FlatIndex:
         check(fn(h, x.ctypes.data_as(ctypes.c_void_p), nq, k, D.ctypes.data_as(ctypes.c_void_p), I.ctypes.data_as(ctypes.c_void_p)))
         return D, I
 
+    def search_to_host(self, x, k: int):
+        """CUDA tensor in -> numpy out: the kernels store the [nq, k] results straight into page-locked host memory
+        (no device result tensors, no device->host copies); synchronises the current stream."""
+        import torch
+        k = int(k)
+        if self._g or not (_is_tensor(x) and x.is_cuda):
+            D, I = self.search(x, k)
+            return (D.cpu().numpy(), I.cpu().numpy()) if _is_tensor(D) else (D, I)
+        if x.dim() != 2 or x.shape[1] != self.d:
+            raise PrsError(_lib.EINVAL, f"search: expected [nq, {self.d}], got {tuple(x.shape)}")
+        x = x.contiguous()
+        nq = int(x.shape[0])
+        cache = self.__dict__.setdefault("_pinned_out", {})
+        buf = cache.get((nq, k))
+        if buf is None:
+            if len(cache) >= 8:
+                cache.clear()
+            buf = cache[(nq, k)] = (torch.empty((nq, k), dtype=torch.float32).pin_memory(), torch.empty((nq, k), dtype=torch.int64).pin_memory())
+        D, I = buf
+        stream = torch.cuda.current_stream(x.device)
+        check(self._L.prs_index_search_device(self._h, ctypes.c_void_p(x.data_ptr()), _torch_dtype_code(x), nq, k,
+                                              ctypes.c_void_p(D.data_ptr()), ctypes.c_void_p(I.data_ptr()), ctypes.c_void_p(stream.cuda_stream)))
+        stream.synchronize()
+        return D.numpy().copy(), I.numpy().copy()
+
     def search_into(self, q_ptr: int, nq: int, k: int, D_ptr: int, I_ptr: int) -> None:
         """Raw host-pointer search (pinned buffers in benchmarks): no allocation per call."""
         self._single_only("search_into")

@@ -171,6 +171,8 @@ class RetrievalSystem:
                 emb = emb[None, :]
             if emb.dtype not in (torch.float32, torch.float16, torch.bfloat16):
                 emb = emb.float()
+            if not want_device and hasattr(self.faiss_index, "search_to_host"):
+                return self.faiss_index.search_to_host(emb, k)      # results land in page-locked host memory, no D2H copies
             D, I = self.faiss_index.search(emb, k)
             return (D, I) if want_device else (D.cpu().numpy(), I.cpu().numpy())
         if hasattr(emb, "detach"):

@@ -518,6 +518,22 @@ def test_one_launch_search_equals_three_kernel_sequence(P):
     assert big.last_fused
 
 
+def test_search_to_host_equals_search(P):
+    """CUDA-tensor queries, results written by the kernels straight into page-locked host memory: same answers as the
+    tensor-out search on every path (one launch, clusters, wide k, the fp32 scan, a tiny index)."""
+    import torch
+    rng = np.random.default_rng(77)
+    for (n, d, nq, k, storage) in [(20000, 768, 64, 10, "fp16"), (9000, 384, 200, 5, "bf16"), (40000, 128, 3, 100, "fp16"),
+                                   (3000, 384, 2, 7, "fp32"), (125, 384, 1, 5, "fp32")]:
+        idx = P.FlatIndex(d, P.METRIC_L2, storage)
+        idx.add(rng.standard_normal((n, d)).astype(np.float32))
+        q = torch.from_numpy(rng.standard_normal((nq, d)).astype(np.float32)).cuda()
+        D, I = idx.search(q, k)
+        for _ in range(2):                                   # second call reuses the cached page-locked buffers
+            Dh, Ih = idx.search_to_host(q, k)
+            assert isinstance(Dh, np.ndarray) and np.array_equal(Ih, I.cpu().numpy()) and np.array_equal(Dh, D.cpu().numpy())
+
+
 def test_auto_path_selection(P):
     rng = np.random.default_rng(6)
     x = rng.standard_normal((2048, 256)).astype(np.float32)
