@@ -65,7 +65,7 @@ def parse():
                          "c4 = batch x k sweep on the 50M x 384 per-GPU share; 'none' skips them")
     ap.add_argument("--no-fuse", action="store_true", help="three-kernel search (prep, scan, merge) instead of the one-launch search (A/B)")
     ap.add_argument("--no-sweep", action="store_true")
-    ap.add_argument("--secondary-budget-s", type=float, default=420.0,
+    ap.add_argument("--secondary-budget-s", type=float, default=540.0,
                     help="seconds the measurements AFTER the headline (sweep, CPU baseline, extra configs) may take before the line is printed without them")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sweep-out", default="")
@@ -971,7 +971,7 @@ def _arm_watchdog(out, rank, budget_s):
 def main():
     a = parse()
     faulthandler.enable()
-    faulthandler.dump_traceback_later(600, exit=False)        # a run this long is stuck: leave the stacks on stderr
+    faulthandler.dump_traceback_later(900, exit=False)        # a run this long is stuck: leave the stacks on stderr
     if a.impl == "reference":
         run_reference(a)
     else:
