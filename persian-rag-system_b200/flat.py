@@ -211,7 +211,8 @@ class FlatIndex:
         D = np.empty((nq, k), dtype=np.float32)
         I = np.empty((nq, k), dtype=np.int64)
         fn, h = (self._L.prs_group_search_host, self._g) if self._g else (self._L.prs_index_search_host, self._h)
-        check(fn(h, x.ctypes.data_as(ctypes.c_void_p), nq, k, D.ctypes.data_as(ctypes.c_void_p), I.ctypes.data_as(ctypes.c_void_p)))
+        # (ndarray.ctypes.data_as costs 2.4 us per call; three of them are a tenth of a small-index search)
+        check(fn(h, ctypes.c_void_p(x.ctypes.data), nq, k, ctypes.c_void_p(D.ctypes.data), ctypes.c_void_p(I.ctypes.data)))
         return D, I
 
     def search_to_host(self, x, k: int):
