@@ -455,6 +455,7 @@ def run_b200(a):
         for s in range(a.steps):
             l2_flush(s)
             torch.cuda.synchronize()
+            barrier()                       # every rank starts the step together, like the device-timed steps do
             t0 = time.perf_counter()
             step_e2e(a.warmup + s)          # synchronous: returns with the results on the host
             e2e_ms += (time.perf_counter() - t0) * 1e3
