@@ -972,7 +972,7 @@ def _arm_watchdog(out, rank, budget_s):
 def main():
     a = parse()
     faulthandler.enable()
-    faulthandler.dump_traceback_later(900, exit=False)        # a run this long is stuck: leave the stacks on stderr
+    faulthandler.dump_traceback_later(240, repeat=True, exit=False)   # a default run takes about a minute: leave the stacks of a stuck one on stderr
     if a.impl == "reference":
         run_reference(a)
     else:
